@@ -1,0 +1,154 @@
+/* rmcl_b200.h — C-ABI of librmcl_b200.so: the B200 (sm_100a) kernels behind the RMCL
+ * contrastive-adversarial training step.
+ *
+ * The reference (stanFurrer/Robust-Multimodal-Contrastive-Learning) has no FFI of its own:
+ * the hot path is a chain of ATen expressions inside two Python functions.  Every entry point
+ * below replaces one such chain; the `replaces:` line cites it (paths relative to the
+ * reference root).  INTEGRATION.md shows the ctypes binding a reference maintainer adds.
+ *
+ * Conventions (all entry points)
+ *   - return value: RMCL_OK (0) or a negative rmcl_status; rmcl_last_error() gives the text of
+ *     the most recent failure on the calling thread.
+ *   - every pointer named *_dev / every tensor argument is DEVICE memory owned by the caller.
+ *     Nothing is allocated, freed, or retained; nothing synchronises the device or the host.
+ *     Work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default).
+ *   - there is no CPU path.  On a machine without an sm_100 device every launch fails with
+ *     RMCL_E_CUDA.
+ *   - thread-compatible: no global mutable state besides the per-thread error string.
+ */
+#ifndef RMCL_B200_H
+#define RMCL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  RMCL_OK = 0,
+  RMCL_E_BADARG = -1,          /* null pointer, non-positive size, K % B != 0 for enqueue, ... */
+  RMCL_E_ALIGN = -2,           /* pointer / stride alignment the kernel needs is not met       */
+  RMCL_E_UNSUPPORTED_DIM = -3, /* shape outside what the kernels are built for                 */
+  RMCL_E_CUDA = -4,            /* a CUDA runtime/driver call failed (see rmcl_last_error)      */
+  RMCL_E_WORKSPACE = -5        /* workspace smaller than rmcl_infonce_workspace_bytes()        */
+} rmcl_status;
+
+typedef enum { RMCL_F32 = 0, RMCL_BF16 = 1 } rmcl_dtype;
+
+typedef enum {
+  RMCL_PGD_REF_LINF = 0,  /* reference rule: delta += lr*g/max(|g|_inf,1e-8); clamp(+-eps) if eps>0 */
+  RMCL_PGD_SIGN_LINF = 1, /* delta += lr*sign(g); clamp(+-eps) if eps>0                             */
+  RMCL_PGD_L2 = 2         /* delta += lr*g/max(|g|_2,1e-8); project onto the eps-ball (L2)          */
+} rmcl_pgd_mode;
+
+/* InfoNCE code paths.  AUTO picks TCGEN05 when the shape/dtype allows it (bf16 queue,
+ * C in {64,128,256}, K % 8 == 0, 16-byte aligned queue) and SIMT otherwise.  Both are device
+ * kernels in this library; forcing TCGEN05 on an unsupported shape is RMCL_E_UNSUPPORTED_DIM. */
+typedef enum { RMCL_INFONCE_AUTO = 0, RMCL_INFONCE_SIMT = 1, RMCL_INFONCE_TCGEN05 = 2 } rmcl_infonce_path;
+
+/* flags for rmcl_infonce_fwd_bwd */
+#define RMCL_INFONCE_NORMALIZE_K 1u /* k is a raw projection: L2-normalise it too (objectives.py:265) */
+#define RMCL_INFONCE_NO_GRAD 2u     /* forward only (clean-query call, objectives.py:269-275)        */
+
+const char* rmcl_last_error(void);
+int rmcl_version(void);      /* 1000*major + minor */
+int rmcl_sm_count(void);     /* SMs of the current device, or a negative rmcl_status */
+
+/* ---------------------------------------------------------------------------------------------
+ * Momentum (EMA) update of the key encoder:  k <- k*m + q*(1-m)  over a list of tensor pairs.
+ * replaces: vilt/modules/objectives.py:219-224 (called x4 at 257-260) — 161 tensors,
+ *           ~483 elementwise launches; MoCo/MoCo_RMCL.py:65-72 (_momentum_update_key_encoder).
+ * Arithmetic is the reference's: round(round(k*mf) + round(q*omf)) in the tensor dtype with
+ * mf=(float)m and omf=(float)(1.0-m) (1.0-m evaluated in double, like Python), not an FMA.
+ *
+ * Planning is a host-only helper: it cuts the tensor list into chunks of at most chunk_elems
+ * elements so that one launch balances 161 very unequal tensors over all SMs.  The caller uploads
+ * the chunk table to the device once (parameter storage does not move between steps) and reuses it.
+ */
+typedef struct {
+  void* k;          /* device pointer into a key-encoder parameter   */
+  const void* q;    /* device pointer into the matching query param  */
+  uint64_t n;       /* elements in this chunk                         */
+} rmcl_ema_chunk;
+
+/* Returns the number of chunks needed (>=0) or a negative status.  If chunks_out is non-NULL it
+ * must have room for that many entries (call once with NULL to size it). */
+int64_t rmcl_ema_plan(const void* const* k_ptrs, const void* const* q_ptrs, const uint64_t* numels,
+                      int n_tensors, rmcl_dtype dtype, uint64_t chunk_elems, rmcl_ema_chunk* chunks_out);
+
+int rmcl_ema_multi(const rmcl_ema_chunk* chunks_dev, int64_t n_chunks, double m, rmcl_dtype dtype,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused InfoNCE forward + backward of queries against [key ; queue], logits never materialised.
+ * replaces: objectives.py:269-274 (clean), 326-334+351 (image-attacked), 289-297+314, 364-372+389;
+ *           attack/pgd_attack_vilt.py:147,152-158 (PGD inner loss); the autograd backward of each;
+ *           the queue.clone() at objectives.py:270.  MoCo/MoCo_RMCL.py:150-164.
+ *
+ *   q        [B,C]   raw projection-head output (normalised inside: q/max(|q|,1e-12))
+ *   k        [B,C]   key; already normalised unless RMCL_INFONCE_NORMALIZE_K
+ *   queue    [C,K]   row stride ldq elements (reference layout: K contiguous, vilt_module.py:92)
+ *   tau              temperature;  loss = loss_scale * mean_i( lse_i - pos_i )
+ *   outputs (any may be NULL except workspace):
+ *     loss          f32[1]    scaled mean loss
+ *     loss_per_row  f32[B]    lse_i - pos_i (unscaled)
+ *     lse           f32[B]    log-sum-exp of row i over the K+1 logits
+ *     pos           f32[B]    positive logit  q^.k^/tau
+ *     argmax        i64[B]    argmax over the K+1 logits (0 = the positive; objectives.py:275,336)
+ *     dq            f32[B,C]  d loss / d q  (through the normalisation)
+ *     dk            f32[B,C]  d loss / d k^ (the reference keeps k under no_grad; provided for
+ *                              symmetric / MoCo-v3 style callers)
+ *     k_hat_out     f32[B,C]  normalised key (what gets enqueued)
+ */
+size_t rmcl_infonce_workspace_bytes(int B, int C, int64_t K, rmcl_dtype queue_dtype, int path);
+
+int rmcl_infonce_fwd_bwd(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_dtype k_dtype,
+                         const void* queue, rmcl_dtype queue_dtype, int B, int C, int64_t K,
+                         int64_t ldq, float tau, float loss_scale, unsigned flags, int path,
+                         float* loss, float* loss_per_row, float* lse, float* pos, int64_t* argmax,
+                         float* dq, float* dk, float* k_hat_out, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Ring-buffer enqueue:  queue[:, ptr:ptr+B] = keys^T ;  ptr = (ptr + B) % K, all on the device.
+ * replaces: objectives.py:244-248 (int(ptr) D2H sync, strided slice-assign, host modulo, H2D
+ *           scalar write); MoCo/MoCo_RMCL.py:81-94.
+ *   queue [C,K] (row stride ldq), keys [B,C] contiguous, *ptr_dev int64 in [0,K).
+ * K % B != 0 is RMCL_E_BADARG (the reference's commented-out assert, objectives.py:245); with it
+ * the slice never wraps.  The "skip unless B == per_step_bs" rule (objectives.py:242-243) lives
+ * in the host wrapper.  While the kernel runs, the upper 32 bits of *ptr_dev are used as an
+ * arrival counter; they are zero again when it finishes.
+ */
+int rmcl_enqueue(void* queue, rmcl_dtype queue_dtype, const void* keys, rmcl_dtype keys_dtype,
+                 int64_t* ptr_dev, int B, int C, int64_t K, int64_t ldq, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * One PGD perturbation update on delta[B,N] given grad[B,N] (per-sample norms over N).
+ * replaces: attack/pgd_attack_vilt.py:162-173 (clone/float, inf-norm, clamp, scale, add, clamp:
+ *           7 kernels, 5 passes).  Works on pixels [B,3,H,W] or embeddings [B,L,768] viewed [B,N].
+ * REF_LINF in f32 is bit-identical to the reference: fadd(delta, fdiv(fmul(lr,g), d)).
+ *   norms_ws  f32[2*B] scratch (per-sample norms); delta is updated in place.
+ */
+int rmcl_pgd_step(void* delta, rmcl_dtype delta_dtype, const void* grad, rmcl_dtype grad_dtype,
+                  int B, int64_t N, float lr, float eps, int mode, float* norms_ws, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-buffer convenience used for the end-to-end measurement: one kernels-only RMCL step
+ * (EMA -> InfoNCE fwd+bwd -> enqueue) with q, k in HOST memory and loss/dq returned to HOST
+ * memory.  Parameters, queue and pointer stay resident on the device (they are model state).
+ * Copies are issued on `stream`; the call returns after the D2H copies completed.
+ */
+int rmcl_step_host(const rmcl_ema_chunk* chunks_dev, int64_t n_chunks, double m,
+                   const void* q_host, const void* k_host, rmcl_dtype qk_dtype,
+                   void* q_dev, void* k_dev,
+                   void* queue, rmcl_dtype queue_dtype, int64_t* ptr_dev, int B, int C, int64_t K,
+                   float tau, int path, float* loss_dev, float* dq_dev, float* k_hat_dev,
+                   float* loss_host, float* dq_host, void* workspace, size_t workspace_bytes,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RMCL_B200_H */

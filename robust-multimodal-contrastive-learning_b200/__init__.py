@@ -1,0 +1,16 @@
+"""rmcl_b200 — B200-native kernels for the RMCL contrastive-adversarial training step.
+
+Public surface (reference names):
+  compute_moco_contrastive, compute_pgd          vilt/modules/objectives.py:217-447, 160-188
+  PGDAttack, PGDAttack_moco                      attack/pgd_attack_vilt.py:7-175
+  MoCo, concat_all_gather                        MoCo/MoCo_RMCL.py
+  ops.{ema_multi_, infonce_fwd_bwd, infonce_loss, enqueue_, pgd_step_}   the kernels themselves
+"""
+from . import ops  # noqa: F401
+from .dist import concat_all_gather  # noqa: F401
+from .moco import MoCo  # noqa: F401
+from .objectives import (compute_moco_contrastive, compute_pgd, dequeue_and_enqueue,  # noqa: F401
+                         momentum_update_key_encoder)
+from .pgd_attack import PGDAttack, PGDAttack_moco  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,72 @@
+"""ctypes binding of librmcl_b200.so (include/rmcl_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, this
+raises.  Build it with ``python __graft_entry__.py build`` (or ``csrc/build.py``).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librmcl_b200.so")
+
+RMCL_F32, RMCL_BF16 = 0, 1
+PGD_MODES = {"ref_linf": 0, "sign_linf": 1, "l2": 2}
+INFONCE_PATHS = {"auto": 0, "simt": 1, "tcgen05": 2}
+FLAG_NORMALIZE_K, FLAG_NO_GRAD = 1, 2
+
+EXPORTS = (
+    "rmcl_last_error", "rmcl_version", "rmcl_sm_count", "rmcl_ema_plan", "rmcl_ema_multi",
+    "rmcl_infonce_workspace_bytes", "rmcl_infonce_fwd_bwd", "rmcl_enqueue", "rmcl_pgd_step", "rmcl_step_host",
+)
+
+
+class EmaChunk(C.Structure):
+    _fields_ = [("k", C.c_void_p), ("q", C.c_void_p), ("n", C.c_uint64)]
+
+
+class RmclError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            f"rmcl_b200: {LIB_PATH} is missing — the CUDA library has not been built and there is no "
+            "CPU fallback. Run `python __graft_entry__.py build`.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32, f64, u32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_uint, C.c_size_t
+    L.rmcl_last_error.restype = C.c_char_p
+    L.rmcl_last_error.argtypes = []
+    L.rmcl_version.restype = i32
+    L.rmcl_sm_count.restype = i32
+    L.rmcl_ema_plan.restype = i64
+    L.rmcl_ema_plan.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint64), i32, i32, C.c_uint64,
+                                C.POINTER(EmaChunk)]
+    L.rmcl_ema_multi.restype = i32
+    L.rmcl_ema_multi.argtypes = [vp, i64, f64, i32, vp]
+    L.rmcl_infonce_workspace_bytes.restype = sz
+    L.rmcl_infonce_workspace_bytes.argtypes = [i32, i32, i64, i32, i32]
+    L.rmcl_infonce_fwd_bwd.restype = i32
+    L.rmcl_infonce_fwd_bwd.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i64, i64, f32, f32, u32, i32,
+                                       vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.rmcl_enqueue.restype = i32
+    L.rmcl_enqueue.argtypes = [vp, i32, vp, i32, vp, i32, i32, i64, i64, vp]
+    L.rmcl_pgd_step.restype = i32
+    L.rmcl_pgd_step.argtypes = [vp, i32, vp, i32, i32, i64, f32, f32, i32, vp, vp]
+    L.rmcl_step_host.restype = i32
+    L.rmcl_step_host.argtypes = [vp, i64, f64, vp, vp, i32, vp, vp, vp, i32, vp, i32, i32, i64, f32, i32,
+                                 vp, vp, vp, vp, vp, vp, sz, vp]
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().rmcl_last_error().decode("utf-8", "replace")
+        raise RmclError(f"{what} failed (status {rc}): {msg}")

@@ -1,0 +1,88 @@
+// Shared helpers for the rmcl_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/rmcl_b200.h"
+
+namespace rmcl {
+
+// ---- per-thread error string -------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define RMCL_CHECK_ARG(cond, ...)          \
+  do {                                     \
+    if (!(cond)) {                         \
+      rmcl::set_error(__VA_ARGS__);        \
+      return RMCL_E_BADARG;                \
+    }                                      \
+  } while (0)
+
+#define RMCL_CUDA_OK(expr)                                                                  \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      rmcl::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return RMCL_E_CUDA;                                                                   \
+    }                                                                                       \
+  } while (0)
+
+#define RMCL_LAUNCH_OK(name)                                                     \
+  do {                                                                           \
+    cudaError_t _e = cudaGetLastError();                                         \
+    if (_e != cudaSuccess) {                                                     \
+      rmcl::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));  \
+      return RMCL_E_CUDA;                                                        \
+    }                                                                            \
+  } while (0)
+
+int sm_count();  // cached per device; <=0 on failure
+
+inline size_t dtype_size(int dt) { return dt == RMCL_BF16 ? 2 : 4; }
+inline bool dtype_ok(int dt) { return dt == RMCL_F32 || dt == RMCL_BF16; }
+
+// ---- element access ------------------------------------------------------------------------
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+// 128-bit streaming accesses (read-once / write-once data: bypass L1 allocation).
+__device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+// plain 128-bit load for data that is also written by this kernel (no .nc)
+__device__ __forceinline__ uint4 ld_u4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_u4(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace rmcl

@@ -1,0 +1,338 @@
+// K1 — fused InfoNCE forward/backward: host dispatch + the prep and finalize stages.
+//
+// Replaces, per call site (vilt/modules/objectives.py:269-274, 326-334+351;
+// attack/pgd_attack_vilt.py:147,152-158; MoCo/MoCo_RMCL.py:150-164) the eager chain
+//   F.normalize -> queue.clone() -> einsum(nc,nc->n) -> einsum(nc,ck->nk) -> cat -> /T ->
+//   CrossEntropyLoss(logits.float(), 0) -> autograd backward
+// without ever materialising the B x (K+1) logits.
+//
+//   prep      one CTA per row: q^ = q/max(|q|,1e-12) (and k^ when asked), positive logit.
+//   partial   split-K flash pass over the queue (infonce_simt.cu / infonce_tc.cu).
+//   finalize  one CTA per row: merge the splits with the positive, emit lse / loss / argmax,
+//             dq^ = (sum_j p_j queue_j + (p_pos-1) k^)/tau * loss_scale/B, then push it through
+//             the normalisation Jacobian: dq = (dq^ - q^ (q^.dq^)) / max(|q|,1e-12).
+//             The last row-CTA to finish reduces the per-row losses in index order (deterministic).
+//
+// bf16 mode (queue_dtype == bf16) mirrors the reference under autocast: q^ and k^ are rounded to
+// bf16 before the dot products, accumulation is fp32, the Jacobian uses the fp32 q^.
+#include "infonce.cuh"
+
+namespace rmcl {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int infonce_make_plan(int B, int C, long long K, int queue_dtype, int path, bool aligned_for_tc, InfoNcePlan* p) {
+  const int sms = sm_count();
+  if (sms <= 0) return RMCL_E_CUDA;
+  const bool tc_ok = aligned_for_tc && queue_dtype == RMCL_BF16 && (C == 64 || C == 128 || C == 256) && (K % 8 == 0);
+  if (path == RMCL_INFONCE_AUTO) path = tc_ok ? RMCL_INFONCE_TCGEN05 : RMCL_INFONCE_SIMT;
+  if (path == RMCL_INFONCE_TCGEN05 && !tc_ok) {
+    set_error("tcgen05 InfoNCE needs a 16B-aligned bf16 queue, C in {64,128,256}, K %% 8 == 0 (got C=%d K=%lld)", C, K);
+    return RMCL_E_UNSUPPORTED_DIM;
+  }
+  if (path == RMCL_INFONCE_SIMT && C > 1024) {
+    set_error("SIMT InfoNCE supports C <= 1024 (got %d)", C);
+    return RMCL_E_UNSUPPORTED_DIM;
+  }
+  p->path = path;
+  if (path == RMCL_INFONCE_SIMT) {
+    p->rows_per_cta = 16;
+    p->tile_cols = (C <= 512) ? 64 : 32;
+  } else {
+    p->rows_per_cta = 128;
+    p->tile_cols = 64;
+  }
+  p->row_blocks = (B + p->rows_per_cta - 1) / p->rows_per_cta;
+  p->b_pad = p->row_blocks * p->rows_per_cta;
+  const long long tiles = (K + p->tile_cols - 1) / p->tile_cols;
+  // SIMT: ~2 waves of CTAs; TC: one persistent CTA per SM
+  long long target = (path == RMCL_INFONCE_SIMT) ? 2ll * sms : sms;
+  long long splits = target / p->row_blocks;
+  if (splits < 1) splits = 1;
+  if (splits > tiles) splits = tiles;
+  const long long tiles_per_split = (tiles + splits - 1) / splits;
+  p->cols_per_split = tiles_per_split * p->tile_cols;
+  p->splits = (int)((K + p->cols_per_split - 1) / p->cols_per_split);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t S = (size_t)p->splits, Bs = (size_t)B;
+  p->off_qhat = take(Bs * C * 4);
+  p->off_khat = take(Bs * C * 4);
+  p->off_inv = take(Bs * 4);
+  p->off_pos2 = take(Bs * 4);
+  p->off_qhat_bf16 = take((size_t)p->b_pad * C * 2);
+  p->off_m = take(S * Bs * 4);
+  p->off_l = take(S * Bs * 4);
+  p->off_av = take(S * Bs * 4);
+  p->off_ai = take(S * Bs * 4);
+  p->off_o = take(S * Bs * C * 4);
+  p->off_rowloss = take(Bs * 4);
+  p->off_counter = take(256);
+  p->total = off;
+  return RMCL_OK;
+}
+
+__device__ __forceinline__ float round_if(float x, bool to_bf16) {
+  return to_bf16 ? __bfloat162float(__float2bfloat16_rn(x)) : x;
+}
+
+__device__ __forceinline__ float block_sum_128(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return red[0] + red[1] + red[2] + red[3];
+}
+
+// ------------------------------------------------------------------------------------ prep
+template <typename TQ, typename TKK>
+__global__ void __launch_bounds__(128) infonce_prep_kernel(const TQ* __restrict__ q, const TKK* __restrict__ k, int B,
+                                                           int C, float scale2, bool normalize_k, bool bf16_mode,
+                                                           float* __restrict__ q_hat, float* __restrict__ k_hat,
+                                                           float* __restrict__ k_hat_out, float* __restrict__ inv_norm,
+                                                           float* __restrict__ pos2,
+                                                           __nv_bfloat16* __restrict__ q_hat_bf16, int b_pad,
+                                                           unsigned int* __restrict__ counter) {
+  __shared__ float red[4];
+  const int row = blockIdx.x;
+  if (row == 0 && threadIdx.x == 0) *counter = 0u;
+  if (row >= B) {  // padding rows of the bf16 operand (TMA reads whole 128-row boxes)
+    for (int c = threadIdx.x; c < C; c += 128) q_hat_bf16[(size_t)row * C + c] = __float2bfloat16_rn(0.f);
+    return;
+  }
+  const TQ* qr = q + (size_t)row * C;
+  const TKK* kr = k + (size_t)row * C;
+  float sq = 0.f, sk = 0.f;
+  for (int c = threadIdx.x; c < C; c += 128) {
+    const float a = to_f32(qr[c]), b = to_f32(kr[c]);
+    sq = fmaf(a, a, sq);
+    sk = fmaf(b, b, sk);
+  }
+  sq = block_sum_128(sq, red);
+  sk = block_sum_128(sk, red);
+  const float qn = fmaxf(sqrtf(sq), 1e-12f);
+  const float kn = normalize_k ? fmaxf(sqrtf(sk), 1e-12f) : 1.f;
+  float dot = 0.f;
+  for (int c = threadIdx.x; c < C; c += 128) {
+    const float qh = __fdiv_rn(to_f32(qr[c]), qn);
+    const float kh = normalize_k ? __fdiv_rn(to_f32(kr[c]), kn) : to_f32(kr[c]);
+    q_hat[(size_t)row * C + c] = qh;
+    k_hat[(size_t)row * C + c] = kh;
+    if (k_hat_out) k_hat_out[(size_t)row * C + c] = kh;
+    if (q_hat_bf16) q_hat_bf16[(size_t)row * C + c] = __float2bfloat16_rn(qh);
+    dot = fmaf(round_if(qh, bf16_mode), round_if(kh, bf16_mode), dot);
+  }
+  dot = block_sum_128(dot, red);
+  if (threadIdx.x == 0) {
+    inv_norm[row] = __fdiv_rn(1.f, qn);
+    pos2[row] = dot * scale2;
+  }
+}
+
+// -------------------------------------------------------------------------------- finalize
+__global__ void __launch_bounds__(256) infonce_finalize_kernel(
+    int B, int C, int splits, float inv_tau, float grad_scale /* loss_scale / B */, float loss_scale, bool bf16_mode,
+    bool want_grad, const float* __restrict__ q_hat, const float* __restrict__ k_hat, const float* __restrict__ inv_norm,
+    const float* __restrict__ pos2, const float* __restrict__ pm, const float* __restrict__ pl,
+    const float* __restrict__ pav, const int* __restrict__ pai, const float* __restrict__ po,
+    float* __restrict__ row_loss, unsigned int* __restrict__ counter, float* __restrict__ loss,
+    float* __restrict__ loss_per_row, float* __restrict__ lse_out, float* __restrict__ pos_out,
+    long long* __restrict__ argmax_out, float* __restrict__ dq, float* __restrict__ dk) {
+  extern __shared__ float sw[];  // [splits] merge weights
+  __shared__ float red[8];
+  __shared__ float s_stats[4];   // 0: scale applied to O  1: p_pos - 1
+  __shared__ bool s_last;
+  const int row = blockIdx.x;
+  const int tid = threadIdx.x;
+
+  if (tid < 32) {
+    // merge the split statistics (one warp; splits is O(100))
+    float mmax = -INFINITY;
+    for (int s = tid; s < splits; s += 32) mmax = fmaxf(mmax, pm[(size_t)s * B + row]);
+    mmax = warp_max(mmax);
+    float lsum = 0.f;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int s = tid; s < splits; s += 32) {
+      const float ms = pm[(size_t)s * B + row];
+      const float w = (ms == -INFINITY) ? 0.f : exp2f(ms - mmax);
+      sw[s] = w;
+      lsum = fmaf(pl[(size_t)s * B + row], w, lsum);
+      const float v = pav[(size_t)s * B + row];
+      const int i = pai[(size_t)s * B + row];
+      if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+    }
+    lsum = warp_sum(lsum);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (tid == 0) {
+      const float p2 = pos2[row];
+      const float M = fmaxf(mmax, p2);
+      const float wneg = exp2f(mmax - M), wpos = exp2f(p2 - M);
+      const float L = fmaf(lsum, wneg, wpos);
+      const float lse = (M + log2f(L)) * kLn2;
+      const float pos = p2 * kLn2;
+      const float lrow = lse - pos;
+      row_loss[row] = lrow;
+      if (loss_per_row) loss_per_row[row] = lrow;
+      if (lse_out) lse_out[row] = lse;
+      if (pos_out) pos_out[row] = pos;
+      if (argmax_out) argmax_out[row] = (p2 >= bv) ? 0ll : (long long)bi + 1;
+      s_stats[0] = wneg / L;
+      s_stats[1] = wpos / L - 1.f;
+    }
+  }
+  __syncthreads();
+
+  if (want_grad) {
+    const float o_scale = s_stats[0], pm1 = s_stats[1];
+    const float gs = grad_scale * inv_tau;
+    // dq^ for the columns this thread owns (C <= 1024 -> at most 4)
+    float dqh[4], qh[4];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = tid + 256 * i;
+      dqh[i] = 0.f;
+      qh[i] = 0.f;
+      if (c < C) {
+        float acc = 0.f;
+        for (int s = 0; s < splits; ++s) acc = fmaf(po[((size_t)s * B + row) * C + c], sw[s], acc);
+        const float kh = round_if(k_hat[(size_t)row * C + c], bf16_mode);
+        qh[i] = q_hat[(size_t)row * C + c];
+        dqh[i] = gs * fmaf(acc, o_scale, pm1 * kh);
+        dot = fmaf(qh[i], dqh[i], dot);
+        if (dk) dk[(size_t)row * C + c] = gs * pm1 * round_if(qh[i], bf16_mode);
+      }
+    }
+    dot = warp_sum(dot);
+    if ((tid & 31) == 0) red[tid >> 5] = dot;
+    __syncthreads();
+    dot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) dot += red[w];
+    const float inv = inv_norm[row];
+    if (dq) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = tid + 256 * i;
+        if (c < C) dq[(size_t)row * C + c] = (dqh[i] - qh[i] * dot) * inv;
+      }
+    }
+  }
+
+  // deterministic loss reduction by the last row-CTA
+  if (loss) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(counter, 1u) == (unsigned)B - 1u);
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      float acc = 0.f;
+      for (int r = tid; r < B; r += 256) acc += __ldcg(row_loss + r);
+      // fixed-shape tree: warp shuffle then 8 partials in order
+      acc = warp_sum(acc);
+      __syncthreads();
+      if ((tid & 31) == 0) red[tid >> 5] = acc;
+      __syncthreads();
+      if (tid == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        *loss = t * (loss_scale / (float)B);
+      }
+    }
+  }
+}
+
+template <typename TQ, typename TKK>
+static int launch_prep(const void* q, const void* k, int B, int C, float scale2, bool nk, bool bf16_mode, char* ws,
+                       const InfoNcePlan& p, float* k_hat_out, bool want_bf16, cudaStream_t s) {
+  const int rows = want_bf16 ? p.b_pad : B;
+  infonce_prep_kernel<TQ, TKK><<<rows, 128, 0, s>>>(
+      (const TQ*)q, (const TKK*)k, B, C, scale2, nk, bf16_mode, (float*)(ws + p.off_qhat), (float*)(ws + p.off_khat),
+      k_hat_out, (float*)(ws + p.off_inv), (float*)(ws + p.off_pos2),
+      want_bf16 ? (__nv_bfloat16*)(ws + p.off_qhat_bf16) : nullptr, p.b_pad, (unsigned int*)(ws + p.off_counter));
+  RMCL_LAUNCH_OK("infonce_prep_kernel");
+  return RMCL_OK;
+}
+
+}  // namespace rmcl
+
+using namespace rmcl;
+
+static bool tc_alignment_ok(const void* queue, int64_t ldq) {
+  return (reinterpret_cast<uintptr_t>(queue) & 15u) == 0 && (ldq % 8 == 0);
+}
+
+extern "C" size_t rmcl_infonce_workspace_bytes(int B, int C, int64_t K, rmcl_dtype queue_dtype, int path) {
+  if (B <= 0 || C <= 0 || K <= 0) return 0;
+  // size for whichever path needs more so that AUTO can pick either at call time
+  size_t best = 0;
+  for (int pth : {RMCL_INFONCE_SIMT, RMCL_INFONCE_TCGEN05}) {
+    if (path != RMCL_INFONCE_AUTO && path != pth) continue;
+    InfoNcePlan p;
+    if (infonce_make_plan(B, C, K, queue_dtype, pth, true, &p) == RMCL_OK && p.total > best) best = p.total;
+  }
+  return best;
+}
+
+extern "C" int rmcl_infonce_fwd_bwd(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_dtype k_dtype,
+                                    const void* queue, rmcl_dtype queue_dtype, int B, int C, int64_t K, int64_t ldq,
+                                    float tau, float loss_scale, unsigned flags, int path, float* loss,
+                                    float* loss_per_row, float* lse, float* pos, int64_t* argmax, float* dq, float* dk,
+                                    float* k_hat_out, void* workspace, size_t workspace_bytes, void* stream) {
+  RMCL_CHECK_ARG(q && k && queue && workspace, "rmcl_infonce_fwd_bwd: null pointer");
+  RMCL_CHECK_ARG(B > 0 && C > 0 && K > 0 && K < (1ll << 31) && ldq >= K, "rmcl_infonce_fwd_bwd: bad sizes B=%d C=%d K=%lld ldq=%lld",
+                 B, C, (long long)K, (long long)ldq);
+  RMCL_CHECK_ARG(tau > 0.f, "rmcl_infonce_fwd_bwd: temperature must be > 0");
+  RMCL_CHECK_ARG(dtype_ok(q_dtype) && dtype_ok(k_dtype) && dtype_ok(queue_dtype), "rmcl_infonce_fwd_bwd: bad dtype");
+  RMCL_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "rmcl_infonce_fwd_bwd: workspace must be 256B aligned");
+  InfoNcePlan p;
+  int rc = infonce_make_plan(B, C, K, queue_dtype, path, tc_alignment_ok(queue, ldq), &p);
+  if (rc != RMCL_OK) return rc;
+  if (workspace_bytes < p.total) {
+    set_error("rmcl_infonce_fwd_bwd: workspace %zu < required %zu", workspace_bytes, p.total);
+    return RMCL_E_WORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  const float scale2 = kLog2e / tau;
+  const bool bf16_mode = (queue_dtype == RMCL_BF16);
+  const bool nk = (flags & RMCL_INFONCE_NORMALIZE_K) != 0;
+  const bool want_grad = (flags & RMCL_INFONCE_NO_GRAD) == 0 && (dq || dk);
+  const bool tc = (p.path == RMCL_INFONCE_TCGEN05);
+  using bf16 = __nv_bfloat16;
+  if (q_dtype == RMCL_F32 && k_dtype == RMCL_F32)
+    rc = launch_prep<float, float>(q, k, B, C, scale2, nk, bf16_mode, ws, p, k_hat_out, tc, s);
+  else if (q_dtype == RMCL_F32)
+    rc = launch_prep<float, bf16>(q, k, B, C, scale2, nk, bf16_mode, ws, p, k_hat_out, tc, s);
+  else if (k_dtype == RMCL_F32)
+    rc = launch_prep<bf16, float>(q, k, B, C, scale2, nk, bf16_mode, ws, p, k_hat_out, tc, s);
+  else
+    rc = launch_prep<bf16, bf16>(q, k, B, C, scale2, nk, bf16_mode, ws, p, k_hat_out, tc, s);
+  if (rc != RMCL_OK) return rc;
+
+  InfoNcePartials parts{(float*)(ws + p.off_m), (float*)(ws + p.off_l), (float*)(ws + p.off_av), (int*)(ws + p.off_ai),
+                        (float*)(ws + p.off_o)};
+  if (tc)
+    rc = infonce_tc_launch((const bf16*)(ws + p.off_qhat_bf16), queue, B, C, K, ldq, scale2, p, parts, s);
+  else
+    rc = infonce_simt_launch((const float*)(ws + p.off_qhat), queue, queue_dtype, B, C, K, ldq, scale2, p, parts, s);
+  if (rc != RMCL_OK) return rc;
+
+  infonce_finalize_kernel<<<B, 256, p.splits * sizeof(float), s>>>(
+      B, C, p.splits, 1.f / tau, loss_scale / (float)B, loss_scale, bf16_mode, want_grad, (const float*)(ws + p.off_qhat),
+      (const float*)(ws + p.off_khat), (const float*)(ws + p.off_inv), (const float*)(ws + p.off_pos2), parts.m, parts.l,
+      parts.av, parts.ai, parts.o, (float*)(ws + p.off_rowloss), (unsigned int*)(ws + p.off_counter), loss, loss_per_row,
+      lse, pos, reinterpret_cast<long long*>(argmax), dq, dk);
+  RMCL_LAUNCH_OK("infonce_finalize_kernel");
+  return RMCL_OK;
+}

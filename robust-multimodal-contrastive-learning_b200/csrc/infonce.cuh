@@ -1,0 +1,50 @@
+// Internal interface between the InfoNCE stages (prep -> partial -> finalize).
+//
+// The fused InfoNCE is a split-K "flash" computation over the queue axis.  Every CTA of the
+// partial stage owns (a block of rows) x (a contiguous range of queue columns) and emits, per row,
+//     m  = max_j s_j                (s_j = q^.queue_j * log2(e)/tau, i.e. logits in log2 units)
+//     l  = sum_j 2^(s_j - m)
+//     O  = sum_j 2^(s_j - m) * queue_j          [C]
+//     (av, ai) = (max value, first index attaining it)   for the row argmax
+// The finalize stage merges the splits and the positive logit into lse / loss / dq / dk.
+// Two partial-stage implementations write this same format:
+//   infonce_simt.cu  — fp32 CUDA-core kernel, any dtype/shape (fp32 parity path, C<=1024)
+//   infonce_tc.cu    — tcgen05/TMEM/TMA kernel for bf16 queues (C in {64,128,256})
+#pragma once
+#include "common.cuh"
+
+namespace rmcl {
+
+struct InfoNcePlan {
+  int path;             // RMCL_INFONCE_SIMT / RMCL_INFONCE_TCGEN05 (never AUTO)
+  int splits;           // number of queue-axis splits
+  long long cols_per_split;
+  int rows_per_cta;     // 16 (simt) / 128 (tc)
+  int row_blocks;
+  int tile_cols;        // queue columns per inner tile
+  int b_pad;            // B rounded up to rows_per_cta
+  // workspace carve-up (byte offsets)
+  size_t off_qhat, off_khat, off_inv, off_pos2, off_qhat_bf16, off_m, off_l, off_av, off_ai, off_o, off_rowloss,
+      off_counter, total;
+};
+
+// Fills plan; returns RMCL_OK or an error (unsupported shape for a forced path).
+int infonce_make_plan(int B, int C, long long K, int queue_dtype, int path, bool aligned_for_tc, InfoNcePlan* plan);
+
+struct InfoNcePartials {
+  float* m;         // [splits][B]
+  float* l;         // [splits][B]
+  float* av;        // [splits][B]
+  int* ai;          // [splits][B]
+  float* o;         // [splits][B][C]
+};
+
+// partial stages
+int infonce_simt_launch(const float* q_hat, const void* queue, int queue_dtype, int B, int C, long long K,
+                        long long ldq, float scale2, const InfoNcePlan& plan, InfoNcePartials out, cudaStream_t s);
+int infonce_tc_launch(const __nv_bfloat16* q_hat_bf16, const void* queue, int B, int C, long long K, long long ldq,
+                      float scale2, const InfoNcePlan& plan, InfoNcePartials out, cudaStream_t s);
+bool infonce_tc_supported(int C, long long K, long long ldq, const void* queue, int queue_dtype);
+size_t infonce_tc_smem_bytes(int C);
+
+}  // namespace rmcl

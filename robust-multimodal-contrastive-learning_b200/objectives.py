@@ -1,0 +1,190 @@
+"""``compute_moco_contrastive`` / ``compute_pgd`` with the reference's signatures, on fused kernels.
+
+Drop-in for vilt/modules/objectives.py:160-188 and 217-447: same arguments
+(``pl_module``, ``batch``), same attributes read from ``pl_module``, same return
+keys (exactly one key containing "loss": ``moco_loss``) and the same ``pl_module.log`` names, so
+``vilt.modules.objectives.compute_moco_contrastive = rmcl_b200.compute_moco_contrastive`` is the
+whole integration.  The backbone forwards (``infer``/``infer_k``/heads) stay on
+torch; what changes is everything between them:
+
+  EMA        161-tensor python loop            -> ops.ema_multi_   (1 launch)
+  InfoNCE    normalize/clone/einsum/cat/CE     -> ops.infonce_*    (logits never materialised)
+  PGD        7-kernel update, deepcopy         -> pgd_attack.PGDAttack_moco / ops.pgd_step_
+  enqueue    int(ptr) sync + strided copy      -> ops.enqueue_     (pointer stays on device)
+  gather     list all_gather + cat             -> dist.concat_all_gather
+"""
+from copy import deepcopy
+
+import torch
+import torch.nn.functional as F
+
+from . import dist as rdist
+from . import ops
+
+_KEY_QUERY_LAYERS = (  # objectives.py:257-260, in this order
+    ("text_embeddings", "k_text_embeddings"),
+    ("token_type_embeddings", "k_token_type_embeddings"),
+    ("transformer", "k_transformer"),
+    ("moco_head", "k_moco_head"),
+)
+
+
+def momentum_update_key_encoder(pl_module):
+    """objectives.py:219-224 + 257-260 as one launch; the chunk table is cached on the module."""
+    plan = pl_module.__dict__.get("_rmcl_ema_plan")
+    if plan is None:
+        pk, pq = [], []
+        for qn, kn in _KEY_QUERY_LAYERS:
+            q_layer, k_layer = getattr(pl_module, qn), getattr(pl_module, kn)
+            for param_q, param_k in zip(q_layer.parameters(), k_layer.parameters()):
+                pq.append(param_q)
+                pk.append(param_k)
+        plan = ops.EmaPlan(pk, pq)
+        pl_module.__dict__["_rmcl_ema_plan"] = plan
+    ops.ema_multi_(plan, pl_module.momentum)
+
+
+def dequeue_and_enqueue(pl_module, keys):
+    """objectives.py:238-248 — gather, skip on a short batch, ring-buffer write, pointer advance."""
+    keys = rdist.concat_all_gather(keys)
+    if not rdist.gathered_batch_matches(pl_module.per_step_bs, keys.shape[0]):
+        return
+    ops.enqueue_(pl_module.proj_queue, keys, pl_module.proj_queue_ptr)
+
+
+def compute_pgd(pl_module, batch, loss_name, k_modality=None):
+    """objectives.py:160-188 (moco branch): run the attacker, add delta to the image, log |delta|."""
+    img_delta = pl_module.pgd_attacker.pgd_attack(pl_module, batch, k_modality=k_modality)
+    if getattr(pl_module.pgd_attacker, "space", "pixel") == "embed":
+        batch["image_embeds_delta"] = img_delta
+    else:
+        # NB the attacker already left img_init+delta_{n-1} in batch; the reference
+        # adds delta_n on top and so do we.
+        batch["image"][0] = batch["image"][0] + img_delta
+    phase = "train" if pl_module.training else "val"
+    pl_module.log(f"{loss_name}_attack/{phase}/delta", torch.linalg.norm(img_delta, dim=1).mean())
+    return batch
+
+
+@torch.no_grad()
+def queue_diagnostics(q_hat, k_hat, queue, cosine, chunk=8192):
+    """pos/neg L2, cosine and dot means of objectives.py:337-349 without the per-sample Python
+    loop: dot and cosine collapse to one [C] reduction of the queue; the L2 term is chunked."""
+    qf = queue.float()
+    out = {
+        "pos_dist": torch.linalg.norm(q_hat - k_hat, dim=1).mean(),
+        "pos_cosine": cosine(q_hat, k_hat).mean(),
+        "pos_dot": torch.sum(q_hat * k_hat, dim=1).mean(),
+    }
+    col_norm = qf.norm(dim=0)                                         # [K]
+    out["neg_dot"] = (q_hat @ qf.mean(dim=1)).mean()
+    qn = q_hat.norm(dim=1).clamp_min(1e-6)
+    out["neg_cosine"] = ((q_hat / qn[:, None]) @ (qf / col_norm.clamp_min(1e-6)).mean(dim=1)).mean()
+    q2 = (q_hat * q_hat).sum(1, keepdim=True)
+    acc = torch.zeros((), device=q_hat.device)
+    for s in range(0, qf.shape[1], chunk):
+        blk = qf[:, s:s + chunk]
+        d2 = q2 - 2.0 * (q_hat @ blk) + (col_norm[s:s + chunk] ** 2)[None, :]
+        acc = acc + d2.clamp_min(0).sqrt().sum()
+    out["neg_dist"] = acc / (q_hat.shape[0] * qf.shape[1])
+    return out
+
+
+def _attacked_view(pl_module, batch, k_hat, prediction_original, suffix, rate_name, ret, diagnostics):
+    """One attacked/augmented view: forward, fused InfoNCE loss (+argmax), diagnostics."""
+    if "image_embeds_delta" in batch:  # embedding-space PGD (extension)
+        tr = pl_module.transformer
+        emb, masks, _, _ = tr.visual_embed(batch["image"][0], max_image_len=pl_module.hparams.config["max_image_len"],
+                                           mask_it=False)
+        infer = pl_module.infer(batch, mask_text=False, mask_image=False,
+                                image_embeds=emb + batch["image_embeds_delta"], image_masks=masks)
+    else:
+        infer = pl_module.infer(batch, mask_text=False, mask_image=False)
+    q_raw = pl_module.moco_head(infer["cls_feats"])
+    loss, argmax = ops.infonce_loss(q_raw, k_hat, pl_module.proj_queue, pl_module.temperature,
+                                    getattr(pl_module, "infonce_path", "auto"))
+    if pl_module.training:
+        pl_module.log(f"moco_attack/{rate_name}_success_rate",
+                      (~(argmax == prediction_original)).sum() / argmax.shape[0])
+    if diagnostics:
+        d = queue_diagnostics(F.normalize(q_raw.detach().float(), dim=1), k_hat, pl_module.proj_queue, pl_module.cosine)
+        for name, v in d.items():
+            ret[f"{name}_attacked_{suffix}"] = v
+    pl_module.log(f"moco_loss/attacked_{suffix}_loss", loss)
+    return loss
+
+
+def compute_moco_contrastive(pl_module, batch, diagnostics=True):
+    ret = {}
+    phase = "train" if pl_module.training else "val"
+    loss, loss_num = 0, 0
+
+    momentum_update_key_encoder(pl_module)
+
+    with torch.no_grad():
+        infer_k = pl_module.infer_k(batch, mask_text=False, mask_image=False)
+        k_raw = pl_module.k_moco_head(infer_k["cls_feats"])
+
+    # clean query: only the row argmax is used (objectives.py:267-275); the same launch
+    # normalises the key, so k^ comes out of it for PGD, the losses and the enqueue.
+    infer = pl_module.infer(batch, mask_text=False, mask_image=False)
+    q_clean = pl_module.moco_head(infer["cls_feats"])
+    clean = ops.infonce_fwd_bwd(q_clean.float(), k_raw.float(), pl_module.proj_queue, pl_module.temperature,
+                                normalize_k=True, need_grad=False, path=getattr(pl_module, "infonce_path", "auto"),
+                                want=("argmax", "k_hat"))
+    prediction_original, k = clean["argmax"], clean["k_hat"]
+
+    attacked_words = None
+    if pl_module.text_view:
+        if pl_module.augmentation:
+            augmented_batch = pl_module.text_augmentation_fn(pl_module, deepcopy(batch))
+        else:
+            augmented_batch = compute_geometric(pl_module, deepcopy(batch), "moco", k_modality=k)
+            attacked_words = {n: deepcopy(augmented_batch[n]) for n in ("text", "text_ids", "text_masks")}
+        loss = loss + _attacked_view(pl_module, augmented_batch, k, prediction_original, "txt", "Geom", ret, diagnostics)
+        loss_num += 1
+
+    if pl_module.image_view:
+        if pl_module.augmentation:
+            augmented_batch = pl_module.image_augmentation_fn(pl_module, deepcopy(batch))
+        else:
+            augmented_batch = compute_pgd(pl_module, deepcopy(batch), "moco", k_modality=k)
+        loss = loss + _attacked_view(pl_module, augmented_batch, k, prediction_original, "img", "PGD", ret, diagnostics)
+        loss_num += 1
+
+    if pl_module.image_view and pl_module.text_view and not pl_module.augmentation:
+        for n in ("text", "text_ids", "text_masks"):
+            augmented_batch[n] = attacked_words[n]
+        loss = loss + _attacked_view(pl_module, augmented_batch, k, prediction_original, "both", "Both", ret, diagnostics)
+        loss_num += 1
+
+    if pl_module.training:
+        dequeue_and_enqueue(pl_module, k)
+
+    ret["moco_loss"] = loss / loss_num
+    metric = getattr(pl_module, f"{phase}_moco_loss")(ret["moco_loss"])
+    pl_module.log(f"moco_loss/step/{phase}", metric)
+    if diagnostics:
+        for view, on in (("img", pl_module.image_view), ("txt", pl_module.text_view),
+                         ("both", pl_module.image_view and pl_module.text_view and not pl_module.augmentation)):
+            if not on:
+                continue
+            for tag, key in (("L2", "dist"), ("Cosine", "cosine"), ("Dot", "dot")):
+                pos, neg = ret[f"pos_{key}_attacked_{view}"], ret[f"neg_{key}_attacked_{view}"]
+                pl_module.log(f"moco_dist_{phase}_{tag}/Pos_attacked_{view}", pos)
+                pl_module.log(f"moco_dist_{phase}_{tag}/Neg_attacked_{view}", neg)
+                pl_module.log(f"moco_dist_{phase}_{tag}/Neg-Pos_attacked_{view}", neg - pos)
+    return ret
+
+
+def compute_geometric(pl_module, batch, loss_name, k_modality=None):
+    """objectives.py:190-215: delegate to the module's greedy text attacker (out of scope here —
+    a CPU tokenizer loop — but its call site is kept so ``text_view=True`` modules still run)."""
+    attack_words = pl_module.greedy_attacker.adv_attack_samples(pl_module, batch, k_modality)
+    batch["text"] = attack_words["text"]
+    batch["text_ids"] = attack_words["txt_input_ids"]
+    batch["text_masks"] = attack_words["text_masks"]
+    phase = "train" if pl_module.training else "val"
+    pl_module.log(f"{loss_name}_attack/{phase}/num_changes", attack_words["num_changes"])
+    pl_module.log(f"{loss_name}_attack/{phase}/change_rate", attack_words["change_rate"])
+    return batch

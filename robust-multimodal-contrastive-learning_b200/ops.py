@@ -1,0 +1,212 @@
+"""Device-tensor wrappers over the C-ABI (include/rmcl_b200.h).
+
+torch is used for what the task allows it for — device memory, streams and autograd plumbing.
+Every function here launches hand-written sm_100a kernels from librmcl_b200.so on the current
+CUDA stream; none has a CPU or eager-torch fallback (CPU tensors raise).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+_DT = {torch.float32: _lib.RMCL_F32, torch.bfloat16: _lib.RMCL_BF16}
+
+
+def _dt(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"rmcl_b200 supports float32 and bfloat16 tensors, got {t.dtype}") from None
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("rmcl_b200 ops run on CUDA tensors only (there is no CPU path)")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+# ------------------------------------------------------------------------------------ EMA
+class EmaPlan:
+    """Chunk table for the multi-tensor momentum update (built once, reused every step).
+
+    Mirrors the pairing of vilt/modules/objectives.py:222 —
+    ``zip(q_layer.parameters(), k_layer.parameters())`` — for any number of layers.
+    """
+
+    def __init__(self, params_k, params_q, chunk_elems=16384):
+        params_k, params_q = list(params_k), list(params_q)
+        if len(params_k) != len(params_q):
+            raise ValueError("key/query parameter lists differ in length")
+        self.groups = []  # (dtype_enum, device_table, n_chunks, keepalive)
+        self.n_params = 0
+        by_dtype = {}
+        for pk, pq in zip(params_k, params_q):
+            pk, pq = getattr(pk, "data", pk), getattr(pq, "data", pq)
+            _need_cuda(pk, pq)
+            if pk.shape != pq.shape or pk.dtype != pq.dtype:
+                raise ValueError(f"parameter pair mismatch: {tuple(pk.shape)}/{pk.dtype} vs {tuple(pq.shape)}/{pq.dtype}")
+            if not (pk.is_contiguous() and pq.is_contiguous()):
+                raise ValueError("EMA expects contiguous parameters")
+            by_dtype.setdefault(pk.dtype, []).append((pk, pq))
+            self.n_params += pk.numel()
+        L = _lib.lib()
+        for dtype, pairs in by_dtype.items():
+            n = len(pairs)
+            kp = (C.c_void_p * n)(*[p[0].data_ptr() for p in pairs])
+            qp = (C.c_void_p * n)(*[p[1].data_ptr() for p in pairs])
+            ne = (C.c_uint64 * n)(*[p[0].numel() for p in pairs])
+            dt = _DT[dtype]
+            cnt = L.rmcl_ema_plan(kp, qp, ne, n, dt, chunk_elems, None)
+            if cnt < 0:
+                check(int(cnt), "rmcl_ema_plan")
+            host = (_lib.EmaChunk * max(cnt, 1))()
+            cnt2 = L.rmcl_ema_plan(kp, qp, ne, n, dt, chunk_elems, host)
+            assert cnt2 == cnt
+            raw = torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8)[: cnt * C.sizeof(_lib.EmaChunk)]
+            table = raw.to(pairs[0][0].device)
+            self.groups.append((dt, table, int(cnt), pairs))
+
+    @property
+    def n_chunks(self):
+        return sum(g[2] for g in self.groups)
+
+
+def ema_multi_(plan, m):
+    """k <- k*m + q*(1-m) for every pair in the plan, one launch per dtype group."""
+    L = _lib.lib()
+    for dt, table, cnt, _ in plan.groups:
+        check(L.rmcl_ema_multi(_p(table), cnt, float(m), dt, _stream()), "rmcl_ema_multi")
+
+
+# -------------------------------------------------------------------------------- InfoNCE
+_ws_cache = {}
+
+
+def _workspace(B, Cdim, K, qdt, path, device):
+    key = (B, Cdim, K, qdt, path, device)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        nbytes = _lib.lib().rmcl_infonce_workspace_bytes(B, Cdim, K, qdt, path)
+        if nbytes == 0:
+            check(-3, "rmcl_infonce_workspace_bytes")
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    off = (-ws.data_ptr()) % 256
+    return ws, off
+
+
+def infonce_fwd_bwd(q, k, queue, temperature, *, loss_scale=1.0, normalize_k=False, need_grad=True,
+                    path="auto", want=("loss", "loss_per_row", "lse", "pos", "argmax", "dq", "dk", "k_hat")):
+    """Fused InfoNCE of raw projections ``q`` [B,C] against [``k`` ; ``queue`` [C,K]].
+
+    Returns a dict with the requested outputs (see include/rmcl_b200.h).  ``loss`` is
+    ``loss_scale * mean_i(lse_i - pos_i)`` — CrossEntropyLoss against label 0
+    (vilt/modules/objectives.py:333-334,351).
+    """
+    _need_cuda(q, k, queue)
+    if q.dim() != 2 or k.shape != q.shape or queue.dim() != 2 or queue.shape[0] != q.shape[1]:
+        raise ValueError(f"shape mismatch: q {tuple(q.shape)} k {tuple(k.shape)} queue {tuple(queue.shape)}")
+    if queue.stride(1) != 1:
+        raise ValueError("queue must be [C,K] with K contiguous (reference layout)")
+    q, k = q.detach().contiguous(), k.detach().contiguous()
+    B, Cd = q.shape
+    K, ldq = queue.shape[1], queue.stride(0)
+    pth = _lib.INFONCE_PATHS[path]
+    ws, off = _workspace(B, Cd, K, _dt(queue), pth, q.device)
+    f32 = dict(dtype=torch.float32, device=q.device)
+    out = {}
+    if "loss" in want:
+        out["loss"] = torch.empty((), **f32)
+    for name in ("loss_per_row", "lse", "pos"):
+        if name in want:
+            out[name] = torch.empty(B, **f32)
+    if "argmax" in want:
+        out["argmax"] = torch.empty(B, dtype=torch.int64, device=q.device)
+    if need_grad and "dq" in want:
+        out["dq"] = torch.empty(B, Cd, **f32)
+    if need_grad and "dk" in want:
+        out["dk"] = torch.empty(B, Cd, **f32)
+    if "k_hat" in want:
+        out["k_hat"] = torch.empty(B, Cd, **f32)
+    flags = (_lib.FLAG_NORMALIZE_K if normalize_k else 0) | (0 if need_grad else _lib.FLAG_NO_GRAD)
+    rc = _lib.lib().rmcl_infonce_fwd_bwd(
+        _p(q), _dt(q), _p(k), _dt(k), _p(queue), _dt(queue), B, Cd, K, ldq, float(temperature), float(loss_scale),
+        flags, pth, _p(out.get("loss")), _p(out.get("loss_per_row")), _p(out.get("lse")), _p(out.get("pos")),
+        _p(out.get("argmax")), _p(out.get("dq")), _p(out.get("dk")), _p(out.get("k_hat")),
+        C.c_void_p(ws.data_ptr() + off), ws.numel() - off, _stream())
+    check(rc, "rmcl_infonce_fwd_bwd")
+    return out
+
+
+class InfoNCE(torch.autograd.Function):
+    """loss = CE([q^.k^ ; q^.queue]/T, 0) with dq computed in the same fused pass.
+
+    Drop-in for the expression chain at objectives.py:326-334+351 (and its PGD twin,
+    attack/pgd_attack_vilt.py:147-158).  ``k`` and ``queue`` get no gradient, as in the reference
+    (``no_grad`` at objectives.py:262, ``.clone().detach()`` at 270).
+    """
+
+    @staticmethod
+    def forward(ctx, q, k, queue, temperature, path="auto", normalize_k=False):
+        res = infonce_fwd_bwd(q, k, queue, temperature, normalize_k=normalize_k, path=path,
+                              want=("loss", "dq", "argmax", "pos", "lse"))
+        ctx.save_for_backward(res["dq"])
+        ctx.q_dtype = q.dtype
+        ctx.extra = res
+        ctx.mark_non_differentiable(res["argmax"])
+        return res["loss"], res["argmax"]
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_argmax):
+        (dq,) = ctx.saved_tensors
+        return (dq * grad_loss).to(ctx.q_dtype), None, None, None, None, None
+
+
+def infonce_loss(q, k, queue, temperature, path="auto", normalize_k=False):
+    """(loss, argmax) with autograd support for ``q``."""
+    return InfoNCE.apply(q, k, queue, temperature, path, normalize_k)
+
+
+# -------------------------------------------------------------------------------- enqueue
+def enqueue_(queue, keys, ptr):
+    """queue[:, ptr:ptr+B] = keys.T; ptr = (ptr+B) % K — on device, no host sync
+    (objectives.py:244-248).  ``ptr`` is the int64[1] buffer ``proj_queue_ptr``."""
+    _need_cuda(queue, keys, ptr)
+    if ptr.dtype != torch.int64 or ptr.numel() != 1:
+        raise TypeError("ptr must be an int64 tensor with one element")
+    if queue.stride(1) != 1 or keys.dim() != 2 or keys.shape[1] != queue.shape[0]:
+        raise ValueError(f"shape mismatch: queue {tuple(queue.shape)} keys {tuple(keys.shape)}")
+    keys = keys.detach().contiguous()
+    rc = _lib.lib().rmcl_enqueue(_p(queue), _dt(queue), _p(keys), _dt(keys), _p(ptr), keys.shape[0], keys.shape[1],
+                                 queue.shape[1], queue.stride(0), _stream())
+    check(rc, "rmcl_enqueue")
+
+
+# ------------------------------------------------------------------------------------ PGD
+def pgd_step_(delta, grad, lr, eps, mode="ref_linf", _scratch={}):
+    """In-place perturbation update (attack/pgd_attack_vilt.py:162-173 for ``ref_linf``)."""
+    _need_cuda(delta, grad)
+    if delta.shape != grad.shape:
+        raise ValueError("delta/grad shape mismatch")
+    if not (delta.is_contiguous() and grad.is_contiguous()):
+        raise ValueError("delta and grad must be contiguous")
+    B = delta.shape[0]
+    N = delta.numel() // B
+    key = (delta.device, B)
+    ws = _scratch.get(key)
+    if ws is None:
+        ws = _scratch[key] = torch.empty(2 * B, dtype=torch.float32, device=delta.device)
+    rc = _lib.lib().rmcl_pgd_step(_p(delta), _dt(delta), _p(grad), _dt(grad), B, N, float(lr), float(eps),
+                                  _lib.PGD_MODES[mode], _p(ws), _stream())
+    check(rc, "rmcl_pgd_step")
+    return delta
