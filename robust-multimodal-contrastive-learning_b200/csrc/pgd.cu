@@ -6,7 +6,7 @@
 //   delta = (delta + (lr*g/d).to(delta)).detach(); if eps > 0: delta = clamp(delta, -eps, eps)
 // (7 kernels / 5 full passes in eager torch).  REF_LINF reproduces that arithmetic operation by
 // operation — fadd(delta, fdiv(fmul(lr,g), d)) — so fp32 results are bit-identical.
-// SIGN_LINF and L2 are the north-star's extra modes (see oracle/rmcl_oracle.py docstring).
+// SIGN_LINF and L2 are the north-star's extra modes (specified in DESIGN.md).
 //
 // Two implementations, both HBM-bound, selected by size:
 //  * cluster path (pgd_cluster_kernel): one thread-block cluster per sample.  Each CTA stages its

@@ -1,0 +1,334 @@
+"""GPU parity tests: the CUDA kernels (through the C-ABI, via rmcl_b200.ops) against
+oracle/rmcl_oracle.py and the committed reference golden vectors.
+
+Bars (BASELINE.json north_star): queue + pointer bit-exact; EMA bit-exact (same two roundings as
+ATen); PGD ref_linf bit-exact in fp32; InfoNCE logits-derived quantities / loss / gradients within
+rel 1e-4 in fp32 and 2e-2 in bf16 (fp32 accumulation).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import rmcl_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+FP32_RTOL = 1e-4
+BF16_RTOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import rmcl_b200
+    return rmcl_b200.ops
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+# =============================================================================== EMA
+def _ema_case(ops, shapes, dtype, m, seed=0, offset=0):
+    g = torch.Generator().manual_seed(seed)
+    ks = [torch.randn(int(np.prod(s)) + offset, generator=g)[offset:].view(s).to(dtype) for s in shapes]
+    qs = [torch.randn(int(np.prod(s)) + offset, generator=g)[offset:].view(s).to(dtype) for s in shapes]
+    # device copies keep the same storage offsets (exercises the unaligned path when offset != 0)
+    kd = [torch.empty(k.numel() + offset, dtype=dtype, device=DEV)[offset:].view(k.shape).copy_(k) for k in ks]
+    qd = [torch.empty(q.numel() + offset, dtype=dtype, device=DEV)[offset:].view(q.shape).copy_(q) for q in qs]
+    plan = ops.EmaPlan(kd, qd)
+    ops.ema_multi_(plan, m)
+    torch.cuda.synchronize()
+    want = O.momentum_update(ks, qs, m)
+    for i, (got, w) in enumerate(zip(kd, want)):
+        assert torch.equal(got.cpu(), w), f"tensor {i} shape {shapes[i]} differs (max {rel_err(got, w):.3e})"
+    for q0, q1 in zip(qs, qd):
+        assert torch.equal(q0, q1.cpu())  # q untouched
+
+
+RAGGED = [(1,), (3,), (7, 5), (768,), (2, 768), (40, 768), (3072, 768), (30522, 13), (16385,), (65537,), (128, 768)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("m", [0.999, 0.5, 1.0, 0.0])
+def test_ema_bit_exact_ragged(ops, dtype, m):
+    _ema_case(ops, RAGGED, dtype, m)
+
+
+@pytest.mark.parametrize("dtype,offset", [(torch.float32, 1), (torch.float32, 3), (torch.bfloat16, 1), (torch.bfloat16, 5)])
+def test_ema_unaligned_views(ops, dtype, offset):
+    _ema_case(ops, [(1000,), (4097,), (33, 7)], dtype, 0.999, offset=offset)
+
+
+def test_ema_golden_reference(ops, golden):
+    for name in ("ref_tiny_c16", "ref_tiny_c128"):
+        g = golden(name)
+        for s in range(g.i("meta/steps")):
+            n = g.i(f"step{s}/ema/n")
+            kd = [g.t(f"step{s}/ema/k_before/{i}").to(DEV) for i in range(n)]
+            qd = [g.t(f"step{s}/ema/q/{i}").to(DEV) for i in range(n)]
+            ops.ema_multi_(ops.EmaPlan(kd, qd), g.f(f"step{s}/momentum"))
+            for i in range(n):
+                assert torch.equal(kd[i].cpu(), g.t(f"step{s}/ema/k_after/{i}")), (name, s, i)
+    g = golden("ref_cfg1_vilt_b32")
+    for i in g.np("step0/ema/kept"):
+        kd, qd = g.t(f"step0/ema/k_before/{i}").to(DEV), g.t(f"step0/ema/q/{i}").to(DEV)
+        ops.ema_multi_(ops.EmaPlan([kd], [qd]), g.f("step0/momentum"))
+        assert torch.equal(kd.cpu(), g.t(f"step0/ema/k_after/{i}"))
+
+
+def test_ema_full_vilt_shape_list(ops, golden):
+    """All 161 tensors / 111.7 M params of the ViLT-B/32 key encoder in one launch; checked by
+    linearity-free exact recomputation on a strided sample plus a float64 checksum."""
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "vilt_b32_key_encoder_shapes.txt")
+    shapes = [tuple(int(d) for d in l.split("x")) for l in open(path) if l.strip() and not l.startswith("#")]
+    assert len(shapes) == 161 and sum(int(np.prod(s)) for s in shapes) == 111_694_848
+    torch.manual_seed(0)
+    kd = [torch.randn(s, device=DEV) for s in shapes]
+    qd = [torch.randn(s, device=DEV) for s in shapes]
+    k0 = [k.clone() for k in kd]
+    plan = ops.EmaPlan(kd, qd)
+    assert plan.n_params == 111_694_848
+    ops.ema_multi_(plan, 0.999)
+    mf, omf = np.float32(0.999), np.float32(1.0 - 0.999)
+    for a, b, c in zip(k0, qd, kd):
+        want = a * float(mf) + b * float(omf)   # torch on GPU: separate mul/mul/add kernels, no contraction
+        assert torch.equal(c, want)
+
+
+# =========================================================================== enqueue
+@pytest.mark.parametrize("B,C,K", [(4, 16, 64), (8, 128, 4096), (256, 256, 65536), (1024, 128, 65536), (33, 70, 33 * 5)])
+@pytest.mark.parametrize("kdt,qdt", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                     (torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.float32)])
+def test_enqueue_bit_exact(ops, B, C, K, kdt, qdt):
+    g = torch.Generator().manual_seed(B + C)
+    queue = torch.randn(C, K, generator=g).to(qdt)
+    for ptr0 in (0, B, K - B):
+        keys = torch.randn(B, C, generator=g).to(kdt)
+        qd, pd = queue.to(DEV), torch.tensor([ptr0], dtype=torch.int64, device=DEV)
+        ops.enqueue_(qd, keys.to(DEV), pd)
+        want_q, want_p = O.dequeue_and_enqueue(queue, ptr0, keys, K)
+        assert pd.item() == want_p == (ptr0 + B) % K
+        assert torch.equal(qd.cpu(), want_q)
+
+
+def test_enqueue_sequence_wraps_and_rejects_bad_k(ops):
+    B, C, K = 8, 16, 32
+    qd, pd = torch.zeros(C, K, device=DEV), torch.zeros(1, dtype=torch.int64, device=DEV)
+    ref_q, ref_p = torch.zeros(C, K), 0
+    for step in range(9):  # wraps twice
+        keys = torch.full((B, C), float(step + 1))
+        ops.enqueue_(qd, keys.to(DEV), pd)
+        ref_q, ref_p = O.dequeue_and_enqueue(ref_q, ref_p, keys, K)
+    assert pd.item() == ref_p == (9 * B) % K and torch.equal(qd.cpu(), ref_q)
+    from rmcl_b200._lib import RmclError
+    with pytest.raises(RmclError):
+        ops.enqueue_(torch.zeros(C, 30, device=DEV), torch.zeros(B, C, device=DEV), pd)  # K % B != 0
+
+
+def test_enqueue_golden_reference(ops, golden):
+    for name in ("ref_tiny_c16", "ref_tiny_c128", "ref_cfg1_vilt_b32"):
+        g = golden(name)
+        B = g.i("meta/B")
+        for s in range(g.i("meta/steps")):
+            p = f"step{s}"
+            ptr0 = g.i(f"{p}/ptr_before")
+            qd = g.t(f"{p}/queue_before").to(DEV)
+            pd = torch.tensor([ptr0], dtype=torch.int64, device=DEV)
+            ops.enqueue_(qd, g.t(f"{p}/k_hat").to(DEV), pd)
+            assert pd.item() == g.i(f"{p}/ptr_after")
+            assert torch.equal(qd[:, ptr0:ptr0 + B].cpu(), g.t(f"{p}/queue_after_cols"))
+            assert qd.double().sum().item() == pytest.approx(g.f(f"{p}/queue_after_sum64"), rel=0, abs=1e-9)
+
+
+# =============================================================================== PGD
+PGD_SHAPES = [(4, 3, 16, 16), (3, 7, 5), (2, 185, 768), (2, 3, 384, 384), (5, 1001), (1, 900_001)]
+
+
+@pytest.mark.parametrize("shape", PGD_SHAPES)
+@pytest.mark.parametrize("eps", [8.0 / 255.0, 0.0])
+def test_pgd_ref_linf_bit_exact(ops, shape, eps):
+    g = torch.Generator().manual_seed(len(shape))
+    delta = torch.zeros(shape)
+    dd = delta.to(DEV)
+    for step in range(3):
+        grad = torch.randn(shape, generator=g) * 10 ** (step - 3)
+        if step == 1:
+            grad[0].zero_()                      # all-zero sample: denominator clamps to 1e-8
+            grad.view(shape[0], -1)[-1, 0] = 1e4  # a single huge element dominates the inf-norm
+        delta = O.pgd_update(delta, grad, 0.05, eps)
+        ops.pgd_step_(dd, grad.to(DEV), 0.05, eps, "ref_linf")
+        assert torch.equal(dd.cpu(), delta), f"step {step}: {rel_err(dd, delta):.3e}"
+
+
+def test_pgd_denormal_gradients(ops):
+    grad = torch.full((2, 64), 1e-41)
+    grad[1] *= -1
+    want = O.pgd_update(torch.zeros(2, 64), grad, 0.05, 0.1)
+    got = ops.pgd_step_(torch.zeros(2, 64, device=DEV), grad.to(DEV), 0.05, 0.1)
+    assert torch.equal(got.cpu(), want)
+
+
+@pytest.mark.parametrize("name", ["ref_pgd_5step", "ref_pgd_noclamp"])
+def test_pgd_golden_reference(ops, golden, name):
+    g = golden(name)
+    n, lr, eps = g.i("n_pgd"), g.f("lr"), g.f("eps")
+    dd = torch.zeros_like(g.t("delta_final")).to(DEV)
+    for s in range(n):
+        ops.pgd_step_(dd, g.t(f"pgd{s}/grad").view_as(dd).to(DEV), lr, eps)
+        if eps > 0:
+            assert torch.equal(dd.cpu(), g.t(f"pgd{s}/delta_after"))
+    assert torch.equal(dd.cpu(), g.t("delta_final"))
+
+
+def test_pgd_golden_cfg1(ops, golden):
+    g = golden("ref_cfg1_vilt_b32")
+    grad = g.t("step0/pgd0/grad")                     # one 3x384x384 sample of the real ViLT gradient
+    dd = torch.zeros_like(grad).to(DEV)
+    ops.pgd_step_(dd, grad.to(DEV), g.f("step0/adv_lr"), g.f("step0/adv_eps"))
+    assert torch.equal(dd.cpu(), g.t("step0/pgd0/delta_after"))
+
+
+@pytest.mark.parametrize("shape", [(4, 3, 16, 16), (2, 185, 768), (2, 3, 384, 384), (1, 900_001)])
+def test_pgd_sign_and_l2_modes(ops, shape):
+    g = torch.Generator().manual_seed(7)
+    grad = torch.randn(shape, generator=g)
+    d0 = torch.randn(shape, generator=g) * 0.01
+    want = O.pgd_update(d0, grad, 2.0 / 255.0, 8.0 / 255.0, mode="sign_linf")
+    got = ops.pgd_step_(d0.to(DEV), grad.to(DEV), 2.0 / 255.0, 8.0 / 255.0, "sign_linf")
+    assert torch.equal(got.cpu(), want)
+    for eps in (1.0, 0.0):
+        want = O.pgd_update(d0.double(), grad.double(), 0.5, eps, mode="l2")
+        got = ops.pgd_step_(d0.to(DEV), grad.to(DEV), 0.5, eps, "l2")
+        assert rel_err(got, want) < FP32_RTOL
+        if eps > 0:
+            assert got.view(shape[0], -1).norm(dim=1).max().item() <= eps * (1 + 1e-5)
+        signs = (torch.sign(got.cpu() - d0) == torch.sign(grad)) | (grad == 0)
+        if eps == 0:
+            assert signs.float().mean().item() >= 0.999
+
+
+def test_pgd_bf16_delta(ops):
+    g = torch.Generator().manual_seed(3)
+    grad = torch.randn(4, 1000, generator=g)
+    d0 = (torch.randn(4, 1000, generator=g) * 0.01).bfloat16()
+    want = O.pgd_update(d0, grad, 0.05, 8.0 / 255.0)
+    got = ops.pgd_step_(d0.to(DEV), grad.to(DEV), 0.05, 8.0 / 255.0)
+    assert torch.equal(got.cpu(), want)
+
+
+# =========================================================================== InfoNCE
+def _infonce_inputs(B, C, K, seed, queue_dtype=torch.float32, normalized_queue=False):
+    g = torch.Generator().manual_seed(seed)
+    q = torch.randn(B, C, generator=g)
+    k = torch.nn.functional.normalize(torch.randn(B, C, generator=g), dim=1)
+    queue = torch.randn(C, K, generator=g)
+    if normalized_queue:
+        queue = torch.nn.functional.normalize(queue, dim=0)
+    return q, k, queue.to(queue_dtype)
+
+
+def _check_infonce(res, ref, rtol, B):
+    assert rel_err(res["loss"], ref["loss"]) < rtol
+    assert rel_err(res["loss_per_row"], ref["loss_per_row"]) < rtol
+    assert rel_err(res["lse"], ref["lse"]) < rtol
+    assert (res["pos"].double().cpu() - ref["pos"].double()).abs().max().item() < rtol * ref["logits"].abs().max().item()
+    assert rel_err(res["dq"], ref["dq"]) < rtol
+
+
+@pytest.mark.parametrize("B,C,K", [(8, 128, 4096), (4, 16, 64), (1, 2, 1), (3, 5, 7), (16, 128, 1000), (33, 96, 333),
+                                   (128, 128, 8192), (17, 768, 520), (8, 256, 4096)])
+@pytest.mark.parametrize("normalized_queue", [False, True])
+def test_infonce_simt_fp32_vs_oracle(ops, B, C, K, normalized_queue):
+    q, k, queue = _infonce_inputs(B, C, K, seed=B * 1000 + C, normalized_queue=normalized_queue)
+    ref = O.info_nce(q, k, queue, 0.07)
+    ref64 = O.info_nce(q.double(), k.double(), queue.double(), 0.07)
+    res = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.to(DEV), 0.07, path="simt")
+    _check_infonce(res, ref64, FP32_RTOL, B)
+    _check_infonce(res, ref, FP32_RTOL, B)
+    # argmax: must agree wherever the oracle's top-2 logits are separated by more than fp32 noise
+    top2 = ref64["logits"].topk(min(2, K + 1), dim=1).values
+    clear = (top2[:, 0] - top2[:, -1]) > 1e-3 if K + 1 > 1 else torch.ones(B, dtype=torch.bool)
+    assert torch.equal(res["argmax"].cpu()[clear], ref64["argmax"][clear])
+    # dk = d loss / d k^ = (p_pos - 1) q^ / (T B)
+    p_pos = torch.exp(ref64["pos"] - ref64["lse"])
+    dk = ((p_pos - 1)[:, None] * ref64["q_hat"]) / (0.07 * B)
+    assert rel_err(res["dk"], dk) < FP32_RTOL
+
+
+def test_infonce_golden_reference(ops, golden):
+    for name in ("ref_tiny_c16", "ref_tiny_c128", "ref_cfg1_vilt_b32"):
+        g = golden(name)
+        for s in range(g.i("meta/steps")):
+            p = f"step{s}"
+            k, queue, T = g.t(f"{p}/k_hat").to(DEV), g.t(f"{p}/queue_before").to(DEV), g.f(f"{p}/temperature")
+            res = ops.infonce_fwd_bwd(g.t(f"{p}/q_raw").to(DEV), k, queue, T, path="simt")
+            logits = g.t(f"{p}/logits")
+            assert rel_err(res["loss"], g.t(f"{p}/loss")) < FP32_RTOL
+            assert rel_err(res["dq"], g.t(f"{p}/dq_raw")) < FP32_RTOL
+            assert rel_err(res["lse"], torch.logsumexp(logits.double(), 1)) < FP32_RTOL
+            assert rel_err(res["pos"], logits[:, 0]) < FP32_RTOL
+            assert torch.equal(res["argmax"].cpu(), logits.argmax(-1))
+            n_pgd = g.i(f"{p}/n_pgd")
+            for a in range(n_pgd):   # PGD-inner call sites: loss / adv_steps
+                res = ops.infonce_fwd_bwd(g.t(f"{p}/pgd{a}/q_raw").to(DEV), k, queue, T, loss_scale=1.0 / n_pgd, path="simt")
+                assert rel_err(res["loss"] * n_pgd, g.t(f"{p}/pgd{a}/loss")) < FP32_RTOL
+                assert rel_err(res["dq"], g.t(f"{p}/pgd{a}/dq_raw")) < FP32_RTOL
+            # clean-query call: raw key in, normalised key + argmax out, no gradient
+            res = ops.infonce_fwd_bwd(g.t(f"{p}/q_clean_raw").to(DEV), g.t(f"{p}/k_raw").to(DEV), queue, T,
+                                      normalize_k=True, need_grad=False, want=("argmax", "k_hat"), path="simt")
+            assert rel_err(res["k_hat"], g.t(f"{p}/k_hat")) < 1e-6
+
+
+def test_infonce_known_answers(ops):
+    q = torch.tensor([[3.0, 4.0]], device=DEV)
+    k = torch.tensor([[0.6, 0.8]], device=DEV)
+    queue = torch.tensor([[1.0], [0.0]], device=DEV)
+    r = ops.infonce_fwd_bwd(q, k, queue, 0.5, path="simt")
+    assert r["loss"].item() == pytest.approx(math.log1p(math.exp((0.6 - 1.0) / 0.5)), rel=1e-5)
+    K = 1000
+    r = ops.infonce_fwd_bwd(q, k, queue.repeat(1, K).contiguous(), 0.5, path="simt")
+    assert r["loss"].item() == pytest.approx(math.log1p(K * math.exp((0.6 - 1.0) / 0.5)), rel=1e-5)
+    assert r["argmax"].item() == 0
+    # a queue column identical to q^ with a worse key: argmax must point at it (index j+1)
+    queue2 = torch.zeros(2, 64, device=DEV)
+    queue2[:, 37] = torch.tensor([0.6, 0.8])
+    r = ops.infonce_fwd_bwd(q, torch.tensor([[1.0, 0.0]], device=DEV), queue2, 0.5, path="simt")
+    assert r["argmax"].item() == 38
+
+
+@pytest.mark.parametrize("B,C,K", [(256, 256, 65536), (128, 128, 65536)])
+def test_infonce_simt_full_size_bf16_queue(ops, B, C, K):
+    """BASELINE cfg2 / cfg4 shapes, bf16 queue: against the float64 oracle fed the same
+    bf16-rounded operands (tolerance 2e-2 per north_star; the achieved error is far smaller)."""
+    q, k, queue = _infonce_inputs(B, C, K, seed=1, queue_dtype=torch.bfloat16)
+    qh = O.l2_normalize(q.double()).bfloat16().double()
+    ref = O.info_nce(q.double(), k.bfloat16().double(), queue.double(), 0.07)
+    res = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.to(DEV), 0.07, path="simt")
+    assert rel_err(res["loss"], ref["loss"]) < BF16_RTOL
+    assert rel_err(res["dq"], ref["dq"]) < BF16_RTOL
+    assert rel_err(res["lse"], ref["lse"]) < BF16_RTOL
+    # size-independent property: gradient is orthogonal to q (normalisation Jacobian)
+    assert ((res["dq"].double().cpu() * q.double()).sum(1).abs().max() / res["dq"].abs().max().item()) < 1e-3
+    del qh
+
+
+def test_infonce_autograd_function(ops):
+    q, k, queue = _infonce_inputs(16, 128, 2048, seed=5)
+    qd = q.to(DEV).requires_grad_(True)
+    loss, argmax = ops.infonce_loss(qd, k.to(DEV), queue.to(DEV), 0.07, "simt")
+    (loss * 3.0).backward()
+    ref = O.info_nce(q, k, queue, 0.07, grad_out=3.0)
+    assert rel_err(qd.grad, ref["dq"]) < FP32_RTOL
+    assert rel_err(loss, ref["loss"]) < FP32_RTOL
+
+
+def test_cpu_tensors_raise(ops):
+    with pytest.raises(RuntimeError):
+        ops.pgd_step_(torch.zeros(2, 4), torch.zeros(2, 4), 0.1, 0.1)
+    with pytest.raises(RuntimeError):
+        ops.infonce_fwd_bwd(torch.zeros(2, 4), torch.zeros(2, 4), torch.zeros(4, 8), 0.07)
