@@ -111,6 +111,13 @@ int rmcl_infonce_fwd_bwd(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_
                          float* dq, float* dk, float* k_hat_out, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* Measurement aid (off by default): when enabled on the calling thread, rmcl_infonce_fwd_bwd
+ * records CUDA events on its stream around its three launches (prep, split-K partial, finalize);
+ * rmcl_profile_infonce_ms waits for the last of them and returns the three durations of the most
+ * recent call.  bench.py uses this for the per-kernel roofline; the product path leaves it off. */
+int rmcl_profile_enable(int on);
+int rmcl_profile_infonce_ms(float* out3);
+
 /* ---------------------------------------------------------------------------------------------
  * Ring-buffer enqueue:  queue[:, ptr:ptr+B] = keys^T ;  ptr = (ptr + B) % K, all on the device.
  * replaces: objectives.py:244-248 (int(ptr) D2H sync, strided slice-assign, host modulo, H2D
@@ -140,7 +147,7 @@ int rmcl_pgd_step(void* delta, rmcl_dtype delta_dtype, const void* grad, rmcl_dt
  * memory.  Parameters, queue and pointer stay resident on the device (they are model state).
  * Copies are issued on `stream`; the call returns after the D2H copies completed.
  */
-int rmcl_step_host(const rmcl_ema_chunk* chunks_dev, int64_t n_chunks, double m,
+int rmcl_step_host(const rmcl_ema_chunk* chunks_dev, int64_t n_chunks, double m, rmcl_dtype param_dtype,
                    const void* q_host, const void* k_host, rmcl_dtype qk_dtype,
                    void* q_dev, void* k_dev,
                    void* queue, rmcl_dtype queue_dtype, int64_t* ptr_dev, int B, int C, int64_t K,

@@ -54,7 +54,8 @@ extern "C" int rmcl_sm_count(void) {
   return n > 0 ? n : RMCL_E_CUDA;
 }
 
-extern "C" int rmcl_step_host(const rmcl_ema_chunk* chunks_dev, int64_t n_chunks, double m, const void* q_host,
+extern "C" int rmcl_step_host(const rmcl_ema_chunk* chunks_dev, int64_t n_chunks, double m,
+                              rmcl_dtype param_dtype, const void* q_host,
                               const void* k_host, rmcl_dtype qk_dtype, void* q_dev, void* k_dev, void* queue,
                               rmcl_dtype queue_dtype, int64_t* ptr_dev, int B, int C, int64_t K, float tau, int path,
                               float* loss_dev, float* dq_dev, float* k_hat_dev, float* loss_host, float* dq_host,
@@ -65,7 +66,7 @@ extern "C" int rmcl_step_host(const rmcl_ema_chunk* chunks_dev, int64_t n_chunks
   const size_t qk_bytes = (size_t)B * C * rmcl::dtype_size(qk_dtype);
   RMCL_CUDA_OK(cudaMemcpyAsync(q_dev, q_host, qk_bytes, cudaMemcpyHostToDevice, s));
   RMCL_CUDA_OK(cudaMemcpyAsync(k_dev, k_host, qk_bytes, cudaMemcpyHostToDevice, s));
-  int rc = rmcl_ema_multi(chunks_dev, n_chunks, m, queue_dtype, stream);
+  int rc = rmcl_ema_multi(chunks_dev, n_chunks, m, param_dtype, stream);
   if (rc != RMCL_OK) return rc;
   rc = rmcl_infonce_fwd_bwd(q_dev, qk_dtype, k_dev, qk_dtype, queue, queue_dtype, B, C, K, K, tau, 1.0f,
                             RMCL_INFONCE_NORMALIZE_K, path, loss_dev, nullptr, nullptr, nullptr, nullptr, dq_dev,

@@ -27,7 +27,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 int infonce_make_plan(int B, int C, long long K, int queue_dtype, int path, bool aligned_for_tc, InfoNcePlan* p) {
   const int sms = sm_count();
   if (sms <= 0) return RMCL_E_CUDA;
-  const bool tc_ok = aligned_for_tc && queue_dtype == RMCL_BF16 && (C == 64 || C == 128 || C == 256) && (K % 8 == 0);
+  const bool tc_ok = infonce_tc_built() && aligned_for_tc && queue_dtype == RMCL_BF16 && (C == 64 || C == 128 || C == 256) && (K % 8 == 0);
   if (path == RMCL_INFONCE_AUTO) path = tc_ok ? RMCL_INFONCE_TCGEN05 : RMCL_INFONCE_SIMT;
   if (path == RMCL_INFONCE_TCGEN05 && !tc_ok) {
     set_error("tcgen05 InfoNCE needs a 16B-aligned bf16 queue, C in {64,128,256}, K %% 8 == 0 (got C=%d K=%lld)", C, K);
@@ -179,7 +179,9 @@ __global__ void __launch_bounds__(256) infonce_finalize_kernel(
       const float L = fmaf(lsum, wneg, wpos);
       const float lse = (M + log2f(L)) * kLn2;
       const float pos = p2 * kLn2;
-      const float lrow = lse - pos;
+      // lse - pos cancels catastrophically when the positive dominates (p_pos -> 1); take the
+      // difference before the log instead: positive is the max -> log1p of the remaining mass.
+      const float lrow = (p2 >= mmax) ? log1pf(lsum * wneg) : fmaf(M - p2, kLn2, logf(L));
       row_loss[row] = lrow;
       if (loss_per_row) loss_per_row[row] = lrow;
       if (lse_out) lse_out[row] = lse;
@@ -268,6 +270,33 @@ static int launch_prep(const void* q, const void* k, int B, int C, float scale2,
 
 using namespace rmcl;
 
+// ---- optional stage timing (measurement aid; off by default) --------------------------------
+static thread_local bool g_prof_on = false;
+static thread_local cudaEvent_t g_prof_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+static thread_local bool g_prof_valid = false;
+
+extern "C" int rmcl_profile_enable(int on) {
+  if (on && !g_prof_ev[0]) {
+    for (int i = 0; i < 4; ++i) RMCL_CUDA_OK(cudaEventCreate(&g_prof_ev[i]));
+  }
+  g_prof_on = on != 0;
+  g_prof_valid = false;
+  return RMCL_OK;
+}
+
+extern "C" int rmcl_profile_infonce_ms(float* out3) {
+  RMCL_CHECK_ARG(out3 != nullptr, "rmcl_profile_infonce_ms: null pointer");
+  RMCL_CHECK_ARG(g_prof_valid, "rmcl_profile_infonce_ms: no profiled rmcl_infonce_fwd_bwd call on this thread");
+  RMCL_CUDA_OK(cudaEventSynchronize(g_prof_ev[3]));
+  for (int i = 0; i < 3; ++i) RMCL_CUDA_OK(cudaEventElapsedTime(out3 + i, g_prof_ev[i], g_prof_ev[i + 1]));
+  return RMCL_OK;
+}
+
+#define RMCL_PROF_MARK(i)                                        \
+  do {                                                           \
+    if (g_prof_on) RMCL_CUDA_OK(cudaEventRecord(g_prof_ev[i], s)); \
+  } while (0)
+
 static bool tc_alignment_ok(const void* queue, int64_t ldq) {
   return (reinterpret_cast<uintptr_t>(queue) & 15u) == 0 && (ldq % 8 == 0);
 }
@@ -310,6 +339,7 @@ extern "C" int rmcl_infonce_fwd_bwd(const void* q, rmcl_dtype q_dtype, const voi
   const bool want_grad = (flags & RMCL_INFONCE_NO_GRAD) == 0 && (dq || dk);
   const bool tc = (p.path == RMCL_INFONCE_TCGEN05);
   using bf16 = __nv_bfloat16;
+  RMCL_PROF_MARK(0);
   if (q_dtype == RMCL_F32 && k_dtype == RMCL_F32)
     rc = launch_prep<float, float>(q, k, B, C, scale2, nk, bf16_mode, ws, p, k_hat_out, tc, s);
   else if (q_dtype == RMCL_F32)
@@ -319,6 +349,7 @@ extern "C" int rmcl_infonce_fwd_bwd(const void* q, rmcl_dtype q_dtype, const voi
   else
     rc = launch_prep<bf16, bf16>(q, k, B, C, scale2, nk, bf16_mode, ws, p, k_hat_out, tc, s);
   if (rc != RMCL_OK) return rc;
+  RMCL_PROF_MARK(1);
 
   InfoNcePartials parts{(float*)(ws + p.off_m), (float*)(ws + p.off_l), (float*)(ws + p.off_av), (int*)(ws + p.off_ai),
                         (float*)(ws + p.off_o)};
@@ -327,6 +358,7 @@ extern "C" int rmcl_infonce_fwd_bwd(const void* q, rmcl_dtype q_dtype, const voi
   else
     rc = infonce_simt_launch((const float*)(ws + p.off_qhat), queue, queue_dtype, B, C, K, ldq, scale2, p, parts, s);
   if (rc != RMCL_OK) return rc;
+  RMCL_PROF_MARK(2);
 
   infonce_finalize_kernel<<<B, 256, p.splits * sizeof(float), s>>>(
       B, C, p.splits, 1.f / tau, loss_scale / (float)B, loss_scale, bf16_mode, want_grad, (const float*)(ws + p.off_qhat),
@@ -334,5 +366,7 @@ extern "C" int rmcl_infonce_fwd_bwd(const void* q, rmcl_dtype q_dtype, const voi
       parts.av, parts.ai, parts.o, (float*)(ws + p.off_rowloss), (unsigned int*)(ws + p.off_counter), loss, loss_per_row,
       lse, pos, reinterpret_cast<long long*>(argmax), dq, dk);
   RMCL_LAUNCH_OK("infonce_finalize_kernel");
+  RMCL_PROF_MARK(3);
+  if (g_prof_on) g_prof_valid = true;
   return RMCL_OK;
 }

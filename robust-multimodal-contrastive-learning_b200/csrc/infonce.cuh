@@ -46,5 +46,6 @@ int infonce_tc_launch(const __nv_bfloat16* q_hat_bf16, const void* queue, int B,
                       float scale2, const InfoNcePlan& plan, InfoNcePartials out, cudaStream_t s);
 bool infonce_tc_supported(int C, long long K, long long ldq, const void* queue, int queue_dtype);
 size_t infonce_tc_smem_bytes(int C);
+bool infonce_tc_built();
 
 }  // namespace rmcl

@@ -210,3 +210,54 @@ def pgd_step_(delta, grad, lr, eps, mode="ref_linf", _scratch={}):
                                   _lib.PGD_MODES[mode], _p(ws), _stream())
     check(rc, "rmcl_pgd_step")
     return delta
+
+
+# ------------------------------------------------------- host-buffer step (end-to-end call)
+class HostStep:
+    """One kernels-only RMCL step (EMA -> fused InfoNCE fwd+bwd -> enqueue) driven from HOST
+    buffers through ``rmcl_step_host``: q/k projections come from pinned host memory, the loss
+    and dq go back to pinned host memory; parameters, queue and pointer stay resident in HBM.
+    This is the call the end-to-end number in bench.py is measured through."""
+
+    def __init__(self, plan, queue, ptr, B, Cdim, temperature, m, qk_dtype=torch.bfloat16, path="auto"):
+        _need_cuda(queue, ptr)
+        if len(plan.groups) != 1:
+            raise ValueError("HostStep expects a single-dtype EMA plan")
+        dev = queue.device
+        self.plan, self.queue, self.ptr = plan, queue, ptr
+        self.B, self.C, self.K = B, Cdim, queue.shape[1]
+        self.tau, self.m, self.path = float(temperature), float(m), _lib.INFONCE_PATHS[path]
+        self.qk_dtype = qk_dtype
+        self.q_dev = torch.empty(B, Cdim, dtype=qk_dtype, device=dev)
+        self.k_dev = torch.empty(B, Cdim, dtype=qk_dtype, device=dev)
+        self.loss_dev = torch.empty((), dtype=torch.float32, device=dev)
+        self.dq_dev = torch.empty(B, Cdim, dtype=torch.float32, device=dev)
+        self.k_hat_dev = torch.empty(B, Cdim, dtype=torch.float32, device=dev)
+        self.loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+        self.dq_host = torch.empty(B, Cdim, dtype=torch.float32).pin_memory()
+        self.ws, self.ws_off = _workspace(B, Cdim, self.K, _dt(queue), self.path, dev)
+        self.h2d_bytes = 2 * B * Cdim * self.q_dev.element_size()
+        self.d2h_bytes = 4 + B * Cdim * 4
+
+    def __call__(self, q_host, k_host):
+        """Blocks until loss_host / dq_host are valid; returns them."""
+        if q_host.is_cuda or k_host.is_cuda or q_host.dtype != self.qk_dtype or k_host.dtype != self.qk_dtype:
+            raise ValueError("HostStep takes host tensors of the configured dtype")
+        dt, table, cnt, _ = self.plan.groups[0]
+        rc = _lib.lib().rmcl_step_host(
+            _p(table), cnt, self.m, dt, _p(q_host), _p(k_host), _DT[self.qk_dtype], _p(self.q_dev), _p(self.k_dev),
+            _p(self.queue), _dt(self.queue), _p(self.ptr), self.B, self.C, self.K, self.tau, self.path,
+            _p(self.loss_dev), _p(self.dq_dev), _p(self.k_hat_dev), _p(self.loss_host), _p(self.dq_host),
+            C.c_void_p(self.ws.data_ptr() + self.ws_off), self.ws.numel() - self.ws_off, _stream())
+        check(rc, "rmcl_step_host")
+        return self.loss_host, self.dq_host
+
+
+def profile_enable(on=True):
+    check(_lib.lib().rmcl_profile_enable(1 if on else 0), "rmcl_profile_enable")
+
+
+def profile_infonce_ms():
+    out = (C.c_float * 3)()
+    check(_lib.lib().rmcl_profile_infonce_ms(out), "rmcl_profile_infonce_ms")
+    return {"prep": out[0], "partial": out[1], "finalize": out[2]}

@@ -232,9 +232,13 @@ def _infonce_inputs(B, C, K, seed, queue_dtype=torch.float32, normalized_queue=F
     return q, k, queue.to(queue_dtype)
 
 
-def _check_infonce(res, ref, rtol, B):
-    assert rel_err(res["loss"], ref["loss"]) < rtol
-    assert rel_err(res["loss_per_row"], ref["loss_per_row"]) < rtol
+def _check_infonce(res, ref, rtol, B, fp32_ref=False):
+    # An fp32 reference loses the loss itself to cancellation when the positive dominates
+    # (loss ~ 1e-5 next to logits ~ 10): allow it one fp32 ulp of the largest logit.
+    slack = 2.0 ** -23 * ref["logits"].abs().max().item() if fp32_ref else 0.0
+    for name in ("loss", "loss_per_row"):
+        a, b = res[name].double().cpu(), ref[name].double()
+        assert ((a - b).abs().max() <= rtol * b.abs().max() + slack), (name, a, b)
     assert rel_err(res["lse"], ref["lse"]) < rtol
     assert (res["pos"].double().cpu() - ref["pos"].double()).abs().max().item() < rtol * ref["logits"].abs().max().item()
     assert rel_err(res["dq"], ref["dq"]) < rtol
@@ -249,7 +253,7 @@ def test_infonce_simt_fp32_vs_oracle(ops, B, C, K, normalized_queue):
     ref64 = O.info_nce(q.double(), k.double(), queue.double(), 0.07)
     res = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.to(DEV), 0.07, path="simt")
     _check_infonce(res, ref64, FP32_RTOL, B)
-    _check_infonce(res, ref, FP32_RTOL, B)
+    _check_infonce(res, ref, FP32_RTOL, B, fp32_ref=True)
     # argmax: must agree wherever the oracle's top-2 logits are separated by more than fp32 noise
     top2 = ref64["logits"].topk(min(2, K + 1), dim=1).values
     clear = (top2[:, 0] - top2[:, -1]) > 1e-3 if K + 1 > 1 else torch.ones(B, dtype=torch.bool)
