@@ -43,7 +43,7 @@ int infonce_make_plan(int B, int C, long long K, int queue_dtype, int path, bool
     p->tile_cols = (C <= 512) ? 64 : 32;
   } else {
     p->rows_per_cta = 128;
-    p->tile_cols = 64;
+    p->tile_cols = infonce_tc_tile_cols(C);
   }
   p->row_blocks = (B + p->rows_per_cta - 1) / p->rows_per_cta;
   p->b_pad = p->row_blocks * p->rows_per_cta;
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) infonce_finalize_kernel(
       if (pos_out) pos_out[row] = pos;
       if (argmax_out) argmax_out[row] = (p2 >= bv) ? 0ll : (long long)bi + 1;
       s_stats[0] = wneg / L;
-      s_stats[1] = wpos / L - 1.f;
+      s_stats[1] = -(lsum * wneg) / L;  // p_pos - 1 without the cancellation of wpos/L - 1
     }
   }
   __syncthreads();
@@ -354,7 +354,7 @@ extern "C" int rmcl_infonce_fwd_bwd(const void* q, rmcl_dtype q_dtype, const voi
   InfoNcePartials parts{(float*)(ws + p.off_m), (float*)(ws + p.off_l), (float*)(ws + p.off_av), (int*)(ws + p.off_ai),
                         (float*)(ws + p.off_o)};
   if (tc)
-    rc = infonce_tc_launch((const bf16*)(ws + p.off_qhat_bf16), queue, B, C, K, ldq, scale2, p, parts, s);
+    rc = infonce_tc_launch((const bf16*)(ws + p.off_qhat_bf16), queue, B, C, K, ldq, scale2, p, parts, argmax != nullptr, s);
   else
     rc = infonce_simt_launch((const float*)(ws + p.off_qhat), queue, queue_dtype, B, C, K, ldq, scale2, p, parts, s);
   if (rc != RMCL_OK) return rc;

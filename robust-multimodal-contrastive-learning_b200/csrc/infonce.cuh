@@ -43,9 +43,8 @@ struct InfoNcePartials {
 int infonce_simt_launch(const float* q_hat, const void* queue, int queue_dtype, int B, int C, long long K,
                         long long ldq, float scale2, const InfoNcePlan& plan, InfoNcePartials out, cudaStream_t s);
 int infonce_tc_launch(const __nv_bfloat16* q_hat_bf16, const void* queue, int B, int C, long long K, long long ldq,
-                      float scale2, const InfoNcePlan& plan, InfoNcePartials out, cudaStream_t s);
-bool infonce_tc_supported(int C, long long K, long long ldq, const void* queue, int queue_dtype);
-size_t infonce_tc_smem_bytes(int C);
+                      float scale2, const InfoNcePlan& plan, InfoNcePartials out, int want_argmax, cudaStream_t s);
+int infonce_tc_tile_cols(int C);
 bool infonce_tc_built();
 
 }  // namespace rmcl

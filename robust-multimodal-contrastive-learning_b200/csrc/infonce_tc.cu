@@ -1,10 +1,481 @@
-// placeholder: tcgen05 path lands next
+// K1 partial stage, tcgen05 / TMEM / TMA version (bf16 queue, C in {64,128,256}).
+//
+// One CTA = 128 query rows x one contiguous range of queue columns, walked in tiles of TN columns
+// ("flash" online softmax over the queue axis; output format in infonce.cuh).  Per tile
+//     S  = Q^ . tile            tcgen05.mma  M128 x N=TN x K=C   A = Q^ (TMEM), B = tile (smem, MN-major)
+//     P  = 2^(S*scale - m)      128 softmax threads, one row each: tcgen05.ld -> ex2 -> bf16 -> st.shared (SW128)
+//     O += P . tile^T           tcgen05.mma  M128 x N=C  x K=TN  A = P  (smem, K-major), B = tile (smem, K-major)
+// The queue tile is staged ONCE by TMA (SWIZZLE_128B boxes of C rows x 64 columns) and serves as
+// the B operand of both GEMMs: the reference layout [C,K] with K contiguous (vilt_module.py:92)
+// is MN-major for the first and K-major for the second, so no transpose is ever materialised.
+//
+// Tensor memory (512 columns x 128 lanes):   [ Q^ : C/2 | O : C | S0 : TN | S1 : TN ]
+//   Q^ is bf16 packed two per column and is the A operand of every S GEMM, so shared memory holds
+//   only the TMA ring of queue tiles and a double-buffered P tile.  P deliberately does NOT alias
+//   its S buffer in tensor memory: tcgen05.mma instructions with different accumulators/shapes are
+//   not ordered against each other, and the S GEMM of tile i+2 was observed overwriting P(i) before
+//   the O GEMM of tile i had read it.  For the same reason no hazard is ever covered by a commit
+//   issued behind a *different* MMA group: every consumer waits on the commit placed directly
+//   behind the group that produces (or last reads) what it needs.
+// Warp roles (192 threads): warps 0-3 softmax + epilogue (TMEM lane quadrant = warp id),
+//   warp 4 TMA producer + TMEM allocator, warp 5 MMA issuer (one elected lane each).
+// Online softmax uses a lazily updated reference maximum: O and l are only rescaled when a row's
+// maximum grows by more than 2^8, which keeps the correction off the critical path while the final
+// (m, l, O) triple stays exact up to fp32 rounding.
+#include <cuda.h>
+
 #include "infonce.cuh"
+
 namespace rmcl {
-bool infonce_tc_built() { return false; }
-int infonce_tc_launch(const __nv_bfloat16*, const void*, int, int, long long, long long, float, const InfoNcePlan&,
-                      InfoNcePartials, cudaStream_t) {
-  set_error("tcgen05 InfoNCE not built");
+
+bool infonce_tc_built() { return true; }
+
+namespace {
+
+constexpr int kTcThreads = 192;
+constexpr int kTcRows = 128;
+constexpr int kSmemBudget = 224 * 1024;   // P double buffer + TMA ring (+1 KB alignment slack on top)
+constexpr float kRescaleThreshold = 8.f;  // log2 units
+
+// ------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a trap (CUDA error) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem descriptor]
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[smem descriptor] . B[smem descriptor]
+__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns <-> 32 registers per thread (lane i of the warp = TMEM lane base+i)
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+// Shared-memory matrix descriptor, SWIZZLE_128B (tcgen05 "version 1" format):
+//   [0,14) start>>4 | [16,30) leading byte offset>>4 | [32,46) stride byte offset>>4 | [46,48)=1 | [61,64)=2
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16: D fp32, A/B bf16, A K-major; b_mn_major selects B's major.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcBarriers {
+  uint64_t k_full[8];
+  uint64_t k_empty[8];
+  uint64_t s_full[2];
+  uint64_t p_full[2];
+  uint64_t o_done[2];   // o_done[i&1]: O GEMM of tile i has completed (committed directly behind it)
+  uint64_t q_full;
+  uint32_t tmem_base;
+};
+
+// ----------------------------------------------------------------------------------- kernel
+template <int C, int TN>
+__global__ void __launch_bounds__(kTcThreads, 1)
+    infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_queue, const __nv_bfloat16* __restrict__ q_hat, int B,
+                      long long K, float scale2, long long cols_per_split, int want_argmax, float* __restrict__ pm,
+                      float* __restrict__ pl, float* __restrict__ pav, int* __restrict__ pai, float* __restrict__ po) {
+  constexpr int kStageBytes = C * TN * 2;
+  constexpr int kBoxBytes = C * 128;            // one TMA box: C rows x 64 bf16 columns
+  constexpr int kBoxes = TN / 64;
+  constexpr int kPBytes = kBoxes * 16384;       // one P tile: 128 rows x TN bf16 as 128-byte-row boxes
+  constexpr int kStages = ((kSmemBudget - 2 * kPBytes) / kStageBytes) < 8 ? ((kSmemBudget - 2 * kPBytes) / kStageBytes) : 8;
+  constexpr uint32_t kTmQ = 0, kTmO = C / 2, kTmS = C / 2 + C;
+  static_assert(C / 2 + C + 2 * TN <= 512, "tensor memory budget");
+  static_assert(TN % 64 == 0 && C % 64 == 0 && C <= 256, "tile shape");
+  static_assert(kTcRows * (C + 1) * 4 <= kStages * kStageBytes, "epilogue staging must fit the ring");
+  constexpr uint32_t kIdescS = make_idesc(128, TN, 1);
+  constexpr uint32_t kIdescO = make_idesc(128, C, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ TcBarriers bars;
+  uint8_t* pbuf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ring = pbuf + 2 * kPBytes;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x;
+  const int row0 = blockIdx.y * kTcRows;
+  const long long k_begin = (long long)split * cols_per_split;
+  const long long k_end = (k_begin + cols_per_split < K) ? k_begin + cols_per_split : K;
+  const int n_tiles = (int)((k_end - k_begin + TN - 1) / TN);
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&bars.k_full[i], 1);
+      mbar_init(&bars.k_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.s_full[i], 1);
+      mbar_init(&bars.p_full[i], kTcRows);
+    }
+    mbar_init(&bars.o_done[0], 1);
+    mbar_init(&bars.o_done[1], 1);
+    mbar_init(&bars.q_full, kTcRows);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_queue) : "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars.tmem_base;
+
+  if (warp < 4) {
+    // =============================================================== softmax + epilogue warps
+    const int r = tid;                                    // row inside the block == TMEM lane
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    // ---- Q^ row -> tensor memory (bf16 pairs, element 2j in the low half of column j)
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(q_hat + (size_t)(row0 + r) * C);
+#pragma unroll
+      for (int ch = 0; ch < C / 64; ++ch) {
+        uint32_t w[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 v = __ldg(src + ch * 8 + i);
+          w[4 * i + 0] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+        tc_st32(tlane + kTmQ + ch * 32, w);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&bars.q_full);
+    }
+
+    float m_used = -INFINITY, l_run = 0.f, av_raw = -INFINITY;
+    int ai = 0;
+    for (int i = 0; i < n_tiles; ++i) {
+      const int b = i & 1;
+      const uint32_t ts = tlane + kTmS + b * TN;
+      mbar_wait(&bars.s_full[b], (i >> 1) & 1);
+      tc_fence_after();
+      uint32_t sv[TN];
+#pragma unroll
+      for (int ch = 0; ch < TN / 32; ++ch) tc_ld32(ts + ch * 32, sv + ch * 32);
+      tc_wait_ld();
+      const long long col0 = k_begin + (long long)i * TN;
+      if (col0 + TN > k_end) {  // ragged last tile: TMA zero-filled the columns past K
+        const int valid = (int)(k_end - col0);
+#pragma unroll
+        for (int j = 0; j < TN; ++j)
+          if (j >= valid) sv[j] = 0xff800000u;  // -inf
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) mx = fmaxf(mx, __uint_as_float(sv[j]));
+      if (want_argmax && mx > av_raw) {  // strict: the earliest tile keeps ties
+        av_raw = mx;
+        int idx = 0;
+#pragma unroll
+        for (int j = TN - 1; j >= 0; --j)
+          if (__uint_as_float(sv[j]) == mx) idx = j;
+        ai = (int)col0 + idx;
+      }
+      const float m_tile = mx * scale2;
+      const bool grow = (i > 0) && (m_tile > m_used + kRescaleThreshold);
+      if (i == 0) m_used = m_tile;
+      if (__any_sync(0xffffffffu, grow)) {
+        // rare: bring O and l of this warp's rows to the new reference maximum.  The O GEMM of the
+        // previous tile must have landed; the one of this tile cannot start before p_full below.
+        const float alpha = grow ? exp2f(m_used - m_tile) : 1.f;
+        if (grow) m_used = m_tile;
+        l_run *= alpha;
+        mbar_wait(&bars.o_done[(i - 1) & 1], ((i - 1) >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int ch = 0; ch < C / 32; ++ch) {
+          uint32_t o[32];
+          tc_ld32(tlane + kTmO + ch * 32, o);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+          tc_st32(tlane + kTmO + ch * 32, o);
+        }
+        tc_wait_st();
+      }
+      // ---- P = 2^(S*scale - m) as bf16 pairs, row sum in fp32
+      const float neg_m = -m_used;
+      float lsum = 0.f;
+      uint32_t pw[TN / 2];
+#pragma unroll
+      for (int j = 0; j < TN / 2; ++j) {
+        const float p0 = exp2f(fmaf(__uint_as_float(sv[2 * j]), scale2, neg_m));
+        const float p1 = exp2f(fmaf(__uint_as_float(sv[2 * j + 1]), scale2, neg_m));
+        lsum += p0 + p1;
+        const __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
+        pw[j] = *reinterpret_cast<const uint32_t*>(&pk);
+      }
+      l_run += lsum;
+      // P buffer b was last read by the O GEMM of tile i-2.  That GEMM's own commit is the only
+      // thing that may be trusted here: the s_full commit behind the (later issued) S GEMM of tile i
+      // does NOT imply it has finished — MMAs with different accumulators overlap and complete out
+      // of order (observed on B200: fast warps overwrote P while the O GEMM was still reading it).
+      if (i >= 2) mbar_wait(&bars.o_done[b], ((i - 2) >> 1) & 1);
+      // row r of P in the K-major SWIZZLE_128B layout: 16-byte chunk c of a 128-byte row lands at c ^ (r & 7)
+      {
+        uint8_t* prow = pbuf + b * kPBytes + r * 128;
+#pragma unroll
+        for (int c = 0; c < TN / 8; ++c) {
+          uint8_t* dst = prow + (c >> 3) * 16384 + (((c & 7) ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(dst) = make_uint4(pw[4 * c], pw[4 * c + 1], pw[4 * c + 2], pw[4 * c + 3]);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core reads
+      tc_fence_before();                                             // S[b] has been read: it may be overwritten
+      mbar_arrive(&bars.p_full[b]);
+    }
+
+    // ---- epilogue: statistics, then O through padded shared memory to coalesced global stores
+    if (n_tiles >= 2) mbar_wait(&bars.o_done[(n_tiles - 2) & 1], ((n_tiles - 2) >> 1) & 1);
+    mbar_wait(&bars.o_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
+    tc_fence_after();
+    const bool row_ok = (row0 + r) < B;
+    if (row_ok) {
+      const size_t o = (size_t)split * B + row0 + r;
+      pm[o] = m_used;
+      pl[o] = l_run;
+      pav[o] = av_raw * scale2;
+      pai[o] = ai;
+    }
+    float* stage = reinterpret_cast<float*>(ring);  // [128][C+1]; every TMA write has been consumed
+#pragma unroll 1
+    for (int ch = 0; ch < C / 32; ++ch) {
+      uint32_t o[32];
+      tc_ld32(tlane + kTmO + ch * 32, o);
+      tc_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) stage[r * (C + 1) + ch * 32 + j] = __uint_as_float(o[j]);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int rr = warp; rr < kTcRows; rr += 4) {
+      if (row0 + rr >= B) break;
+      float* dst = po + ((size_t)split * B + row0 + rr) * C;
+#pragma unroll
+      for (int c = lane; c < C; c += 32) dst[c] = stage[rr * (C + 1) + c];
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // ========================================================================= TMA producer
+    if (lane == 0) {
+      for (int i = 0; i < n_tiles; ++i) {
+        const int st = i % kStages;
+        mbar_wait(&bars.k_empty[st], ((i / kStages) & 1) ^ 1);
+        mbar_expect_tx(&bars.k_full[st], kStageBytes);
+        const long long col0 = k_begin + (long long)i * TN;
+#pragma unroll
+        for (int bx = 0; bx < kBoxes; ++bx)
+          tma_load_2d(ring + (size_t)st * kStageBytes + (size_t)bx * kBoxBytes, &tmap_queue, &bars.k_full[st],
+                      (int)(col0 + bx * 64), 0);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================================================================== MMA issuer
+    if (lane == 0) {
+      mbar_wait(&bars.q_full, 0);
+      tc_fence_after();
+      auto issue_s = [&](int i) {
+        const int st = i % kStages;
+        mbar_wait(&bars.k_full[st], (i / kStages) & 1);
+        tc_fence_after();
+        const uint32_t sbase = smem_u32(ring + (size_t)st * kStageBytes);
+        const uint32_t d = tmem + kTmS + (i & 1) * TN;
+#pragma unroll
+        for (int s = 0; s < C / 16; ++s) {
+          // B = tile as [N=TN columns][K=16 rows of C], MN-major: 8-row groups 1024 B apart,
+          // 64-column boxes kBoxBytes apart
+          const uint64_t bd = make_sw128_desc(sbase + s * 2048, kBoxBytes, 1024);
+          tc_mma_ts(d, tmem + kTmQ + s * 8, bd, kIdescS, s > 0);
+        }
+        tc_commit(&bars.s_full[i & 1]);
+      };
+      issue_s(0);
+      for (int i = 0; i < n_tiles; ++i) {
+        if (i + 1 < n_tiles) issue_s(i + 1);
+        mbar_wait(&bars.p_full[i & 1], (i >> 1) & 1);
+        tc_fence_after();
+        const int st = i % kStages;
+        const uint32_t sbase = smem_u32(ring + (size_t)st * kStageBytes);
+        const uint32_t pa = smem_u32(pbuf + (i & 1) * kPBytes);
+#pragma unroll
+        for (int s = 0; s < TN / 16; ++s) {
+          // A = P as [M=128 rows][K=16 columns], B = tile as [N=C rows][K=16 columns]; both K-major:
+          // rows 128 B apart, 8-row groups 1024 B apart, 16 columns = 32 B inside the swizzled row
+          const uint64_t ad = make_sw128_desc(pa + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024);
+          const uint64_t bd = make_sw128_desc(sbase + (s >> 2) * kBoxBytes + (s & 3) * 32, 16, 1024);
+          tc_mma_ss(tmem + kTmO, ad, bd, kIdescO, (i > 0 || s > 0) ? 1u : 0u);
+        }
+        tc_commit(&bars.k_empty[st]);
+        tc_commit(&bars.o_done[i & 1]);
+      }
+    }
+    __syncwarp();
+  }
+
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+template <int C, int TN>
+int launch_tc(const __nv_bfloat16* q_hat, const void* queue, int B, long long K, long long ldq, float scale2,
+              const InfoNcePlan& p, InfoNcePartials out, int want_argmax, cudaStream_t s) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return RMCL_E_CUDA;
+  }
+  alignas(64) CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)C};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ldq * 2};
+  const cuuint32_t box[2] = {64, (cuuint32_t)C};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(queue), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (C=%d K=%lld ldq=%lld)", (int)cr, C, K, ldq);
+    return RMCL_E_CUDA;
+  }
+  constexpr int kStageBytes = C * TN * 2;
+  constexpr int kPBytes = (TN / 64) * 16384;
+  constexpr int kStages = ((kSmemBudget - 2 * kPBytes) / kStageBytes) < 8 ? ((kSmemBudget - 2 * kPBytes) / kStageBytes) : 8;
+  const size_t smem = (size_t)kStages * kStageBytes + 2 * kPBytes + 1024;
+  auto kern = infonce_tc_kernel<C, TN>;
+  RMCL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(p.splits, p.row_blocks);
+  kern<<<grid, kTcThreads, smem, s>>>(tmap, q_hat, B, K, scale2, p.cols_per_split, want_argmax, out.m, out.l, out.av,
+                                      out.ai, out.o);
+  RMCL_LAUNCH_OK("infonce_tc_kernel");
+  return RMCL_OK;
+}
+
+}  // namespace
+
+int infonce_tc_tile_cols(int C) { return C == 256 ? 64 : 128; }
+
+int infonce_tc_launch(const __nv_bfloat16* q_hat, const void* queue, int B, int C, long long K, long long ldq,
+                      float scale2, const InfoNcePlan& p, InfoNcePartials out, int want_argmax, cudaStream_t s) {
+  if (p.row_blocks > 65535) {
+    set_error("InfoNCE: too many rows (%d)", B);
+    return RMCL_E_UNSUPPORTED_DIM;
+  }
+  switch (C) {
+    case 256: return launch_tc<256, 64>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s);
+    case 128: return launch_tc<128, 128>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s);
+    case 64: return launch_tc<64, 128>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s);
+  }
+  set_error("tcgen05 InfoNCE supports C in {64,128,256} (got %d)", C);
   return RMCL_E_UNSUPPORTED_DIM;
 }
+
 }  // namespace rmcl

@@ -336,3 +336,89 @@ def test_cpu_tensors_raise(ops):
         ops.pgd_step_(torch.zeros(2, 4), torch.zeros(2, 4), 0.1, 0.1)
     with pytest.raises(RuntimeError):
         ops.infonce_fwd_bwd(torch.zeros(2, 4), torch.zeros(2, 4), torch.zeros(4, 8), 0.07)
+
+
+# ================================================================ InfoNCE, tcgen05 path
+def _bf16_oracle(q, k, queue, T, grad_out=1.0):
+    """float64 oracle fed the operands the bf16 path sees: q^ and k^ rounded to bf16 before the
+    dot products (autocast semantics), bf16 queue, exact accumulation."""
+    qh = O.l2_normalize(q.double())
+    qh16 = qh.float().bfloat16().double()
+    k16 = k.float().bfloat16().double()
+    qd = queue.double()
+    logits = torch.cat([(qh16 * k16).sum(1, keepdim=True), qh16 @ qd], dim=1) / T
+    lse = torch.logsumexp(logits, 1)
+    p = torch.exp(logits - lse[:, None])
+    B = q.shape[0]
+    dqh = (p[:, 1:] @ qd.T + (p[:, :1] - 1) * k16) / (T * B) * grad_out
+    n = q.double().norm(dim=1, keepdim=True).clamp_min(1e-12)
+    dq = (dqh - qh * (qh * dqh).sum(1, keepdim=True)) / n
+    return {"logits": logits, "lse": lse, "pos": logits[:, 0], "loss_per_row": lse - logits[:, 0],
+            "loss": (lse - logits[:, 0]).mean(), "dq": dq, "argmax": logits.argmax(1)}
+
+
+TC_SHAPES = [(128, 128, 1024), (256, 256, 4096), (128, 64, 2048), (8, 128, 4096), (200, 256, 8192),
+             (128, 128, 1000), (64, 256, 520), (130, 64, 136), (256, 256, 65536), (128, 128, 65536),
+             (512, 128, 16384), (1, 128, 8)]
+
+
+@pytest.mark.parametrize("B,C,K", TC_SHAPES)
+@pytest.mark.parametrize("normalized_queue", [True, False])
+def test_infonce_tcgen05_vs_oracle(ops, B, C, K, normalized_queue):
+    q, k, queue = _infonce_inputs(B, C, K, seed=B + C + K, queue_dtype=torch.bfloat16, normalized_queue=normalized_queue)
+    ref = _bf16_oracle(q, k, queue, 0.07)
+    res = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.to(DEV), 0.07, path="tcgen05")
+    torch.cuda.synchronize()
+    assert rel_err(res["lse"], ref["lse"]) < BF16_RTOL
+    assert rel_err(res["loss"], ref["loss"]) < BF16_RTOL
+    assert (res["loss_per_row"].double().cpu() - ref["loss_per_row"]).abs().max() < BF16_RTOL * ref["logits"].abs().max()
+    assert rel_err(res["dq"], ref["dq"]) < BF16_RTOL
+    # tighter: the only deviations from the oracle are fp32 accumulation and P rounded to bf16
+    assert rel_err(res["lse"], ref["lse"]) < 1e-4
+    assert rel_err(res["dq"], ref["dq"]) < 1e-2
+    top2 = ref["logits"].topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-3
+    assert torch.equal(res["argmax"].cpu()[clear], ref["argmax"][clear])
+
+
+@pytest.mark.parametrize("C", [64, 128, 256])
+def test_infonce_tcgen05_matches_simt_path(ops, C):
+    """Both device paths write the same partial format; on identical bf16 operands they must agree
+    far inside the bf16 tolerance (the SIMT path keeps P in fp32)."""
+    q, k, queue = _infonce_inputs(96, C, 3000 // 8 * 8, seed=C, queue_dtype=torch.bfloat16)
+    a = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.to(DEV), 0.07, path="simt")
+    b = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.to(DEV), 0.07, path="tcgen05")
+    assert rel_err(b["lse"], a["lse"]) < 1e-5
+    assert rel_err(b["loss"], a["loss"]) < 1e-5
+    assert rel_err(b["dq"], a["dq"]) < 1e-2
+    assert rel_err(b["dk"], a["dk"]) < 1e-2
+
+
+@pytest.mark.parametrize("B,C,K", [(1024, 128, 8192), (2048, 256, 4096), (1024, 64, 16384)])
+def test_infonce_tcgen05_growing_maximum(ops, B, C, K):
+    """Columns ordered so that every tile raises the row maximum by far more than the lazy-rescale
+    threshold; B is large so that each CTA owns several tiles (few splits) and the O/l correction
+    path runs on every one of them."""
+    g = torch.Generator().manual_seed(11)
+    q = torch.randn(B, C, generator=g)
+    k = torch.nn.functional.normalize(torch.randn(B, C, generator=g), dim=1)
+    base = torch.nn.functional.normalize(torch.randn(C, K, generator=g), dim=0)
+    ramp = torch.linspace(0.05, 3.0, K)[None, :]        # later columns are longer -> larger |logits|
+    qbar = torch.nn.functional.normalize(q, dim=1).mean(0)
+    queue = ((base + 0.5 * qbar[:, None]) * ramp).bfloat16()
+    ref = _bf16_oracle(q, k, queue, 0.07)
+    res = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.to(DEV), 0.07, path="tcgen05")
+    assert rel_err(res["lse"], ref["lse"]) < 1e-4
+    assert rel_err(res["dq"], ref["dq"]) < 1e-2
+
+
+def test_infonce_tcgen05_strided_queue_and_auto_dispatch(ops):
+    B, C, K = 64, 128, 2048
+    q, k, queue = _infonce_inputs(B, C, K + 64, seed=3, queue_dtype=torch.bfloat16)
+    view = queue.to(DEV)[:, :K]                       # ldq = K + 64
+    ref = _bf16_oracle(q, k, queue[:, :K], 0.07)
+    res = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), view, 0.07, path="auto")
+    assert rel_err(res["lse"], ref["lse"]) < 1e-4 and rel_err(res["dq"], ref["dq"]) < 1e-2
+    from rmcl_b200._lib import RmclError
+    with pytest.raises(RmclError):                     # fp32 queue cannot take the tcgen05 path
+        ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.float().to(DEV), 0.07, path="tcgen05")
