@@ -347,6 +347,30 @@ def run_cuda(args):
             ach, peak, unit = work / t / 1e12, pk_peak["tf_sust"], "TFLOP/s"
         kernels[name] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                          "ms": kern_ms[name], "traffic": traffic.get(name)}
+    # ---- cfg3: the PGD update kernel alone (not part of the cfg2 step): B=128, 5 steps, pixel and
+    #      embedding perturbations; 12 B/element (read g, read delta, write delta)
+    if world == 1 and not args.no_pgd:
+        for tag, shape, mode, lr, eps in (("pgd_pixel_ref_linf", (128, 3, 384, 384), "ref_linf", 0.05, 8 / 255),
+                                          ("pgd_pixel_l2", (128, 3, 384, 384), "l2", 0.5, 1.0),
+                                          ("pgd_embed_ref_linf", (128, 185, 768), "ref_linf", 0.05, 8 / 255),
+                                          ("pgd_embed_sign_linf", (128, 185, 768), "sign_linf", 2 / 255, 8 / 255)):
+            grad = torch.randn(shape, device=dev, generator=g)
+            delta = torch.zeros(shape, device=dev)
+            for _ in range(3):
+                ops.pgd_step_(delta, grad, lr, eps, mode)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                ops.pgd_step_(delta, grad, lr, eps, mode)
+            e1.record()
+            torch.cuda.synchronize()
+            t = e0.elapsed_time(e1) / 5 * 1e-3
+            nbytes = 12.0 * grad.numel()
+            kernels[tag] = {"bound": "hbm", "achieved": nbytes / t / 1e9, "peak": pk_peak["hbm"], "unit": "GB/s",
+                            "frac": nbytes / t / 1e9 / pk_peak["hbm"], "ms": t * 1e3, "traffic": traffic.get(tag),
+                            "shape": list(shape)}
+            del grad, delta
     for name in ("infonce_prep", "infonce_finalize"):
         kernels[name] = {"ms": kern_ms[name]}
     dominant = max(alg, key=lambda n: kern_ms[n])
@@ -385,6 +409,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--path", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pgd", action="store_true", help="skip the cfg3 PGD-kernel roofline lines")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

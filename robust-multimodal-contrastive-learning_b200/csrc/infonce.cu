@@ -205,8 +205,19 @@ __global__ void __launch_bounds__(256) infonce_finalize_kernel(
       dqh[i] = 0.f;
       qh[i] = 0.f;
       if (c < C) {
+        // 8 independent loads in flight per thread: the merge is a pure stream over the partials
+        const float* pcol = po + (size_t)row * C + c;
+        const size_t sstride = (size_t)B * C;
         float acc = 0.f;
-        for (int s = 0; s < splits; ++s) acc = fmaf(po[((size_t)s * B + row) * C + c], sw[s], acc);
+        int s = 0;
+        for (; s + 8 <= splits; s += 8) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = __ldcs(pcol + (size_t)(s + u) * sstride);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc = fmaf(v[u], sw[s + u], acc);
+        }
+        for (; s < splits; ++s) acc = fmaf(__ldcs(pcol + (size_t)s * sstride), sw[s], acc);
         const float kh = round_if(k_hat[(size_t)row * C + c], bf16_mode);
         qh[i] = q_hat[(size_t)row * C + c];
         dqh[i] = gs * fmaf(acc, o_scale, pm1 * kh);

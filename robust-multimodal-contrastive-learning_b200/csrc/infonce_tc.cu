@@ -20,8 +20,9 @@
 // Warp roles (192 threads): warps 0-3 softmax + epilogue (TMEM lane quadrant = warp id),
 //   warp 4 TMA producer + TMEM allocator, warp 5 MMA issuer (one elected lane each).
 // Online softmax uses a lazily updated reference maximum: O and l are only rescaled when a row's
-// maximum grows by more than 2^8, which keeps the correction off the critical path while the final
-// (m, l, O) triple stays exact up to fp32 rounding.
+// maximum grows by more than 2^40 (everything is floating point, so a stale reference costs no
+// precision until it threatens overflow), which keeps the correction off the critical path while
+// the final (m, l, O) triple stays exact up to fp32 rounding.
 #include <cuda.h>
 
 #include "infonce.cuh"
@@ -35,7 +36,7 @@ namespace {
 constexpr int kTcThreads = 192;
 constexpr int kTcRows = 128;
 constexpr int kSmemBudget = 224 * 1024;   // P double buffer + TMA ring (+1 KB alignment slack on top)
-constexpr float kRescaleThreshold = 8.f;  // log2 units
+constexpr float kRescaleThreshold = 40.f;  // log2 units: P <= 2^40, far inside bf16/fp32 range
 
 // ------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -128,6 +129,28 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 
+// One lane of a converged warp.  Issuing tcgen05/TMA instructions under an `elect.sync` predicate
+// (rather than `lane == 0`) lets ptxas emit them straight-line; under an ordinary divergent branch
+// it wraps every UTCHMMA in an ELECT/branch loop that cost ~70 cycles per MMA here.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ float ex2_ftz(float x) {  // one MUFU.EX2: arguments are <= 40, -inf/underflow -> 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void bulk_store_row(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+
 // Shared-memory matrix descriptor, SWIZZLE_128B (tcgen05 "version 1" format):
 //   [0,14) start>>4 | [16,30) leading byte offset>>4 | [32,46) stride byte offset>>4 | [46,48)=1 | [61,64)=2
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -168,7 +191,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   constexpr uint32_t kTmQ = 0, kTmO = C / 2, kTmS = C / 2 + C;
   static_assert(C / 2 + C + 2 * TN <= 512, "tensor memory budget");
   static_assert(TN % 64 == 0 && C % 64 == 0 && C <= 256, "tile shape");
-  static_assert(kTcRows * (C + 1) * 4 <= kStages * kStageBytes, "epilogue staging must fit the ring");
+  static_assert(kTcRows * (C + 4) * 4 <= kStages * kStageBytes, "epilogue staging must fit the ring");
   constexpr uint32_t kIdescS = make_idesc(128, TN, 1);
   constexpr uint32_t kIdescO = make_idesc(128, C, 0);
 
@@ -214,17 +237,29 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // =============================================================== softmax + epilogue warps
     const int r = tid;                                    // row inside the block == TMEM lane
     const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
-    // ---- Q^ row -> tensor memory (bf16 pairs, element 2j in the low half of column j)
+    // ---- Q^ rows -> tensor memory (bf16 pairs, element 2j in the low half of column j).
+    // Coalesced global loads (8 lanes cover one 128-byte row segment), transposed through this
+    // warp's 4 KB of the (still unused) P buffer with the same 16-byte XOR swizzle that keeps both
+    // the row-segment writes and the one-row-per-lane reads bank-conflict free.
     {
-      const uint4* src = reinterpret_cast<const uint4*>(q_hat + (size_t)(row0 + r) * C);
+      uint8_t* scratch = pbuf + warp * 4096;
+      const __nv_bfloat16* qw = q_hat + (size_t)(row0 + warp * 32) * C;
 #pragma unroll
       for (int ch = 0; ch < C / 64; ++ch) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int rr = 4 * j + (lane >> 3), pc = lane & 7;
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(qw + (size_t)rr * C + ch * 64) + pc);
+          *reinterpret_cast<uint4*>(scratch + rr * 128 + ((pc ^ (rr & 7)) << 4)) = v;
+        }
+        __syncwarp();
         uint32_t w[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint4 v = __ldg(src + ch * 8 + i);
-          w[4 * i + 0] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        for (int pc = 0; pc < 8; ++pc) {
+          const uint4 v = *reinterpret_cast<const uint4*>(scratch + lane * 128 + ((pc ^ (lane & 7)) << 4));
+          w[4 * pc + 0] = v.x; w[4 * pc + 1] = v.y; w[4 * pc + 2] = v.z; w[4 * pc + 3] = v.w;
         }
+        __syncwarp();
         tc_st32(tlane + kTmQ + ch * 32, w);
       }
       tc_wait_st();
@@ -285,17 +320,17 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       }
       // ---- P = 2^(S*scale - m) as bf16 pairs, row sum in fp32
       const float neg_m = -m_used;
-      float lsum = 0.f;
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};   // independent partial sums: no 64-deep dependent add chain
       uint32_t pw[TN / 2];
 #pragma unroll
       for (int j = 0; j < TN / 2; ++j) {
-        const float p0 = exp2f(fmaf(__uint_as_float(sv[2 * j]), scale2, neg_m));
-        const float p1 = exp2f(fmaf(__uint_as_float(sv[2 * j + 1]), scale2, neg_m));
-        lsum += p0 + p1;
+        const float p0 = ex2_ftz(fmaf(__uint_as_float(sv[2 * j]), scale2, neg_m));
+        const float p1 = ex2_ftz(fmaf(__uint_as_float(sv[2 * j + 1]), scale2, neg_m));
+        ls[j & 3] += p0 + p1;
         const __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
         pw[j] = *reinterpret_cast<const uint32_t*>(&pk);
       }
-      l_run += lsum;
+      l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       // P buffer b was last read by the O GEMM of tile i-2.  That GEMM's own commit is the only
       // thing that may be trusted here: the s_full commit behind the (later issued) S GEMM of tile i
       // does NOT imply it has finished — MMAs with different accumulators overlap and complete out
@@ -315,7 +350,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       mbar_arrive(&bars.p_full[b]);
     }
 
-    // ---- epilogue: statistics, then O through padded shared memory to coalesced global stores
+    // ---- epilogue: statistics, then O
     if (n_tiles >= 2) mbar_wait(&bars.o_done[(n_tiles - 2) & 1], ((n_tiles - 2) >> 1) & 1);
     mbar_wait(&bars.o_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
     tc_fence_after();
@@ -327,29 +362,32 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       pav[o] = av_raw * scale2;
       pai[o] = ai;
     }
-    float* stage = reinterpret_cast<float*>(ring);  // [128][C+1]; every TMA write has been consumed
+    // O row r: tensor memory -> this thread's own staging row (16-byte chunks, row stride C+4 floats
+    // keeps the 128-bit stores bank-conflict free) -> one bulk async copy per row to global.  No
+    // cross-thread synchronisation: every thread stores exactly what it staged.
+    float* stage = reinterpret_cast<float*>(ring) + (size_t)r * (C + 4);   // every TMA write has been consumed
 #pragma unroll 1
     for (int ch = 0; ch < C / 32; ++ch) {
       uint32_t o[32];
       tc_ld32(tlane + kTmO + ch * 32, o);
       tc_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) stage[r * (C + 1) + ch * 32 + j] = __uint_as_float(o[j]);
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(stage + ch * 32 + 4 * j) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    for (int rr = warp; rr < kTcRows; rr += 4) {
-      if (row0 + rr >= B) break;
-      float* dst = po + ((size_t)split * B + row0 + rr) * C;
-#pragma unroll
-      for (int c = lane; c < C; c += 32) dst[c] = stage[rr * (C + 1) + c];
+    if (row_ok) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      bulk_store_row(po + ((size_t)split * B + row0 + r) * C, stage, C * 4);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     tc_fence_before();
   } else if (warp == 4) {
     // ========================================================================= TMA producer
-    if (lane == 0) {
-      for (int i = 0; i < n_tiles; ++i) {
-        const int st = i % kStages;
-        mbar_wait(&bars.k_empty[st], ((i / kStages) & 1) ^ 1);
+    for (int i = 0; i < n_tiles; ++i) {
+      const int st = i % kStages;
+      mbar_wait(&bars.k_empty[st], ((i / kStages) & 1) ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&bars.k_full[st], kStageBytes);
         const long long col0 = k_begin + (long long)i * TN;
 #pragma unroll
@@ -357,17 +395,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           tma_load_2d(ring + (size_t)st * kStageBytes + (size_t)bx * kBoxBytes, &tmap_queue, &bars.k_full[st],
                       (int)(col0 + bx * 64), 0);
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // =========================================================================== MMA issuer
-    if (lane == 0) {
-      mbar_wait(&bars.q_full, 0);
+    // The whole warp walks the protocol (waits are warp-uniform); one elected lane issues.
+    mbar_wait(&bars.q_full, 0);
+    tc_fence_after();
+    auto issue_s = [&](int i) {
+      const int st = i % kStages;
+      mbar_wait(&bars.k_full[st], (i / kStages) & 1);
       tc_fence_after();
-      auto issue_s = [&](int i) {
-        const int st = i % kStages;
-        mbar_wait(&bars.k_full[st], (i / kStages) & 1);
-        tc_fence_after();
+      if (elect_one()) {
         const uint32_t sbase = smem_u32(ring + (size_t)st * kStageBytes);
         const uint32_t d = tmem + kTmS + (i & 1) * TN;
 #pragma unroll
@@ -378,12 +417,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           tc_mma_ts(d, tmem + kTmQ + s * 8, bd, kIdescS, s > 0);
         }
         tc_commit(&bars.s_full[i & 1]);
-      };
-      issue_s(0);
-      for (int i = 0; i < n_tiles; ++i) {
-        if (i + 1 < n_tiles) issue_s(i + 1);
-        mbar_wait(&bars.p_full[i & 1], (i >> 1) & 1);
-        tc_fence_after();
+      }
+      __syncwarp();
+    };
+    issue_s(0);
+    for (int i = 0; i < n_tiles; ++i) {
+      if (i + 1 < n_tiles) issue_s(i + 1);
+      mbar_wait(&bars.p_full[i & 1], (i >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
         const int st = i % kStages;
         const uint32_t sbase = smem_u32(ring + (size_t)st * kStageBytes);
         const uint32_t pa = smem_u32(pbuf + (i & 1) * kPBytes);
@@ -398,8 +440,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         tc_commit(&bars.k_empty[st]);
         tc_commit(&bars.o_done[i & 1]);
       }
+      __syncwarp();
     }
-    __syncwarp();
   }
 
   __syncthreads();

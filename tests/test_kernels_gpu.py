@@ -241,7 +241,9 @@ def _check_infonce(res, ref, rtol, B, fp32_ref=False):
         assert ((a - b).abs().max() <= rtol * b.abs().max() + slack), (name, a, b)
     assert rel_err(res["lse"], ref["lse"]) < rtol
     assert (res["pos"].double().cpu() - ref["pos"].double()).abs().max().item() < rtol * ref["logits"].abs().max().item()
-    assert rel_err(res["dq"], ref["dq"]) < rtol
+    # the same cancellation (p_pos - 1 with p_pos -> 1) costs an fp32 reference up to ~1e-4 of its own
+    # gradient; the strict bar applies against the float64 oracle, the fp32 one gets 2x
+    assert rel_err(res["dq"], ref["dq"]) < (2 * rtol if fp32_ref else rtol)
 
 
 @pytest.mark.parametrize("B,C,K", [(8, 128, 4096), (4, 16, 64), (1, 2, 1), (3, 5, 7), (16, 128, 1000), (33, 96, 333),
