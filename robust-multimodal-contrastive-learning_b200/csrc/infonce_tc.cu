@@ -17,8 +17,9 @@
 //   the O GEMM of tile i had read it.  For the same reason no hazard is ever covered by a commit
 //   issued behind a *different* MMA group: every consumer waits on the commit placed directly
 //   behind the group that produces (or last reads) what it needs.
-// Warp roles (192 threads): warps 0-3 softmax + epilogue (TMEM lane quadrant = warp id),
-//   warp 4 TMA producer + TMEM allocator, warp 5 MMA issuer (one elected lane each).
+// Warp roles (320 threads): warps 0-7 softmax + epilogue (TMEM lane quadrant = warp % 4; warp w
+//   owns the even tiles, warp w+4 the odd tiles of the same 32 rows), warp 8 TMA producer + TMEM
+//   allocator, warp 9 MMA issuer (one elected lane each).
 // Online softmax uses a lazily updated reference maximum: O and l are only rescaled when a row's
 // maximum grows by more than 2^40 (everything is floating point, so a stale reference costs no
 // precision until it threatens overflow), which keeps the correction off the critical path while
@@ -33,9 +34,11 @@ bool infonce_tc_built() { return true; }
 
 namespace {
 
-constexpr int kTcThreads = 192;
+constexpr int kSoftmaxWarps = 8;   // warps w and w+4 share TMEM lane quadrant w and alternate tiles
+constexpr int kTmaWarp = 8, kMmaWarp = 9;
+constexpr int kTcThreads = 320;
 constexpr int kTcRows = 128;
-constexpr int kSmemBudget = 224 * 1024;   // P double buffer + TMA ring (+1 KB alignment slack on top)
+constexpr int kSmemBudget = 208 * 1024;   // P double buffer + TMA ring; leaves room for alignment slack + static smem
 constexpr float kRescaleThreshold = 40.f;  // log2 units: P <= 2^40, far inside bf16/fp32 range
 
 // ------------------------------------------------------------------------------- PTX wrappers
@@ -167,15 +170,28 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int b_mn_major) 
          ((uint32_t)(M >> 4) << 24);
 }
 
-struct TcBarriers {
+struct TcShared {
   uint64_t k_full[8];
   uint64_t k_empty[8];
-  uint64_t s_full[2];
-  uint64_t p_full[2];
+  uint64_t s_full[2];   // S GEMM of a tile has landed in S[b]
+  uint64_t s_free[2];   // S[b] is in registers: the S GEMM two tiles ahead may overwrite it
+  uint64_t p_full[2];   // P[b] is in shared memory: the O GEMM of the tile may start
   uint64_t o_done[2];   // o_done[i&1]: O GEMM of tile i has completed (committed directly behind it)
   uint64_t q_full;
   uint32_t tmem_base;
+  float m_ref[kTcRows];        // reference maximum (log2 units) of the O accumulator row
+  float xm[kTcRows];           // end of kernel: odd-tile warps hand (m, l, argmax) to the even-tile warps
+  float xl[kTcRows];
+  float xav[kTcRows];
+  int xai[kTcRows];
 };
+
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t n) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
 
 // ----------------------------------------------------------------------------------- kernel
 template <int C, int TN>
@@ -189,14 +205,17 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   constexpr int kPBytes = kBoxes * 16384;       // one P tile: 128 rows x TN bf16 as 128-byte-row boxes
   constexpr int kStages = ((kSmemBudget - 2 * kPBytes) / kStageBytes) < 8 ? ((kSmemBudget - 2 * kPBytes) / kStageBytes) : 8;
   constexpr uint32_t kTmQ = 0, kTmO = C / 2, kTmS = C / 2 + C;
+  constexpr int HC = C / 2;                     // O columns per thread in the epilogue
   static_assert(C / 2 + C + 2 * TN <= 512, "tensor memory budget");
   static_assert(TN % 64 == 0 && C % 64 == 0 && C <= 256, "tile shape");
+  static_assert(kStages >= 4, "three tiles are live (S GEMM runs two ahead of the O GEMM) plus one in flight");
   static_assert(kTcRows * (C + 4) * 4 <= kStages * kStageBytes, "epilogue staging must fit the ring");
+  static_assert(2 * kPBytes >= kSoftmaxWarps * 4096, "Q^ transpose scratch lives in the P buffers");
   constexpr uint32_t kIdescS = make_idesc(128, TN, 1);
   constexpr uint32_t kIdescO = make_idesc(128, C, 0);
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ TcBarriers bars;
+  __shared__ TcShared sh;
   uint8_t* pbuf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = pbuf + 2 * kPBytes;
 
@@ -209,21 +228,21 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&bars.k_full[i], 1);
-      mbar_init(&bars.k_empty[i], 1);
+      mbar_init(&sh.k_full[i], 1);
+      mbar_init(&sh.k_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bars.s_full[i], 1);
-      mbar_init(&bars.p_full[i], kTcRows);
+      mbar_init(&sh.s_full[i], 1);
+      mbar_init(&sh.s_free[i], kTcRows);
+      mbar_init(&sh.p_full[i], kTcRows);
+      mbar_init(&sh.o_done[i], 1);
     }
-    mbar_init(&bars.o_done[0], 1);
-    mbar_init(&bars.o_done[1], 1);
-    mbar_init(&bars.q_full, kTcRows);
+    mbar_init(&sh.q_full, kSoftmaxWarps * 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_queue) : "memory");
   }
-  if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars.tmem_base)),
+  if (warp == kTmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh.tmem_base)),
                  "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -231,53 +250,81 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = bars.tmem_base;
+  const uint32_t tmem = sh.tmem_base;
 
-  if (warp < 4) {
+  if (warp < kSoftmaxWarps) {
     // =============================================================== softmax + epilogue warps
-    const int r = tid;                                    // row inside the block == TMEM lane
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    // Two warps per row quadrant (a warp may only touch TMEM lanes 32*(w%4)..+31): warp w owns the
+    // even tiles of rows 32w..32w+31, warp w+4 the odd tiles, so the two work half a period out of
+    // phase — one is in its MUFU-bound exponential while the other waits on barriers / moves data —
+    // and each has two tile periods to finish one tile.  They share the O accumulator, hence one
+    // reference maximum per row (sh.m_ref); rescale decisions are taken strictly in tile order
+    // through a named-barrier handshake between the two warps (ids 1..8).
+    const int quad = warp & 3, par = warp >> 2;
+    const int r = quad * 32 + lane;                       // row inside the block == TMEM lane
+    const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
+    const uint32_t dec_mine = 1 + quad * 2 + par;         // "decision of one of my tiles is published"
+    const uint32_t dec_other = 1 + quad * 2 + (par ^ 1);
+
     // ---- Q^ rows -> tensor memory (bf16 pairs, element 2j in the low half of column j).
-    // Coalesced global loads (8 lanes cover one 128-byte row segment), transposed through this
-    // warp's 4 KB of the (still unused) P buffer with the same 16-byte XOR swizzle that keeps both
-    // the row-segment writes and the one-row-per-lane reads bank-conflict free.
+    // Coalesced global loads (8 lanes cover one 128-byte row segment), all issued before the first
+    // use, transposed through this warp's 4 KB of the (still unused) P buffers with the same
+    // 16-byte XOR swizzle that keeps the segment writes and the row-per-lane reads conflict free.
     {
+      constexpr int kChunks = C / 64;                     // 64-column chunks of a row
+      constexpr int kMine = (kChunks + 1) / 2;            // chunks handled by this warp: ch = 2*t + par
       uint8_t* scratch = pbuf + warp * 4096;
-      const __nv_bfloat16* qw = q_hat + (size_t)(row0 + warp * 32) * C;
+      const __nv_bfloat16* qw = q_hat + (size_t)(row0 + quad * 32) * C;
+      uint4 v[kMine][8];
 #pragma unroll
-      for (int ch = 0; ch < C / 64; ++ch) {
+      for (int t = 0; t < kMine; ++t) {
+        const int ch = 2 * t + par;
+        if (ch < kChunks) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int rr = 4 * j + (lane >> 3), pc = lane & 7;
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(qw + (size_t)rr * C + ch * 64) + pc);
-          *reinterpret_cast<uint4*>(scratch + rr * 128 + ((pc ^ (rr & 7)) << 4)) = v;
+          for (int j = 0; j < 8; ++j)
+            v[t][j] = __ldg(reinterpret_cast<const uint4*>(qw + (size_t)(4 * j + (lane >> 3)) * C + ch * 64) + (lane & 7));
         }
-        __syncwarp();
-        uint32_t w[32];
+      }
 #pragma unroll
-        for (int pc = 0; pc < 8; ++pc) {
-          const uint4 v = *reinterpret_cast<const uint4*>(scratch + lane * 128 + ((pc ^ (lane & 7)) << 4));
-          w[4 * pc + 0] = v.x; w[4 * pc + 1] = v.y; w[4 * pc + 2] = v.z; w[4 * pc + 3] = v.w;
+      for (int t = 0; t < kMine; ++t) {
+        const int ch = 2 * t + par;
+        if (ch < kChunks) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int rr = 4 * j + (lane >> 3), pc = lane & 7;
+            *reinterpret_cast<uint4*>(scratch + rr * 128 + ((pc ^ (rr & 7)) << 4)) = v[t][j];
+          }
+          __syncwarp();
+          uint32_t w[32];
+#pragma unroll
+          for (int pc = 0; pc < 8; ++pc) {
+            const uint4 u = *reinterpret_cast<const uint4*>(scratch + lane * 128 + ((pc ^ (lane & 7)) << 4));
+            w[4 * pc + 0] = u.x; w[4 * pc + 1] = u.y; w[4 * pc + 2] = u.z; w[4 * pc + 3] = u.w;
+          }
+          __syncwarp();
+          tc_st32(tlane + kTmQ + ch * 32, w);
         }
-        __syncwarp();
-        tc_st32(tlane + kTmQ + ch * 32, w);
       }
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(&bars.q_full);
+      mbar_arrive(&sh.q_full);
     }
 
-    float m_used = -INFINITY, l_run = 0.f, av_raw = -INFINITY;
+    // m_mine: the reference maximum this warp's row sum l_run is expressed in
+    float m_mine = -INFINITY, l_run = 0.f, av_raw = -INFINITY;
     int ai = 0;
-    for (int i = 0; i < n_tiles; ++i) {
-      const int b = i & 1;
+    for (int i = par; i < n_tiles; i += 2) {
+      const int b = par;                                  // == i & 1
+      const uint32_t ph = (i >> 1) & 1;
       const uint32_t ts = tlane + kTmS + b * TN;
-      mbar_wait(&bars.s_full[b], (i >> 1) & 1);
+      mbar_wait(&sh.s_full[b], ph);
       tc_fence_after();
       uint32_t sv[TN];
 #pragma unroll
       for (int ch = 0; ch < TN / 32; ++ch) tc_ld32(ts + ch * 32, sv + ch * 32);
       tc_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&sh.s_free[b]);                         // S[b] is in registers
       const long long col0 = k_begin + (long long)i * TN;
       if (col0 + TN > k_end) {  // ragged last tile: TMA zero-filled the columns past K
         const int valid = (int)(k_end - col0);
@@ -297,15 +344,22 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         ai = (int)col0 + idx;
       }
       const float m_tile = mx * scale2;
-      const bool grow = (i > 0) && (m_tile > m_used + kRescaleThreshold);
-      if (i == 0) m_used = m_tile;
+
+      // ---- decision point of tile i: everything up to tile i-1 has been decided by the other warp
+      if (i > 0) named_bar_sync(dec_other, 64);
+      float m_now = (i > 0) ? sh.m_ref[r] : m_tile;
+      if (m_now != m_mine) {            // the other warp moved the reference (or this is my first tile)
+        l_run *= exp2f(m_mine - m_now); // first tile: l_run == 0
+        m_mine = m_now;
+      }
+      const bool grow = (i > 0) && (m_tile > m_now + kRescaleThreshold);
       if (__any_sync(0xffffffffu, grow)) {
-        // rare: bring O and l of this warp's rows to the new reference maximum.  The O GEMM of the
-        // previous tile must have landed; the one of this tile cannot start before p_full below.
-        const float alpha = grow ? exp2f(m_used - m_tile) : 1.f;
-        if (grow) m_used = m_tile;
-        l_run *= alpha;
-        mbar_wait(&bars.o_done[(i - 1) & 1], ((i - 1) >> 1) & 1);
+        // rare: bring this quadrant's O rows to the new reference maximum.  Every O GEMM up to
+        // tile i-1 must have landed (same accumulator => in order, so the latest commit suffices);
+        // the one of tile i cannot start before this warp arrives on p_full below.
+        const float alpha = grow ? exp2f(m_now - m_tile) : 1.f;
+        if (grow) { m_mine = m_tile; l_run *= alpha; }
+        mbar_wait(&sh.o_done[(i - 1) & 1], ((i - 1) >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
         for (int ch = 0; ch < C / 32; ++ch) {
@@ -318,9 +372,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
         tc_wait_st();
       }
+      if (i == 0 || grow) sh.m_ref[r] = m_mine;
+      if (i + 1 < n_tiles) {            // publish the decision to the warp that owns tile i+1
+        __threadfence_block();
+        named_bar_arrive(dec_mine, 64);
+      }
+
       // ---- P = 2^(S*scale - m) as bf16 pairs, row sum in fp32
-      const float neg_m = -m_used;
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};   // independent partial sums: no 64-deep dependent add chain
+      const float neg_m = -m_mine;
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};   // independent partial sums: no long dependent add chain
       uint32_t pw[TN / 2];
 #pragma unroll
       for (int j = 0; j < TN / 2; ++j) {
@@ -332,10 +392,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       }
       l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       // P buffer b was last read by the O GEMM of tile i-2.  That GEMM's own commit is the only
-      // thing that may be trusted here: the s_full commit behind the (later issued) S GEMM of tile i
-      // does NOT imply it has finished — MMAs with different accumulators overlap and complete out
-      // of order (observed on B200: fast warps overwrote P while the O GEMM was still reading it).
-      if (i >= 2) mbar_wait(&bars.o_done[b], ((i - 2) >> 1) & 1);
+      // thing that may be trusted here: a commit behind a later MMA group with another accumulator
+      // does NOT imply it has finished — such groups overlap and complete out of order (observed
+      // on B200: fast warps overwrote P while the O GEMM was still reading it).
+      if (i >= 2) mbar_wait(&sh.o_done[b], ((i - 2) >> 1) & 1);
       // row r of P in the K-major SWIZZLE_128B layout: 16-byte chunk c of a 128-byte row lands at c ^ (r & 7)
       {
         uint8_t* prow = pbuf + b * kPBytes + r * 128;
@@ -346,30 +406,42 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core reads
-      tc_fence_before();                                             // S[b] has been read: it may be overwritten
-      mbar_arrive(&bars.p_full[b]);
+      mbar_arrive(&sh.p_full[b]);
     }
 
-    // ---- epilogue: statistics, then O
-    if (n_tiles >= 2) mbar_wait(&bars.o_done[(n_tiles - 2) & 1], ((n_tiles - 2) >> 1) & 1);
-    mbar_wait(&bars.o_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
+    // ---- epilogue: merge the two warps' statistics (odd-tile warp -> even-tile warp), then O
+    if (n_tiles >= 2) mbar_wait(&sh.o_done[(n_tiles - 2) & 1], ((n_tiles - 2) >> 1) & 1);
+    mbar_wait(&sh.o_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
     tc_fence_after();
     const bool row_ok = (row0 + r) < B;
-    if (row_ok) {
+    if (par == 1) {
+      sh.xm[r] = m_mine;
+      sh.xl[r] = l_run;
+      sh.xav[r] = av_raw;
+      sh.xai[r] = ai;
+    }
+    named_bar_sync(9 + quad, 64);
+    if (par == 0 && row_ok) {
+      const float m_fin = sh.m_ref[r];
+      // exp2f(-inf) == 0 covers a warp that never owned a tile (l == 0, m == -inf)
+      const float l_tot = l_run * exp2f(m_mine - m_fin) + sh.xl[r] * exp2f(sh.xm[r] - m_fin);
+      const float av1 = sh.xav[r];
+      const int ai1 = sh.xai[r];
+      if (av1 > av_raw || (av1 == av_raw && ai1 < ai)) { av_raw = av1; ai = ai1; }
       const size_t o = (size_t)split * B + row0 + r;
-      pm[o] = m_used;
-      pl[o] = l_run;
+      pm[o] = m_fin;
+      pl[o] = l_tot;
       pav[o] = av_raw * scale2;
       pai[o] = ai;
     }
-    // O row r: tensor memory -> this thread's own staging row (16-byte chunks, row stride C+4 floats
-    // keeps the 128-bit stores bank-conflict free) -> one bulk async copy per row to global.  No
-    // cross-thread synchronisation: every thread stores exactly what it staged.
-    float* stage = reinterpret_cast<float*>(ring) + (size_t)r * (C + 4);   // every TMA write has been consumed
+    // O row r, half of the columns per warp: tensor memory -> this thread's own staging segment
+    // (16-byte chunks; row stride C+4 floats keeps the 128-bit stores bank-conflict free) -> one
+    // bulk async copy to global.  No cross-thread synchronisation: every thread stores what it staged.
+    float* stage = reinterpret_cast<float*>(ring) + (size_t)r * (C + 4) + par * HC;  // every TMA write has been consumed
 #pragma unroll 1
-    for (int ch = 0; ch < C / 32; ++ch) {
+    for (int ch = 0; ch < HC / 32; ++ch) {
       uint32_t o[32];
-      tc_ld32(tlane + kTmO + ch * 32, o);
+      tc_ld32(tlane + kTmO + par * HC + ch * 32, o);
       tc_wait_ld();
 #pragma unroll
       for (int j = 0; j < 8; ++j)
@@ -377,34 +449,34 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
     if (row_ok) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      bulk_store_row(po + ((size_t)split * B + row0 + r) * C, stage, C * 4);
+      bulk_store_row(po + ((size_t)split * B + row0 + r) * C + par * HC, stage, HC * 4);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     tc_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == kTmaWarp) {
     // ========================================================================= TMA producer
     for (int i = 0; i < n_tiles; ++i) {
       const int st = i % kStages;
-      mbar_wait(&bars.k_empty[st], ((i / kStages) & 1) ^ 1);
+      mbar_wait(&sh.k_empty[st], ((i / kStages) & 1) ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(&bars.k_full[st], kStageBytes);
+        mbar_expect_tx(&sh.k_full[st], kStageBytes);
         const long long col0 = k_begin + (long long)i * TN;
 #pragma unroll
         for (int bx = 0; bx < kBoxes; ++bx)
-          tma_load_2d(ring + (size_t)st * kStageBytes + (size_t)bx * kBoxBytes, &tmap_queue, &bars.k_full[st],
+          tma_load_2d(ring + (size_t)st * kStageBytes + (size_t)bx * kBoxBytes, &tmap_queue, &sh.k_full[st],
                       (int)(col0 + bx * 64), 0);
       }
       __syncwarp();
     }
-  } else {
+  } else if (warp == kMmaWarp) {
     // =========================================================================== MMA issuer
     // The whole warp walks the protocol (waits are warp-uniform); one elected lane issues.
-    mbar_wait(&bars.q_full, 0);
+    mbar_wait(&sh.q_full, 0);
     tc_fence_after();
     auto issue_s = [&](int i) {
       const int st = i % kStages;
-      mbar_wait(&bars.k_full[st], (i / kStages) & 1);
+      mbar_wait(&sh.k_full[st], (i / kStages) & 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sbase = smem_u32(ring + (size_t)st * kStageBytes);
@@ -416,14 +488,20 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           const uint64_t bd = make_sw128_desc(sbase + s * 2048, kBoxBytes, 1024);
           tc_mma_ts(d, tmem + kTmQ + s * 8, bd, kIdescS, s > 0);
         }
-        tc_commit(&bars.s_full[i & 1]);
+        tc_commit(&sh.s_full[i & 1]);
       }
       __syncwarp();
     };
+    // S GEMMs run two tiles ahead of the O GEMMs: S[b] is free again as soon as the softmax warps
+    // hold tile i in registers (s_free), long before P(i) is ready.
     issue_s(0);
+    if (n_tiles > 1) issue_s(1);
     for (int i = 0; i < n_tiles; ++i) {
-      if (i + 1 < n_tiles) issue_s(i + 1);
-      mbar_wait(&bars.p_full[i & 1], (i >> 1) & 1);
+      if (i + 2 < n_tiles) {
+        mbar_wait(&sh.s_free[i & 1], (i >> 1) & 1);
+        issue_s(i + 2);
+      }
+      mbar_wait(&sh.p_full[i & 1], (i >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
         const int st = i % kStages;
@@ -437,15 +515,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           const uint64_t bd = make_sw128_desc(sbase + (s >> 2) * kBoxBytes + (s & 3) * 32, 16, 1024);
           tc_mma_ss(tmem + kTmO, ad, bd, kIdescO, (i > 0 || s > 0) ? 1u : 0u);
         }
-        tc_commit(&bars.k_empty[st]);
-        tc_commit(&bars.o_done[i & 1]);
+        tc_commit(&sh.k_empty[st]);
+        tc_commit(&sh.o_done[i & 1]);
       }
       __syncwarp();
     }
   }
 
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kTmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }

@@ -18,4 +18,5 @@ for it in range(3):
     d = list(buf)
     print(f"iter {it}: q_loaded@{d[0]} loop_end@{d[1]} epilogue_end@{d[2]} all_end@{d[3]}")
     print("  sm  (wait_s, softmax, end@):", [(d[8+4*i], d[9+4*i], d[10+4*i]) for i in range(14)])
+    print("  sm detail (ldtm, max+pairsync, exp, odone_wait):", [(d[160+4*i], d[161+4*i], d[162+4*i], d[163+4*i]) for i in range(14)])
     print("  mma (wait_p, @, wait_k, @):", [(d[100+4*i], d[101+4*i], d[102+4*i], d[103+4*i]) for i in range(14)])
