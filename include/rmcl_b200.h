@@ -136,10 +136,18 @@ int rmcl_enqueue(void* queue, rmcl_dtype queue_dtype, const void* keys, rmcl_dty
  * replaces: attack/pgd_attack_vilt.py:162-173 (clone/float, inf-norm, clamp, scale, add, clamp:
  *           7 kernels, 5 passes).  Works on pixels [B,3,H,W] or embeddings [B,L,768] viewed [B,N].
  * REF_LINF in f32 is bit-identical to the reference: fadd(delta, fdiv(fmul(lr,g), d)).
- *   norms_ws  f32[2*B] scratch (per-sample norms); delta is updated in place.
+ * One persistent launch; the gradient is re-read from L2, so DRAM sees 12 B/element.
+ *   workspace  rmcl_pgd_workspace_bytes(B, N, grad_dtype) bytes, 256-byte aligned, caller-owned
+ *              (arrival counters + per-chunk partial norms).  It must be ZERO-FILLED once before
+ *              its first use; every call leaves the counters zeroed again, so no memset launch is
+ *              needed between calls.  Calls sharing a workspace must be stream-ordered.
+ *              delta is updated in place.
  */
+size_t rmcl_pgd_workspace_bytes(int B, int64_t N, rmcl_dtype grad_dtype);
+
 int rmcl_pgd_step(void* delta, rmcl_dtype delta_dtype, const void* grad, rmcl_dtype grad_dtype,
-                  int B, int64_t N, float lr, float eps, int mode, float* norms_ws, void* stream);
+                  int B, int64_t N, float lr, float eps, int mode, void* workspace,
+                  size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer convenience used for the end-to-end measurement: one kernels-only RMCL step

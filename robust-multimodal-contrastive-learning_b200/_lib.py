@@ -16,7 +16,7 @@ FLAG_NORMALIZE_K, FLAG_NO_GRAD = 1, 2
 
 EXPORTS = (
     "rmcl_last_error", "rmcl_version", "rmcl_sm_count", "rmcl_ema_plan", "rmcl_ema_multi",
-    "rmcl_infonce_workspace_bytes", "rmcl_infonce_fwd_bwd", "rmcl_enqueue", "rmcl_pgd_step", "rmcl_step_host",
+    "rmcl_infonce_workspace_bytes", "rmcl_infonce_fwd_bwd", "rmcl_enqueue", "rmcl_pgd_workspace_bytes", "rmcl_pgd_step", "rmcl_step_host",
     "rmcl_profile_enable", "rmcl_profile_infonce_ms",
 )
 
@@ -59,7 +59,9 @@ def lib():
     L.rmcl_enqueue.restype = i32
     L.rmcl_enqueue.argtypes = [vp, i32, vp, i32, vp, i32, i32, i64, i64, vp]
     L.rmcl_pgd_step.restype = i32
-    L.rmcl_pgd_step.argtypes = [vp, i32, vp, i32, i32, i64, f32, f32, i32, vp, vp]
+    L.rmcl_pgd_step.argtypes = [vp, i32, vp, i32, i32, i64, f32, f32, i32, vp, sz, vp]
+    L.rmcl_pgd_workspace_bytes.restype = sz
+    L.rmcl_pgd_workspace_bytes.argtypes = [i32, i64, i32]
     L.rmcl_step_host.restype = i32
     L.rmcl_step_host.argtypes = [vp, i64, f64, i32, vp, vp, i32, vp, vp, vp, i32, vp, i32, i32, i64, f32, i32,
                                  vp, vp, vp, vp, vp, vp, sz, vp]

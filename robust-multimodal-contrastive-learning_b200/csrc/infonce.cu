@@ -133,7 +133,10 @@ __global__ void __launch_bounds__(128) infonce_prep_kernel(const TQ* __restrict_
 }
 
 // -------------------------------------------------------------------------------- finalize
-__global__ void __launch_bounds__(256) infonce_finalize_kernel(
+constexpr int kFinGroups = 4;                 // split groups streaming the partials concurrently
+constexpr int kFinThreads = 256 * kFinGroups;
+
+__global__ void __launch_bounds__(kFinThreads) infonce_finalize_kernel(
     int B, int C, int splits, float inv_tau, float grad_scale /* loss_scale / B */, float loss_scale, bool bf16_mode,
     bool want_grad, const float* __restrict__ q_hat, const float* __restrict__ k_hat, const float* __restrict__ inv_norm,
     const float* __restrict__ pos2, const float* __restrict__ pm, const float* __restrict__ pl,
@@ -141,12 +144,15 @@ __global__ void __launch_bounds__(256) infonce_finalize_kernel(
     float* __restrict__ row_loss, unsigned int* __restrict__ counter, float* __restrict__ loss,
     float* __restrict__ loss_per_row, float* __restrict__ lse_out, float* __restrict__ pos_out,
     long long* __restrict__ argmax_out, float* __restrict__ dq, float* __restrict__ dk) {
-  extern __shared__ float sw[];  // [splits] merge weights
+  extern __shared__ float fin_smem[];
+  float* sw = fin_smem;                       // [splits] merge weights
+  float* part = fin_smem + ((splits + 3) & ~3);  // [kFinGroups-1][C] partial column sums of groups 1..
   __shared__ float red[8];
   __shared__ float s_stats[4];   // 0: scale applied to O  1: p_pos - 1
   __shared__ bool s_last;
   const int row = blockIdx.x;
   const int tid = threadIdx.x;
+  const int grp = tid >> 8, ct = tid & 255;   // split group, column thread
 
   if (tid < 32) {
     // merge the split statistics (one warp; splits is O(100))
@@ -194,49 +200,63 @@ __global__ void __launch_bounds__(256) infonce_finalize_kernel(
   __syncthreads();
 
   if (want_grad) {
-    const float o_scale = s_stats[0], pm1 = s_stats[1];
-    const float gs = grad_scale * inv_tau;
-    // dq^ for the columns this thread owns (C <= 1024 -> at most 4)
-    float dqh[4], qh[4];
-    float dot = 0.f;
+    // Column sums of the partials: group g streams splits g, g+G, ... with 4 independent loads in
+    // flight per owned column; groups are then added in group order (deterministic).
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const size_t sstride = (size_t)B * C;
+    const float* prow = po + (size_t)row * C;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int c = tid + 256 * i;
-      dqh[i] = 0.f;
-      qh[i] = 0.f;
+      const int c = ct + 256 * i;
       if (c < C) {
-        // 8 independent loads in flight per thread: the merge is a pure stream over the partials
-        const float* pcol = po + (size_t)row * C + c;
-        const size_t sstride = (size_t)B * C;
-        float acc = 0.f;
-        int s = 0;
-        for (; s + 8 <= splits; s += 8) {
-          float v[8];
+        const float* pcol = prow + c;
+        int s = grp;
+        for (; s + 3 * kFinGroups < splits; s += 4 * kFinGroups) {
+          float v[4];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = __ldcs(pcol + (size_t)(s + u) * sstride);
+          for (int u = 0; u < 4; ++u) v[u] = __ldcs(pcol + (size_t)(s + u * kFinGroups) * sstride);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) acc = fmaf(v[u], sw[s + u], acc);
+          for (int u = 0; u < 4; ++u) acc[i] = fmaf(v[u], sw[s + u * kFinGroups], acc[i]);
         }
-        for (; s < splits; ++s) acc = fmaf(__ldcs(pcol + (size_t)s * sstride), sw[s], acc);
-        const float kh = round_if(k_hat[(size_t)row * C + c], bf16_mode);
-        qh[i] = q_hat[(size_t)row * C + c];
-        dqh[i] = gs * fmaf(acc, o_scale, pm1 * kh);
-        dot = fmaf(qh[i], dqh[i], dot);
-        if (dk) dk[(size_t)row * C + c] = gs * pm1 * round_if(qh[i], bf16_mode);
+        for (; s < splits; s += kFinGroups) acc[i] = fmaf(__ldcs(pcol + (size_t)s * sstride), sw[s], acc[i]);
+        if (grp > 0) part[(size_t)(grp - 1) * C + c] = acc[i];
       }
     }
-    dot = warp_sum(dot);
-    if ((tid & 31) == 0) red[tid >> 5] = dot;
     __syncthreads();
-    dot = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) dot += red[w];
-    const float inv = inv_norm[row];
-    if (dq) {
+    if (grp == 0) {
+      const float o_scale = s_stats[0], pm1 = s_stats[1];
+      const float gs = grad_scale * inv_tau;
+      float dqh[4], qh[4];
+      float dot = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int c = tid + 256 * i;
-        if (c < C) dq[(size_t)row * C + c] = (dqh[i] - qh[i] * dot) * inv;
+        const int c = ct + 256 * i;
+        dqh[i] = 0.f;
+        qh[i] = 0.f;
+        if (c < C) {
+          float a = acc[i];
+#pragma unroll
+          for (int g = 1; g < kFinGroups; ++g) a += part[(size_t)(g - 1) * C + c];
+          const float kh = round_if(k_hat[(size_t)row * C + c], bf16_mode);
+          qh[i] = q_hat[(size_t)row * C + c];
+          dqh[i] = gs * fmaf(a, o_scale, pm1 * kh);
+          dot = fmaf(qh[i], dqh[i], dot);
+          if (dk) dk[(size_t)row * C + c] = gs * pm1 * round_if(qh[i], bf16_mode);
+        }
+      }
+      dot = warp_sum(dot);
+      if ((ct & 31) == 0) red[ct >> 5] = dot;
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 warps of group 0 only
+      dot = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) dot += red[w];
+      const float inv = inv_norm[row];
+      if (dq) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = ct + 256 * i;
+          if (c < C) dq[(size_t)row * C + c] = (dqh[i] - qh[i] * dot) * inv;
+        }
       }
     }
   }
@@ -247,15 +267,15 @@ __global__ void __launch_bounds__(256) infonce_finalize_kernel(
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(counter, 1u) == (unsigned)B - 1u);
     __syncthreads();
-    if (s_last) {
+    if (s_last && tid < 256) {
       __threadfence();
       float acc = 0.f;
       for (int r = tid; r < B; r += 256) acc += __ldcg(row_loss + r);
       // fixed-shape tree: warp shuffle then 8 partials in order
       acc = warp_sum(acc);
-      __syncthreads();
+      asm volatile("bar.sync 2, 256;" ::: "memory");
       if ((tid & 31) == 0) red[tid >> 5] = acc;
-      __syncthreads();
+      asm volatile("bar.sync 2, 256;" ::: "memory");
       if (tid == 0) {
         float t = 0.f;
         for (int w = 0; w < 8; ++w) t += red[w];
@@ -371,7 +391,8 @@ extern "C" int rmcl_infonce_fwd_bwd(const void* q, rmcl_dtype q_dtype, const voi
   if (rc != RMCL_OK) return rc;
   RMCL_PROF_MARK(2);
 
-  infonce_finalize_kernel<<<B, 256, p.splits * sizeof(float), s>>>(
+  const size_t fin_smem = ((size_t)((p.splits + 3) & ~3) + (size_t)(kFinGroups - 1) * C) * sizeof(float);
+  infonce_finalize_kernel<<<B, kFinThreads, fin_smem, s>>>(
       B, C, p.splits, 1.f / tau, loss_scale / (float)B, loss_scale, bf16_mode, want_grad, (const float*)(ws + p.off_qhat),
       (const float*)(ws + p.off_khat), (const float*)(ws + p.off_inv), (const float*)(ws + p.off_pos2), parts.m, parts.l,
       parts.av, parts.ai, parts.o, (float*)(ws + p.off_rowloss), (unsigned int*)(ws + p.off_counter), loss, loss_per_row,

@@ -8,22 +8,25 @@
 // operation — fadd(delta, fdiv(fmul(lr,g), d)) — so fp32 results are bit-identical.
 // SIGN_LINF and L2 are the north-star's extra modes (specified in DESIGN.md).
 //
-// Two implementations, both HBM-bound, selected by size:
-//  * cluster path (pgd_cluster_kernel): one thread-block cluster per sample.  Each CTA stages its
-//    slice of the gradient in shared memory with one pass over HBM, the per-sample norm is
-//    reduced warp-shuffle -> CTA -> cluster (distributed shared memory), and the update runs out
-//    of shared memory: 12 B/element (read g, read delta, write delta) — the algorithmic minimum.
-//  * streaming path (norm kernel + update kernel [+ projection kernel for L2]): any N; re-reads
-//    the gradient (16 B/element; from L2 when B*N*4 fits the 126 MB L2).
-#include <cooperative_groups.h>
-
+// HBM-bound, and the per-sample norm makes it a two-phase computation (three for the L2 projection):
+// the gradient is needed once for the norm and once for the update.  One persistent launch walks an
+// ordered list of work items (sample, 32 KB chunk) handed out by an atomic ticket:
+//     round r:   P1(batch r)    read g chunk            -> partial norm of the chunk
+//                P2(batch r-1)  re-read g, read delta   -> write delta'   (+ partial |delta'|^2 for L2)
+//                P3(batch r-2)  (L2 only, if it shrinks) re-read delta', scale, write
+// A batch is a group of samples whose gradients fit in a fraction of the 126 MB L2, so that the
+// re-read of P2 (and P3) is served by L2 and DRAM sees the algorithmic minimum of 12 B/element
+// (read g, read delta, write delta).  A later-phase item spins on a per-sample arrival counter; all
+// the items it waits for have smaller tickets, i.e. are already running, so the wait cannot deadlock
+// regardless of how many CTAs are resident.  Per-chunk partials are combined by a fixed-shape tree, so
+// the result is deterministic (and the inf-norm, hence REF_LINF, is exact).
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace rmcl {
 
 constexpr int kPgdThreads = 256;
+constexpr int kPgdChunkBytes = 32 * 1024;                 // per operand per work item
+constexpr long long kPgdBatchBytes = 24ll * 1024 * 1024;  // gradient bytes per batch kept L2-resident
 
 __device__ __forceinline__ float block_reduce(float v, bool is_max, float* red /*[32]*/) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -65,287 +68,348 @@ template <> __device__ __forceinline__ float clamp_eps<__nv_bfloat16>(float v, f
   return fminf(fmaxf(v, -e), e);
 }
 
-// ------------------------------------------------------------------ streaming path
-// norms[b] (max|g| as uint bits, or sum g^2) accumulated with one atomic per CTA.
-template <typename TG>
-__global__ void __launch_bounds__(kPgdThreads) pgd_norm_kernel(const TG* __restrict__ grad, long long N, int mode,
-                                                               float* __restrict__ norms) {
-  __shared__ float red[32];
-  const int b = blockIdx.y;
-  const TG* g = grad + (long long)b * N;
-  const bool is_max = (mode == RMCL_PGD_REF_LINF);
+struct PgdPlan {
+  long long N;
+  int B;
+  int mode;
+  float lr, eps;
+  int chunk_elems;       // elements per work item
+  int chunks;            // work items per sample and phase
+  int batch;             // samples per batch
+  int n_batches;
+  int phases;            // 1 (sign: update only), 2 (norm, update), 3 (+ L2 projection)
+  long long total_items;
+  // workspace
+  unsigned int* ticket;  // [1]
+  unsigned int* exits;   // [1] CTAs that have left the work loop
+  unsigned int* done1;   // [B] chunks of the sample whose first phase has finished
+  unsigned int* done2;   // [B]
+  float* part1;          // [B][chunks] per-chunk max|g| or sum g^2
+  float* norm1;          // [B] combined by the last arriving chunk of the sample
+  float* part2;          // [B][chunks] per-chunk sum delta'^2
+  float* norm2;          // [B]
+};
+
+struct PgdItem {
+  int phase;  // 0 = norm, 1 = update, 2 = project
+  int sample;
+  int chunk;
+};
+
+// ticket -> (phase, sample, chunk) in the round order described at the top of the file
+__device__ __forceinline__ PgdItem pgd_decode(const PgdPlan& p, long long t) {
+  const int first_phase = (p.phases == 1) ? 1 : 0;  // sign mode has no norm phase
+  const int rounds = p.n_batches + p.phases - 1;
+  for (int r = 0; r < rounds; ++r) {
+    for (int k = 0; k < p.phases; ++k) {
+      const int b = r - k;
+      if (b < 0 || b >= p.n_batches) continue;
+      const int s0 = b * p.batch;
+      const int ns = (s0 + p.batch <= p.B ? p.batch : p.B - s0);
+      const long long cnt = (long long)ns * p.chunks;
+      if (t < cnt) return PgdItem{first_phase + k, s0 + (int)(t / p.chunks), (int)(t % p.chunks)};
+      t -= cnt;
+    }
+  }
+  return PgdItem{-1, 0, 0};
+}
+
+__device__ __forceinline__ void spin_until(const unsigned int* counter, unsigned int target) {
+  unsigned int v;
+  do {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+  } while (v < target);
+}
+
+// Stores this item's partial; the item that arrives last for its sample combines all the sample's
+// partials (thread c takes chunks c, c+256, ... then a fixed-shape block tree: deterministic no matter
+// which CTA happens to be last) and publishes the sample norm, followed by one more arrival, so that
+// waiters need a single load.  Must be called by the whole CTA.
+__device__ __forceinline__ bool pgd_publish_partial(float* part, float* norms, unsigned int* done, const PgdItem& it,
+                                                    int chunks, float value, bool is_max, float* red) {
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    part[(long long)it.sample * chunks + it.chunk] = value;
+    __threadfence();
+    s_last = (atomicAdd(done + it.sample, 1u) == (unsigned)chunks - 1u);
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  const float* pp = part + (long long)it.sample * chunks;
   float acc = 0.f;
-  constexpr int VE = 16 / sizeof(TG);
-  const bool vec = (N % VE == 0) && ((reinterpret_cast<uintptr_t>(grad) & 15u) == 0);
-  if (vec) {
-    const long long nv = N / VE;
-    const uint4* gv = reinterpret_cast<const uint4*>(g);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
-      uint4 u = ld_stream_u4(gv + i);
-      const TG* e = reinterpret_cast<const TG*>(&u);
-#pragma unroll
-      for (int j = 0; j < VE; ++j) {
-        const float x = to_f32(e[j]);
-        acc = is_max ? fmaxf(acc, fabsf(x)) : fmaf(x, x, acc);
-      }
-    }
-  } else {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
-      const float x = to_f32(g[i]);
-      acc = is_max ? fmaxf(acc, fabsf(x)) : fmaf(x, x, acc);
-    }
+  for (int c = threadIdx.x; c < chunks; c += kPgdThreads) {
+    const float v = __ldcg(pp + c);
+    acc = is_max ? fmaxf(acc, v) : acc + v;
   }
   acc = block_reduce(acc, is_max, red);
   if (threadIdx.x == 0) {
-    if (is_max) atomicMax(reinterpret_cast<unsigned int*>(norms + b), __float_as_uint(acc));
-    else atomicAdd(norms + b, acc);
+    norms[it.sample] = acc;
+    __threadfence();
+    atomicAdd(done + it.sample, 1u);
   }
+  return true;
 }
 
 template <typename TD, typename TG>
-__global__ void __launch_bounds__(kPgdThreads) pgd_update_kernel(TD* __restrict__ delta, const TG* __restrict__ grad,
-                                                                 long long N, float lr, float eps, int mode,
-                                                                 const float* __restrict__ norms,
-                                                                 float* __restrict__ dnorm2) {
+__global__ void __launch_bounds__(kPgdThreads) pgd_ticket_kernel(TD* __restrict__ delta, const TG* __restrict__ grad,
+                                                                 const PgdPlan p) {
   __shared__ float red[32];
-  const int b = blockIdx.y;
-  TD* d = delta + (long long)b * N;
-  const TG* g = grad + (long long)b * N;
-  float denom = 1.f;
-  if (mode == RMCL_PGD_REF_LINF) denom = fmaxf(norms[b], 1e-8f);
-  else if (mode == RMCL_PGD_L2) denom = fmaxf(sqrtf(norms[b]), 1e-8f);
-  const bool do_clamp = (eps > 0.f) && (mode != RMCL_PGD_L2);
-  float acc = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
-    float v = pgd_apply<TD>(to_f32(d[i]), to_f32(g[i]), lr, denom, mode);
-    if (do_clamp) v = clamp_eps<TD>(v, eps);
-    d[i] = from_f32<TD>(v);
-    acc = fmaf(v, v, acc);
-  }
-  if (mode == RMCL_PGD_L2 && eps > 0.f) {
-    acc = block_reduce(acc, false, red);
-    if (threadIdx.x == 0) atomicAdd(dnorm2 + b, acc);
-  }
-}
-
-template <typename TD>
-__global__ void __launch_bounds__(kPgdThreads) pgd_project_l2_kernel(TD* __restrict__ delta, long long N, float eps,
-                                                                     const float* __restrict__ dnorm2) {
-  const int b = blockIdx.y;
-  const float dn = fmaxf(sqrtf(dnorm2[b]), 1e-12f);
-  const float s = fminf(__fdiv_rn(eps, dn), 1.f);
-  if (s >= 1.f) return;
-  TD* d = delta + (long long)b * N;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x)
-    d[i] = from_f32<TD>(__fmul_rn(to_f32(d[i]), s));
-}
-
-// ------------------------------------------------------------------ cluster path
-// grid = (cluster_size, B), cluster dims (cluster_size,1,1): cluster y == sample.
-// dynamic smem: slice_elems floats (the CTA's slice of g as fp32; reused for delta' in L2 mode).
-template <typename T>
-__device__ __forceinline__ void unpack_to_smem(const uint4& u, float* dst, float& acc, bool is_max) {
-  constexpr int V = 16 / sizeof(T);
-  const T* e = reinterpret_cast<const T*>(&u);
-  float x[V];
-#pragma unroll
-  for (int j = 0; j < V; ++j) {
-    x[j] = to_f32(e[j]);
-    acc = is_max ? fmaxf(acc, fabsf(x[j])) : fmaf(x[j], x[j], acc);
-  }
-#pragma unroll
-  for (int j = 0; j < V; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
-}
-
-template <typename TD, typename TG>
-__global__ void __launch_bounds__(kPgdThreads) pgd_cluster_kernel(TD* __restrict__ delta, const TG* __restrict__ grad,
-                                                                  long long N, long long slice_elems, float lr,
-                                                                  float eps, int mode) {
-  extern __shared__ __align__(16) float sg[];
-  __shared__ float red[32];
-  __shared__ float partial[2];  // [0]: norm of g, [1]: norm of delta'  (read by peer CTAs over DSMEM)
-  cg::cluster_group cluster = cg::this_cluster();
-  const unsigned rank = cluster.block_rank(), csz = cluster.num_blocks();
-  const int b = blockIdx.y;
-  const long long lo = (long long)rank * slice_elems;
-  long long n = N - lo;
-  n = n < 0 ? 0 : (n > slice_elems ? slice_elems : n);
-  const TG* g = grad + (long long)b * N + lo;
-  TD* d = delta + (long long)b * N + lo;
-  const bool is_max = (mode == RMCL_PGD_REF_LINF);
+  __shared__ PgdItem s_item;
+  __shared__ float s_norm;
   constexpr int VG = 16 / sizeof(TG), VD = 16 / sizeof(TD);
-  // slice_elems % 64 == 0, so N % 8 == 0 makes every sample/slice start 16B-aligned and n % 8 == 0
-  const bool vec = (N % 8 == 0) &&
+  constexpr int VE = VG > VD ? VG : VD;  // elements per thread step in the vector path (8 if any bf16, else 4)
+  const bool is_max = (p.mode == RMCL_PGD_REF_LINF);
+  const bool vec = (p.N % VE == 0) && (p.chunk_elems % VE == 0) &&
                    (((reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(delta)) & 15u) == 0);
+  const bool l2proj = (p.mode == RMCL_PGD_L2) && (p.eps > 0.f);
+  const bool do_clamp = (p.eps > 0.f) && (p.mode != RMCL_PGD_L2);
+  // g is read twice a few tens of MB apart: keep it (evict_last) until its second use, then let it go;
+  // delta is touched once (twice under the L2 projection) and must not push g out of L2.
+  const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
 
-  // pass 1: HBM -> smem (as fp32), 4 independent 16-byte loads in flight per thread; norm on the fly
-  float acc = 0.f;
-  if (vec) {
-    const uint4* gv = reinterpret_cast<const uint4*>(g);
-    const long long nv = n / VG;
-    long long i = threadIdx.x;
-    for (; i + 3 * kPgdThreads < nv; i += 4 * kPgdThreads) {
-      uint4 u[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = ld_stream_u4(gv + i + k * kPgdThreads);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) unpack_to_smem<TG>(u[k], sg + (i + k * kPgdThreads) * VG, acc, is_max);
-    }
-    for (; i < nv; i += kPgdThreads) unpack_to_smem<TG>(ld_stream_u4(gv + i), sg + i * VG, acc, is_max);
-  } else {
-    for (long long i = threadIdx.x; i < n; i += kPgdThreads) {
-      const float x = to_f32(g[i]);
-      sg[i] = x;
-      acc = is_max ? fmaxf(acc, fabsf(x)) : fmaf(x, x, acc);
-    }
-  }
-  float denom = 1.f;
-  if (mode != RMCL_PGD_SIGN_LINF) {
-    acc = block_reduce(acc, is_max, red);
-    if (threadIdx.x == 0) partial[0] = acc;
-    cluster.sync();
-    float tot = 0.f;
-    for (unsigned r = 0; r < csz; ++r) {  // same order in every CTA -> identical denominators
-      const float p = *cluster.map_shared_rank(&partial[0], r);
-      tot = is_max ? fmaxf(tot, p) : tot + p;
-    }
-    denom = fmaxf(is_max ? tot : sqrtf(tot), 1e-8f);
-  } else {
+  for (;;) {
     __syncthreads();
-  }
-
-  // pass 2: update out of smem; delta is read and written exactly once
-  const bool l2proj = (mode == RMCL_PGD_L2) && (eps > 0.f);
-  const bool do_clamp = (eps > 0.f) && (mode != RMCL_PGD_L2);
-  float acc2 = 0.f;
-  if (vec) {
-    uint4* dv = reinterpret_cast<uint4*>(d);
-    const long long nv = n / VD;
-    for (long long i = threadIdx.x; i < nv; i += kPgdThreads) {
-      uint4 u = ld_u4(dv + i);
-      TD* e = reinterpret_cast<TD*>(&u);
-      float gs[VD];
-#pragma unroll
-      for (int j = 0; j < VD; j += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(sg + i * VD + j);
-        gs[j] = t.x; gs[j + 1] = t.y; gs[j + 2] = t.z; gs[j + 3] = t.w;
+    if (threadIdx.x == 0) {
+      const long long t = (long long)atomicAdd(p.ticket, 1u);
+      s_item = (t < p.total_items) ? pgd_decode(p, t) : PgdItem{-1, 0, 0};
+    }
+    __syncthreads();
+    const PgdItem it = s_item;
+    if (it.phase < 0) {
+      // The last CTA to leave returns the control words to zero, so the next call needs no memset launch
+      // (every item has completed by then: a CTA only gets here after finishing all its items).
+      if (threadIdx.x == 0 && atomicAdd(p.exits, 1u) == gridDim.x - 1u) {
+        for (int i = 0; i < 2 * p.B; ++i) p.done1[i] = 0u;   // done1 and done2 are contiguous
+        *p.exits = 0u;
+        __threadfence();
+        *p.ticket = 0u;
       }
+      break;
+    }
+    const long long e0 = (long long)it.chunk * p.chunk_elems;
+    long long n = p.N - e0;
+    if (n > p.chunk_elems) n = p.chunk_elems;
+    const TG* g = grad + (long long)it.sample * p.N + e0;
+    TD* d = delta + (long long)it.sample * p.N + e0;
+
+    if (it.phase == 0) {
+      // ------------------------------------------------------------ P1: partial norm of the chunk
+      float acc = 0.f;
+      if (vec) {
+        const uint4* gv = reinterpret_cast<const uint4*>(g);
+        const long long nv = n / VG;
+        long long i = threadIdx.x;
+        for (; i + 3 * kPgdThreads < nv; i += 4 * kPgdThreads) {
+          uint4 u[4];
 #pragma unroll
-      for (int j = 0; j < VD; ++j) {
-        float v = pgd_apply<TD>(to_f32(e[j]), gs[j], lr, denom, mode);
-        if (do_clamp) v = clamp_eps<TD>(v, eps);
-        gs[j] = v;
-        acc2 = fmaf(v, v, acc2);
-        e[j] = from_f32<TD>(v);
+          for (int k = 0; k < 4; ++k) u[k] = ld_u4_hint(gv + i + k * kPgdThreads, keep);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const TG* e = reinterpret_cast<const TG*>(&u[k]);
+#pragma unroll
+            for (int j = 0; j < VG; ++j) {
+              const float x = to_f32(e[j]);
+              acc = is_max ? fmaxf(acc, fabsf(x)) : fmaf(x, x, acc);
+            }
+          }
+        }
+        for (; i < nv; i += kPgdThreads) {
+          const uint4 u = ld_u4_hint(gv + i, keep);
+          const TG* e = reinterpret_cast<const TG*>(&u);
+#pragma unroll
+          for (int j = 0; j < VG; ++j) {
+            const float x = to_f32(e[j]);
+            acc = is_max ? fmaxf(acc, fabsf(x)) : fmaf(x, x, acc);
+          }
+        }
+      } else {
+        for (long long i = threadIdx.x; i < n; i += kPgdThreads) {
+          const float x = to_f32(g[i]);
+          acc = is_max ? fmaxf(acc, fabsf(x)) : fmaf(x, x, acc);
+        }
+      }
+      acc = block_reduce(acc, is_max, red);
+      pgd_publish_partial(p.part1, p.norm1, p.done1, it, p.chunks, acc, is_max, red);
+    } else if (it.phase == 1) {
+      // ------------------------------------------------------------ P2: the update
+      float denom = 1.f;
+      if (p.mode != RMCL_PGD_SIGN_LINF) {
+        if (threadIdx.x == 0) {
+          spin_until(p.done1 + it.sample, (unsigned)p.chunks + 1u);   // +1: the sample norm has been published
+          s_norm = __ldcg(p.norm1 + it.sample);
+        }
+        __syncthreads();
+        const float tot = s_norm;
+        denom = fmaxf(is_max ? tot : sqrtf(tot), 1e-8f);
+      }
+      float acc2 = 0.f;
+      if (vec) {
+        // one thread step = VE elements = 16 B of the narrower-typed operand
+        const long long nv = n / VE;
+        for (long long i = threadIdx.x; i < nv; i += 2 * kPgdThreads) {
+          const bool second = (i + kPgdThreads) < nv;
+          float gx[2][VE], dx[2][VE];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !second) break;
+            const long long base = (i + h * kPgdThreads) * VE;
+#pragma unroll
+            for (int q = 0; q < VE / VG; ++q) {
+              const uint4 u = ld_u4_hint(reinterpret_cast<const uint4*>(g + base) + q, stream);  // last use of g
+              const TG* e = reinterpret_cast<const TG*>(&u);
+#pragma unroll
+              for (int j = 0; j < VG; ++j) gx[h][q * VG + j] = to_f32(e[j]);
+            }
+#pragma unroll
+            for (int q = 0; q < VE / VD; ++q) {
+              const uint4 u = ld_u4_hint(reinterpret_cast<const uint4*>(d + base) + q, stream);
+              const TD* e = reinterpret_cast<const TD*>(&u);
+#pragma unroll
+              for (int j = 0; j < VD; ++j) dx[h][q * VD + j] = to_f32(e[j]);
+            }
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !second) break;
+            const long long base = (i + h * kPgdThreads) * VE;
+#pragma unroll
+            for (int q = 0; q < VE / VD; ++q) {
+              uint4 u;
+              TD* e = reinterpret_cast<TD*>(&u);
+#pragma unroll
+              for (int j = 0; j < VD; ++j) {
+                float v = pgd_apply<TD>(dx[h][q * VD + j], gx[h][q * VD + j], p.lr, denom, p.mode);
+                if (do_clamp) v = clamp_eps<TD>(v, p.eps);
+                acc2 = fmaf(v, v, acc2);
+                e[j] = from_f32<TD>(v);
+              }
+              st_u4_hint(reinterpret_cast<uint4*>(d + base) + q, u, l2proj ? keep : stream);  // P3 re-reads delta'
+            }
+          }
+        }
+      } else {
+        for (long long i = threadIdx.x; i < n; i += kPgdThreads) {
+          float v = pgd_apply<TD>(to_f32(d[i]), to_f32(g[i]), p.lr, denom, p.mode);
+          if (do_clamp) v = clamp_eps<TD>(v, p.eps);
+          acc2 = fmaf(v, v, acc2);
+          d[i] = from_f32<TD>(v);
+        }
       }
       if (l2proj) {
+        acc2 = block_reduce(acc2, false, red);
+        pgd_publish_partial(p.part2, p.norm2, p.done2, it, p.chunks, acc2, false, red);
+      }
+    } else {
+      // ------------------------------------------------------------ P3: L2 projection onto the eps-ball
+      if (threadIdx.x == 0) {
+        spin_until(p.done2 + it.sample, (unsigned)p.chunks + 1u);
+        s_norm = __ldcg(p.norm2 + it.sample);
+      }
+      __syncthreads();
+      const float tot = s_norm;
+      const float s = fminf(__fdiv_rn(p.eps, fmaxf(sqrtf(tot), 1e-12f)), 1.f);
+      if (s < 1.f) {
+        if (vec) {
+          uint4* dv = reinterpret_cast<uint4*>(d);
+          const long long nv = n / VD;
+          for (long long i = threadIdx.x; i < nv; i += kPgdThreads) {
+            uint4 u = ld_u4_hint(dv + i, stream);
+            TD* e = reinterpret_cast<TD*>(&u);
 #pragma unroll
-        for (int j = 0; j < VD; j += 4)
-          *reinterpret_cast<float4*>(sg + i * VD + j) = make_float4(gs[j], gs[j + 1], gs[j + 2], gs[j + 3]);
-      } else {
-        st_stream_u4(dv + i, u);
+            for (int j = 0; j < VD; ++j) e[j] = from_f32<TD>(__fmul_rn(to_f32(e[j]), s));
+            st_u4_hint(dv + i, u, stream);
+          }
+        } else {
+          for (long long i = threadIdx.x; i < n; i += kPgdThreads) d[i] = from_f32<TD>(__fmul_rn(to_f32(d[i]), s));
+        }
       }
     }
-  } else {
-    for (long long i = threadIdx.x; i < n; i += kPgdThreads) {
-      float v = pgd_apply<TD>(to_f32(d[i]), sg[i], lr, denom, mode);
-      if (do_clamp) v = clamp_eps<TD>(v, eps);
-      acc2 = fmaf(v, v, acc2);
-      if (l2proj) sg[i] = v;
-      else d[i] = from_f32<TD>(v);
-    }
   }
-  if (l2proj) {
-    acc2 = block_reduce(acc2, false, red);
-    if (threadIdx.x == 0) partial[1] = acc2;
-    cluster.sync();
-    float tot = 0.f;
-    for (unsigned r = 0; r < csz; ++r) tot += *cluster.map_shared_rank(&partial[1], r);
-    const float s = fminf(__fdiv_rn(eps, fmaxf(sqrtf(tot), 1e-12f)), 1.f);
-    for (long long i = threadIdx.x; i < n; i += kPgdThreads) {
-      const float v = sg[i];
-      d[i] = from_f32<TD>(s < 1.f ? __fmul_rn(v, s) : v);
-    }
+}
+
+static int pgd_make_plan(int B, long long N, float lr, float eps, int mode, size_t gsize, PgdPlan* p) {
+  p->N = N;
+  p->B = B;
+  p->mode = mode;
+  p->lr = lr;
+  p->eps = eps;
+  p->chunk_elems = kPgdChunkBytes / (int)gsize;
+  const long long chunks = (N + p->chunk_elems - 1) / p->chunk_elems;
+  if (chunks > (1ll << 30)) {
+    set_error("rmcl_pgd_step: N=%lld is too large", N);
+    return RMCL_E_UNSUPPORTED_DIM;
   }
-  cluster.sync();  // keep partial[] alive until every peer has read it
+  p->chunks = (int)chunks;
+  long long batch = kPgdBatchBytes / (N * (long long)gsize);
+  if (batch < 1) batch = 1;
+  if (batch > B) batch = B;
+  p->batch = (int)batch;
+  p->n_batches = (B + p->batch - 1) / p->batch;
+  p->phases = (mode == RMCL_PGD_SIGN_LINF) ? 1 : ((mode == RMCL_PGD_L2 && eps > 0.f) ? 3 : 2);
+  p->total_items = (long long)p->phases * B * p->chunks;
+  return RMCL_OK;
+}
+
+static size_t pgd_ws_bytes(const PgdPlan& p) {
+  const size_t ctrl = ((size_t)(2 + 2 * p.B) * sizeof(unsigned int) + 255) / 256 * 256;
+  return ctrl + 2 * ((size_t)p.B * p.chunks + p.B) * sizeof(float);
 }
 
 template <typename TD, typename TG>
-static int launch_pgd(void* delta, const void* grad, int B, long long N, float lr, float eps, int mode, float* ws,
-                      cudaStream_t s) {
-  TD* d = (TD*)delta;
-  const TG* g = (const TG*)grad;
+static int launch_pgd(void* delta, const void* grad, PgdPlan p, void* ws, size_t ws_bytes, cudaStream_t s) {
   const int sms = sm_count();
   if (sms <= 0) return RMCL_E_CUDA;
-
-  // ---- cluster path: smallest cluster whose per-CTA slice fits ~100 KB (2 CTAs/SM), else up to 200 KB
-  int csz = 0;
-  long long slice = 0;
-  for (int c = 1; c <= 16; c *= 2) {
-    long long sl = ((N + c - 1) / c + 63) / 64 * 64;
-    if (sl * 4 <= 100 * 1024) { csz = c; slice = sl; break; }
+  const size_t need = pgd_ws_bytes(p);
+  if (!ws || ws_bytes < need) {
+    set_error("rmcl_pgd_step: workspace %zu < required %zu (rmcl_pgd_workspace_bytes)", ws_bytes, need);
+    return RMCL_E_WORKSPACE;
   }
-  if (!csz) {
-    long long sl = ((N + 15) / 16 + 63) / 64 * 64;
-    if (sl * 4 <= 200 * 1024) { csz = 16; slice = sl; }
-  }
-  if (csz) {
-    auto kern = pgd_cluster_kernel<TD, TG>;
-    const size_t smem = (size_t)slice * 4;
-    RMCL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (csz > 8) RMCL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(csz, B, 1);
-    cfg.blockDim = dim3(kPgdThreads, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = csz;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    RMCL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, d, g, N, slice, lr, eps, mode));
-    return RMCL_OK;
-  }
-
-  // ---- streaming path
-  RMCL_CHECK_ARG(ws != nullptr, "rmcl_pgd_step: norms_ws is required for N=%lld", N);
-  RMCL_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(float) * 2 * (size_t)B, s));
-  long long bps = (N + (long long)kPgdThreads * 16 - 1) / ((long long)kPgdThreads * 16);
-  long long cap = ((long long)sms * 8 + B - 1) / B;
-  if (bps > cap) bps = cap;
-  if (bps < 1) bps = 1;
-  dim3 grid((unsigned)bps, B);
-  if (mode != RMCL_PGD_SIGN_LINF) {
-    pgd_norm_kernel<TG><<<grid, kPgdThreads, 0, s>>>(g, N, mode, ws);
-    RMCL_LAUNCH_OK("pgd_norm_kernel");
-  }
-  pgd_update_kernel<TD, TG><<<grid, kPgdThreads, 0, s>>>(d, g, N, lr, eps, mode, ws, ws + B);
-  RMCL_LAUNCH_OK("pgd_update_kernel");
-  if (mode == RMCL_PGD_L2 && eps > 0.f) {
-    pgd_project_l2_kernel<TD><<<grid, kPgdThreads, 0, s>>>(d, N, eps, ws + B);
-    RMCL_LAUNCH_OK("pgd_project_l2_kernel");
-  }
+  const size_t ctrl = ((size_t)(2 + 2 * p.B) * sizeof(unsigned int) + 255) / 256 * 256;
+  unsigned int* c = reinterpret_cast<unsigned int*>(ws);
+  p.ticket = c;
+  p.exits = c + 1;
+  p.done1 = c + 2;
+  p.done2 = c + 2 + p.B;
+  p.part1 = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ctrl);
+  p.norm1 = p.part1 + (size_t)p.B * p.chunks;
+  p.part2 = p.norm1 + p.B;
+  p.norm2 = p.part2 + (size_t)p.B * p.chunks;
+  long long grid = (long long)sms * 8;
+  if (grid > p.total_items) grid = p.total_items;
+  pgd_ticket_kernel<TD, TG><<<(unsigned)grid, kPgdThreads, 0, s>>>((TD*)delta, (const TG*)grad, p);
+  RMCL_LAUNCH_OK("pgd_ticket_kernel");
   return RMCL_OK;
 }
 
 }  // namespace rmcl
 
+extern "C" size_t rmcl_pgd_workspace_bytes(int B, int64_t N, rmcl_dtype grad_dtype) {
+  if (B <= 0 || N <= 0 || !rmcl::dtype_ok(grad_dtype)) return 0;
+  rmcl::PgdPlan p;
+  // the largest layout over the modes (L2 uses both partial arrays; sizes do not depend on mode otherwise)
+  if (rmcl::pgd_make_plan(B, N, 0.f, 1.f, RMCL_PGD_L2, rmcl::dtype_size(grad_dtype), &p) != RMCL_OK) return 0;
+  return rmcl::pgd_ws_bytes(p);
+}
+
 extern "C" int rmcl_pgd_step(void* delta, rmcl_dtype delta_dtype, const void* grad, rmcl_dtype grad_dtype, int B,
-                             int64_t N, float lr, float eps, int mode, float* norms_ws, void* stream) {
+                             int64_t N, float lr, float eps, int mode, void* workspace, size_t workspace_bytes,
+                             void* stream) {
   RMCL_CHECK_ARG(delta && grad, "rmcl_pgd_step: null pointer");
-  RMCL_CHECK_ARG(B > 0 && N > 0 && B <= 65535, "rmcl_pgd_step: bad sizes B=%d N=%lld", B, (long long)N);
+  RMCL_CHECK_ARG(B > 0 && N > 0 && B <= (1 << 24), "rmcl_pgd_step: bad sizes B=%d N=%lld", B, (long long)N);
   RMCL_CHECK_ARG(mode >= RMCL_PGD_REF_LINF && mode <= RMCL_PGD_L2, "rmcl_pgd_step: bad mode %d", mode);
   RMCL_CHECK_ARG(rmcl::dtype_ok(delta_dtype) && rmcl::dtype_ok(grad_dtype), "rmcl_pgd_step: bad dtype");
+  RMCL_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "rmcl_pgd_step: workspace must be 256B aligned");
   cudaStream_t s = (cudaStream_t)stream;
+  rmcl::PgdPlan p;
+  const int rc = rmcl::pgd_make_plan(B, N, lr, eps, mode, rmcl::dtype_size(grad_dtype), &p);
+  if (rc != RMCL_OK) return rc;
   using bf16 = __nv_bfloat16;
   if (delta_dtype == RMCL_F32 && grad_dtype == RMCL_F32)
-    return rmcl::launch_pgd<float, float>(delta, grad, B, N, lr, eps, mode, norms_ws, s);
+    return rmcl::launch_pgd<float, float>(delta, grad, p, workspace, workspace_bytes, s);
   if (delta_dtype == RMCL_F32 && grad_dtype == RMCL_BF16)
-    return rmcl::launch_pgd<float, bf16>(delta, grad, B, N, lr, eps, mode, norms_ws, s);
+    return rmcl::launch_pgd<float, bf16>(delta, grad, p, workspace, workspace_bytes, s);
   if (delta_dtype == RMCL_BF16 && grad_dtype == RMCL_F32)
-    return rmcl::launch_pgd<bf16, float>(delta, grad, B, N, lr, eps, mode, norms_ws, s);
-  return rmcl::launch_pgd<bf16, bf16>(delta, grad, B, N, lr, eps, mode, norms_ws, s);
+    return rmcl::launch_pgd<bf16, float>(delta, grad, p, workspace, workspace_bytes, s);
+  return rmcl::launch_pgd<bf16, bf16>(delta, grad, p, workspace, workspace_bytes, s);
 }

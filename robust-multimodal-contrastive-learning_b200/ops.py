@@ -202,12 +202,16 @@ def pgd_step_(delta, grad, lr, eps, mode="ref_linf", _scratch={}):
         raise ValueError("delta and grad must be contiguous")
     B = delta.shape[0]
     N = delta.numel() // B
-    key = (delta.device, B)
+    key = (delta.device, B, N, grad.dtype)
     ws = _scratch.get(key)
     if ws is None:
-        ws = _scratch[key] = torch.empty(2 * B, dtype=torch.float32, device=delta.device)
+        nbytes = _lib.lib().rmcl_pgd_workspace_bytes(B, N, _dt(grad))
+        if nbytes == 0:
+            check(-1, "rmcl_pgd_workspace_bytes")
+        ws = _scratch[key] = torch.zeros(nbytes + 256, dtype=torch.uint8, device=delta.device)   # zero-filled once
+    off = (-ws.data_ptr()) % 256
     rc = _lib.lib().rmcl_pgd_step(_p(delta), _dt(delta), _p(grad), _dt(grad), B, N, float(lr), float(eps),
-                                  _lib.PGD_MODES[mode], _p(ws), _stream())
+                                  _lib.PGD_MODES[mode], C.c_void_p(ws.data_ptr() + off), ws.numel() - off, _stream())
     check(rc, "rmcl_pgd_step")
     return delta
 

@@ -67,8 +67,10 @@ def test_argument_validation_without_gpu(L):
     assert L.rmcl_enqueue(one, 0, one, 0, one, 8, 16, 30, 30, None) == -1
     assert b"multiple" in L.rmcl_last_error()
     assert L.rmcl_enqueue(None, 0, one, 0, one, 8, 16, 32, 32, None) == -1
-    assert L.rmcl_pgd_step(one, 0, one, 0, 0, 10, 0.1, 0.1, 0, None, None) == -1
-    assert L.rmcl_pgd_step(one, 0, one, 0, 2, 10, 0.1, 0.1, 7, None, None) == -1
+    assert L.rmcl_pgd_step(one, 0, one, 0, 0, 10, 0.1, 0.1, 0, None, 0, None) == -1
+    assert L.rmcl_pgd_step(one, 0, one, 0, 2, 10, 0.1, 0.1, 7, None, 0, None) == -1
+    assert L.rmcl_pgd_workspace_bytes(4, 1000, 0) >= (2 + 2 * 4) * 4 + 2 * (4 + 4) * 4
+    assert L.rmcl_pgd_workspace_bytes(0, 1000, 0) == 0
     assert L.rmcl_ema_multi(None, 5, 0.999, 0, None) == -1
     assert L.rmcl_ema_multi(None, 0, 0.999, 0, None) == 0          # empty list is a no-op
     assert L.rmcl_infonce_fwd_bwd(one, 0, one, 0, one, 0, 4, 8, 16, 16, 0.0, 1.0, 0, 0, None, None, None, None, None,
@@ -87,7 +89,9 @@ def test_no_cpu_fallback():
     assert L.rmcl_sm_count() < 0 and len(L.rmcl_last_error()) > 0
     # a launch attempt without a device reports RMCL_E_CUDA, it does not compute anything
     buf = (C.c_float * 64)()
-    rc = L.rmcl_pgd_step(buf, 0, buf, 0, 2, 32, 0.1, 0.1, 0, buf, None)
+    ws = (C.c_char * 4096)()
+    aligned = (C.addressof(ws) + 255) // 256 * 256
+    rc = L.rmcl_pgd_step(buf, 0, buf, 0, 2, 32, 0.1, 0.1, 0, C.c_void_p(aligned), 3072, None)
     assert rc == -4
     assert RmclError is not None
 
