@@ -74,6 +74,28 @@ __device__ __forceinline__ void st_stream_u4(void* p, const uint4& v) {
                : "memory");
 }
 
+// Programmatic dependent launch: a kernel launched with launch_pdl() may start while its
+// predecessor in the stream is still running; it must call pdl_wait() before touching anything the
+// predecessor writes.  pdl_trigger() in the predecessor lets the dependent's CTAs become resident early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // L2 eviction-priority policies for data with a known reuse distance
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   uint64_t p;

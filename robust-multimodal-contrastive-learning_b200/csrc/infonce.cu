@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(128) infonce_prep_kernel(const TQ* __restrict_
                                                            unsigned int* __restrict__ counter) {
   __shared__ float red[4];
   const int row = blockIdx.x;
+  if (threadIdx.x == 0) pdl_trigger();   // the partial kernel may set itself up while this one runs
   if (row == 0 && threadIdx.x == 0) *counter = 0u;
   if (row >= B) {  // padding rows of the bf16 operand (TMA reads whole 128-row boxes)
     for (int c = threadIdx.x; c < C; c += 128) q_hat_bf16[(size_t)row * C + c] = __float2bfloat16_rn(0.f);
@@ -153,22 +154,48 @@ __global__ void __launch_bounds__(kFinThreads) infonce_finalize_kernel(
   const int row = blockIdx.x;
   const int tid = threadIdx.x;
   const int grp = tid >> 8, ct = tid & 255;   // split group, column thread
+  pdl_wait();                                 // launched early (PDL): the partials must be complete
+
+  // The partial stream does not depend on the merge weights until the multiply: put the first
+  // batch of loads (column ct, splits grp, grp+G, ...) in flight before waiting for the statistics.
+  constexpr int kPre = 8;
+  float pre[kPre];
+  {
+    const float* pcol = po + (size_t)row * C + ct;
+    const size_t sstride = (size_t)B * C;
+#pragma unroll
+    for (int u = 0; u < kPre; ++u) {
+      const int s = grp + u * kFinGroups;
+      pre[u] = (want_grad && ct < C && s < splits) ? __ldcs(pcol + (size_t)s * sstride) : 0.f;
+    }
+  }
+
+  // row data needed after the merge: in flight now
+  const bool own0 = want_grad && grp == 0 && ct < C;
+  float qh_pre = 0.f, kh_pre = 0.f;
+  if (own0) {
+    qh_pre = q_hat[(size_t)row * C + ct];
+    kh_pre = k_hat[(size_t)row * C + ct];
+  }
 
   if (tid < 32) {
-    // merge the split statistics (one warp; splits is O(100))
+    // merge the split statistics (one warp; a row's statistics are contiguous => coalesced loads)
+    const float* rm = pm + (size_t)row * splits;
+    const float* rl = pl + (size_t)row * splits;
+    const float* rav = pav + (size_t)row * splits;
+    const int* rai = pai + (size_t)row * splits;
     float mmax = -INFINITY;
-    for (int s = tid; s < splits; s += 32) mmax = fmaxf(mmax, pm[(size_t)s * B + row]);
+    for (int s = tid; s < splits; s += 32) mmax = fmaxf(mmax, __ldcg(rm + s));
     mmax = warp_max(mmax);
     float lsum = 0.f;
     float bv = -INFINITY;
     int bi = 0x7fffffff;
     for (int s = tid; s < splits; s += 32) {
-      const float ms = pm[(size_t)s * B + row];
+      const float ms = __ldcg(rm + s), ls = __ldcg(rl + s), v = __ldcg(rav + s);
+      const int i = __ldcg(rai + s);
       const float w = (ms == -INFINITY) ? 0.f : exp2f(ms - mmax);
       sw[s] = w;
-      lsum = fmaf(pl[(size_t)s * B + row], w, lsum);
-      const float v = pav[(size_t)s * B + row];
-      const int i = pai[(size_t)s * B + row];
+      lsum = fmaf(ls, w, lsum);
       if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
     }
     lsum = warp_sum(lsum);
@@ -211,6 +238,14 @@ __global__ void __launch_bounds__(kFinThreads) infonce_finalize_kernel(
       if (c < C) {
         const float* pcol = prow + c;
         int s = grp;
+        if (i == 0) {  // the prefetched batch
+#pragma unroll
+          for (int u = 0; u < kPre; ++u) {
+            const int sp = grp + u * kFinGroups;
+            if (sp < splits) acc[0] = fmaf(pre[u], sw[sp], acc[0]);
+          }
+          s = grp + kPre * kFinGroups;
+        }
         for (; s + 3 * kFinGroups < splits; s += 4 * kFinGroups) {
           float v[4];
 #pragma unroll
@@ -237,8 +272,8 @@ __global__ void __launch_bounds__(kFinThreads) infonce_finalize_kernel(
           float a = acc[i];
 #pragma unroll
           for (int g = 1; g < kFinGroups; ++g) a += part[(size_t)(g - 1) * C + c];
-          const float kh = round_if(k_hat[(size_t)row * C + c], bf16_mode);
-          qh[i] = q_hat[(size_t)row * C + c];
+          const float kh = round_if(i == 0 ? kh_pre : k_hat[(size_t)row * C + c], bf16_mode);
+          qh[i] = (i == 0) ? qh_pre : q_hat[(size_t)row * C + c];
           dqh[i] = gs * fmaf(a, o_scale, pm1 * kh);
           dot = fmaf(qh[i], dqh[i], dot);
           if (dk) dk[(size_t)row * C + c] = gs * pm1 * round_if(qh[i], bf16_mode);
@@ -392,12 +427,11 @@ extern "C" int rmcl_infonce_fwd_bwd(const void* q, rmcl_dtype q_dtype, const voi
   RMCL_PROF_MARK(2);
 
   const size_t fin_smem = ((size_t)((p.splits + 3) & ~3) + (size_t)(kFinGroups - 1) * C) * sizeof(float);
-  infonce_finalize_kernel<<<B, kFinThreads, fin_smem, s>>>(
+  RMCL_CUDA_OK(launch_pdl(infonce_finalize_kernel, dim3(B), dim3(kFinThreads), fin_smem, s,
       B, C, p.splits, 1.f / tau, loss_scale / (float)B, loss_scale, bf16_mode, want_grad, (const float*)(ws + p.off_qhat),
       (const float*)(ws + p.off_khat), (const float*)(ws + p.off_inv), (const float*)(ws + p.off_pos2), parts.m, parts.l,
       parts.av, parts.ai, parts.o, (float*)(ws + p.off_rowloss), (unsigned int*)(ws + p.off_counter), loss, loss_per_row,
-      lse, pos, reinterpret_cast<long long*>(argmax), dq, dk);
-  RMCL_LAUNCH_OK("infonce_finalize_kernel");
+      lse, pos, reinterpret_cast<long long*>(argmax), dq, dk));
   RMCL_PROF_MARK(3);
   if (g_prof_on) g_prof_valid = true;
   return RMCL_OK;

@@ -32,10 +32,10 @@ struct InfoNcePlan {
 int infonce_make_plan(int B, int C, long long K, int queue_dtype, int path, bool aligned_for_tc, InfoNcePlan* plan);
 
 struct InfoNcePartials {
-  float* m;         // [splits][B]
-  float* l;         // [splits][B]
-  float* av;        // [splits][B]
-  int* ai;          // [splits][B]
+  float* m;         // [B][splits]  (a row's statistics are contiguous: one coalesced load in finalize)
+  float* l;         // [B][splits]
+  float* av;        // [B][splits]
+  int* ai;          // [B][splits]
   float* o;         // [splits][B][C]
 };
 

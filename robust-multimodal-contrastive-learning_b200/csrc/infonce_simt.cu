@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kSimtThreads) infonce_simt_kernel(
 
   // ---- emit partials
   if (tid < kSimtRows && row0 + tid < B) {
-    const size_t o = (size_t)split * B + row0 + tid;
+    const size_t o = (size_t)(row0 + tid) * gridDim.x + split;
     pm[o] = s_m[tid];
     pl[o] = s_l[tid];
     pav[o] = s_av[tid];

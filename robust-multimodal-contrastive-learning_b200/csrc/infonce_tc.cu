@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // Coalesced global loads (8 lanes cover one 128-byte row segment), all issued before the first
     // use, transposed through this warp's 4 KB of the (still unused) P buffers with the same
     // 16-byte XOR swizzle that keeps the segment writes and the row-per-lane reads conflict free.
+    pdl_wait();   // launched early (PDL): q_hat is written by the prep kernel that may still be running
     {
       constexpr int kChunks = C / 64;                     // 64-column chunks of a row
       constexpr int kMine = (kChunks + 1) / 2;            // chunks handled by this warp: ch = 2*t + par
@@ -410,6 +411,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
 
     // ---- epilogue: merge the two warps' statistics (odd-tile warp -> even-tile warp), then O
+    if (tid == 0) pdl_trigger();   // the finalize kernel's CTAs may become resident now
     if (n_tiles >= 2) mbar_wait(&sh.o_done[(n_tiles - 2) & 1], ((n_tiles - 2) >> 1) & 1);
     mbar_wait(&sh.o_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
     tc_fence_after();
@@ -428,7 +430,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const float av1 = sh.xav[r];
       const int ai1 = sh.xai[r];
       if (av1 > av_raw || (av1 == av_raw && ai1 < ai)) { av_raw = av1; ai = ai1; }
-      const size_t o = (size_t)split * B + row0 + r;
+      const size_t o = (size_t)(row0 + r) * gridDim.x + split;
       pm[o] = m_fin;
       pl[o] = l_tot;
       pav[o] = av_raw * scale2;
@@ -573,9 +575,8 @@ int launch_tc(const __nv_bfloat16* q_hat, const void* queue, int B, long long K,
   auto kern = infonce_tc_kernel<C, TN>;
   RMCL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(p.splits, p.row_blocks);
-  kern<<<grid, kTcThreads, smem, s>>>(tmap, q_hat, B, K, scale2, p.cols_per_split, want_argmax, out.m, out.l, out.av,
-                                      out.ai, out.o);
-  RMCL_LAUNCH_OK("infonce_tc_kernel");
+  RMCL_CUDA_OK(launch_pdl(kern, grid, dim3(kTcThreads), smem, s, tmap, q_hat, B, K, scale2, p.cols_per_split, want_argmax,
+                          out.m, out.l, out.av, out.ai, out.o));
   return RMCL_OK;
 }
 
