@@ -391,15 +391,60 @@ def make_pgd_direct(ref):
         print(f"wrote {path}: {os.path.getsize(path) / 1e3:.1f} kB")
 
 
+def make_facade(ref):
+    """Whole-step golden for the drop-in facade: the tiny module's complete state, the batch, and
+    everything the reference's compute_moco_contrastive + backward produced (loss, diagnostics,
+    logged values, queue/pointer, EMA'd key params, gradients of every query param)."""
+    for name, B, C, K, n_pgd, lr, eps, seed in (("ref_facade_c128", 8, 128, 256, 2, 0.05, 8.0 / 255.0, 5),
+                                                   ("ref_facade_c16", 4, 16, 64, 1, 0.05, 0.005, 6)):
+        mod = build_tiny_module(ref, B, C, K, hidden=32, n_pgd=n_pgd, lr=lr, eps=eps, T=0.07, m=0.999, seed=seed)
+        out = {"meta/B": np.int64(B), "meta/C": np.int64(C), "meta/K": np.int64(K), "meta/hidden": np.int64(32),
+               "meta/n_pgd": np.int64(n_pgd), "meta/lr": np.float64(lr), "meta/eps": np.float64(eps),
+               "meta/T": np.float64(0.07), "meta/m": np.float64(0.999), "meta/steps": np.int64(2)}
+        for k, v in mod.state_dict().items():
+            out[f"state/{k}"] = _np(v)
+        for s in range(2):
+            mod.zero_grad()
+            batch = tiny_batch(B, 16, 6, seed * 100 + s)
+            out[f"step{s}/batch/image"] = _np(batch["image"][0])
+            out[f"step{s}/batch/text_ids"] = _np(batch["text_ids"])
+            ret = ref.objectives.compute_moco_contrastive(mod, deepcopy(batch))
+            ret["moco_loss"].backward()
+            for k, v in ret.items():
+                out[f"step{s}/ret/{k}"] = _np(v)
+            for k, v in mod.__dict__.get("_logged", {}).items():
+                out[f"step{s}/log/{k}"] = _np(torch.as_tensor(v))
+            out[f"step{s}/queue_after"] = _np(mod.proj_queue)
+            out[f"step{s}/ptr_after"] = np.int64(int(mod.proj_queue_ptr))
+            for k, v in mod.named_parameters():
+                if k.startswith("k_"):
+                    out[f"step{s}/k_after/{k}"] = _np(v)
+                elif v.grad is not None:
+                    out[f"step{s}/grad/{k}"] = _np(v.grad)
+            with torch.no_grad():   # optimiser-like nudge so that step 1 differs
+                for k, v in mod.named_parameters():
+                    if v.grad is not None:
+                        v.add_(-0.1 * v.grad)
+        path = os.path.join(GOLDEN_DIR, f"{name}.npz")
+        np.savez_compressed(path, **out)
+        print(f"wrote {path}: {os.path.getsize(path) / 1e3:.1f} kB, losses "
+              f"{out['step0/ret/moco_loss']}, {out['step1/ret/moco_loss']}")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg1", action="store_true")
     ap.add_argument("--only-cfg1", action="store_true")
+    ap.add_argument("--only-facade", action="store_true")
     args = ap.parse_args()
     ref = ref_harness.load_reference()
     ref_harness.ensure_process_group()
     torch.set_num_threads(8)
+    if args.only_facade:
+        make_facade(ref)
+        return
     if not args.only_cfg1:
+        make_facade(ref)
         make_tiny(ref, "ref_tiny_c16", B=4, C=16, K=64, n_pgd=1, lr=0.05, eps=8.0 / 255.0, steps=3)
         make_tiny(ref, "ref_tiny_c128", B=8, C=128, K=256, n_pgd=3, lr=0.05, eps=0.005, steps=2, seed=1)
         make_pgd_direct(ref)

@@ -1,0 +1,216 @@
+"""GPU: the drop-in facade (rmcl_b200.compute_moco_contrastive / compute_pgd / PGDAttack_moco) run
+end to end on a small stand-in LightningModule, against what the UNMODIFIED reference produced for
+the same module state and batches (tests/golden/ref_facade_*.npz, written by
+oracle/make_golden.py:make_facade from vilt/modules/objectives.py:217-447 +
+attack/pgd_attack_vilt.py:130-175 on CPU).
+
+The module below re-creates the stand-in of oracle/make_golden.py (toy encoder, the reference's
+MOCOHead layout heads.py:129-143) so that the golden state_dict loads 1:1.  Backbone forwards run
+in torch on the GPU, everything between them in the CUDA kernels (fp32 parity path)."""
+from copy import deepcopy
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+class ToyBlock(nn.Module):
+    def __init__(self, h):
+        super().__init__()
+        self.n1, self.n2 = nn.LayerNorm(h), nn.LayerNorm(h)
+        self.qkv, self.proj = nn.Linear(h, 3 * h), nn.Linear(h, h)
+        self.fc1, self.fc2 = nn.Linear(h, 2 * h), nn.Linear(2 * h, h)
+
+    def forward(self, x, mask=None):
+        q, k, v = self.qkv(self.n1(x)).chunk(3, dim=-1)
+        a = torch.softmax(q @ k.transpose(1, 2) / q.shape[-1] ** 0.5, dim=-1)
+        x = x + self.proj(a @ v)
+        x = x + self.fc2(torch.nn.functional.gelu(self.fc1(self.n2(x))))
+        return x, a
+
+
+class ToyTransformer(nn.Module):
+    def __init__(self, h, patch):
+        super().__init__()
+        self.patch_embed = nn.Conv2d(3, h, patch, patch)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, h))
+        self.blocks = nn.ModuleList([ToyBlock(h), ToyBlock(h)])
+        self.norm = nn.LayerNorm(h)
+
+    def visual_embed(self, img, max_image_len=200, mask_it=False):
+        x = self.patch_embed(img).flatten(2).transpose(1, 2)
+        x = torch.cat([self.cls_token.expand(x.shape[0], -1, -1), x], dim=1)
+        return x, torch.ones(x.shape[0], x.shape[1], dtype=torch.long, device=x.device), None, None
+
+
+class ToyPooler(nn.Module):
+    def __init__(self, h):
+        super().__init__()
+        self.dense = nn.Linear(h, h)
+
+    def forward(self, x):
+        return torch.tanh(self.dense(x[:, 0]))
+
+
+class MOCOHead(nn.Module):  # parameter layout of vilt/modules/heads.py:129-143
+    def __init__(self, i, h, o):
+        super().__init__()
+        self.projector = nn.Sequential(nn.Linear(i, h), nn.LayerNorm(h), nn.ReLU(), nn.Linear(h, o, bias=False))
+
+    def forward(self, x):
+        return self.projector(x)
+
+
+class TinyModule(nn.Module):
+    """Duck-typed stand-in for ViLTransformerSS: exactly the attributes the objective reads
+    (vilt_module.py:69-107)."""
+
+    def __init__(self, g, infonce_path):
+        super().__init__()
+        import rmcl_b200
+        h, C, K = g.i("meta/hidden"), g.i("meta/C"), g.i("meta/K")
+        self.text_embeddings = nn.Embedding(50, h)
+        self.token_type_embeddings = nn.Embedding(2, h)
+        self.transformer = ToyTransformer(h, 8)
+        self.pooler = ToyPooler(h)
+        self.moco_head = MOCOHead(h, h, C)
+        self.k_text_embeddings = deepcopy(self.text_embeddings)
+        self.k_token_type_embeddings = deepcopy(self.token_type_embeddings)
+        self.k_transformer = deepcopy(self.transformer)
+        self.k_moco_head = deepcopy(self.moco_head)
+        for l in (self.k_text_embeddings, self.k_token_type_embeddings, self.k_transformer, self.k_moco_head):
+            for p in l.parameters():
+                p.requires_grad = False
+        self.momentum, self.temperature = g.f("meta/m"), g.f("meta/T")
+        self.text_view, self.image_view, self.augmentation = False, True, False
+        self.num_negative, self.per_step_bs = K, g.i("meta/B")
+        self.cosine = nn.CosineSimilarity(dim=1, eps=1e-6)
+        self.register_buffer("proj_queue", torch.zeros(C, K))
+        self.register_buffer("proj_queue_ptr", torch.zeros(1, dtype=torch.long))
+        cfg = dict(adv_steps_img=g.i("meta/n_pgd"), adv_lr_img=g.f("meta/lr"), adv_max_norm_img=g.f("meta/eps"),
+                   max_image_len=200)
+        self.pgd_attacker = rmcl_b200.PGDAttack_moco(cfg, infonce_path=infonce_path)
+        self.infonce_path = infonce_path
+        self.max_image_len = 200
+        self.train_moco_loss = lambda x: x
+        self.val_moco_loss = lambda x: x
+        self.logged = {}
+        self.load_state_dict({k[len("state/"):]: g.t(k) for k in g.z.files if k.startswith("state/")})
+
+    def log(self, name, value, **kw):
+        self.logged[name] = value
+
+    def infer(self, batch, mask_text=False, mask_image=False, **kw):
+        import rmcl_b200
+        return rmcl_b200.PGDAttack.infer(self, batch, mask_text, mask_image, **kw)
+
+    def infer_k(self, batch, mask_text=False, mask_image=False):
+        import types
+        import rmcl_b200
+        view = types.SimpleNamespace(text_embeddings=self.k_text_embeddings,
+                                     token_type_embeddings=self.k_token_type_embeddings,
+                                     transformer=self.k_transformer, pooler=self.pooler, max_image_len=200)
+        return rmcl_b200.PGDAttack.infer(view, batch, mask_text, mask_image)
+
+
+def _batch(g, s):
+    img = g.t(f"step{s}/batch/image").to(DEV)
+    ids = g.t(f"step{s}/batch/text_ids").to(DEV)
+    return {"image": [img], "text": ["x"] * img.shape[0], "text_ids": ids,
+            "text_labels": torch.full_like(ids, -100), "text_masks": torch.ones_like(ids)}
+
+
+def _close(a, b, rtol, what):
+    a, b = a.detach().double().cpu(), torch.as_tensor(b).double()
+    err = (a - b).abs().max().item()
+    ref = b.abs().max().item()
+    assert err <= rtol * max(ref, 1e-12), f"{what}: max err {err:.3e} vs scale {ref:.3e}"
+
+
+@pytest.mark.parametrize("name", ["ref_facade_c128", "ref_facade_c16"])
+def test_compute_moco_contrastive_matches_reference(golden, name):
+    import rmcl_b200
+    g = golden(name)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    mod = TinyModule(g, "simt").to(DEV).train()
+    for s in range(g.i("meta/steps")):
+        mod.zero_grad()
+        mod.logged.clear()
+        ret = rmcl_b200.compute_moco_contrastive(mod, _batch(g, s))
+        assert [k for k in ret if "loss" in k] == ["moco_loss"]            # vilt_module.py:475 sums "*loss*" keys
+        ret["moco_loss"].backward()
+        torch.cuda.synchronize()
+        _close(ret["moco_loss"], g.np(f"step{s}/ret/moco_loss"), 1e-4, f"step {s} moco_loss")
+        for k in g.z.files:
+            if k.startswith(f"step{s}/ret/") and not k.endswith("moco_loss"):
+                _close(ret[k.split("/")[-1]], g.np(k), 2e-4, k)
+        # queue: the enqueued keys come out of a GPU forward of the key encoder -> fp32 noise only
+        assert mod.proj_queue_ptr.item() == g.i(f"step{s}/ptr_after")
+        _close(mod.proj_queue, g.np(f"step{s}/queue_after"), 1e-5, f"step {s} queue")
+        # EMA'd key parameters: elementwise fp32 arithmetic on identical inputs -> bit-exact at step 0
+        for k, v in mod.named_parameters():
+            if k.startswith("k_"):
+                want = g.t(f"step{s}/k_after/{k}")
+                if s == 0:
+                    assert torch.equal(v.detach().cpu(), want), k
+                else:
+                    _close(v, want, 1e-5, k)
+            elif f"step{s}/grad/{k}" in g:
+                _close(v.grad, g.np(f"step{s}/grad/{k}"), 5e-3, f"step {s} grad {k}")
+        rate = mod.logged["moco_attack/PGD_success_rate"]
+        assert float(rate) == pytest.approx(g.f(f"step{s}/log/moco_attack/PGD_success_rate"), abs=1e-6)
+        _close(mod.logged["moco_attack/train/delta"], g.np(f"step{s}/log/moco_attack/train/delta"), 1e-3, "delta norm")
+        with torch.no_grad():   # the generator's optimiser-like nudge between the steps
+            for k, v in mod.named_parameters():
+                if v.grad is not None:
+                    v.add_(-0.1 * v.grad)
+
+
+def test_facade_bf16_queue_takes_tcgen05_path(golden):
+    """Same step with a bf16 queue (tcgen05 kernel): loss within the bf16 tolerance of the reference."""
+    import rmcl_b200
+    g = golden("ref_facade_c128")
+    mod = TinyModule(g, "auto").to(DEV).train()
+    mod.proj_queue = mod.proj_queue.bfloat16()
+    ret = rmcl_b200.compute_moco_contrastive(mod, _batch(g, 0))
+    ret["moco_loss"].backward()
+    torch.cuda.synchronize()
+    _close(ret["moco_loss"], g.np("step0/ret/moco_loss"), 2e-2, "bf16 moco_loss")
+    assert mod.proj_queue_ptr.item() == g.i("step0/ptr_after")
+    assert mod.moco_head.projector[0].weight.grad is not None
+
+
+def test_moco_module_api(golden):
+    """MoCo sketch API (MoCo/MoCo_RMCL.py): method names, two enqueues per step, pointer advance."""
+    import rmcl_b200
+
+    class Enc(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.t, self.i = nn.Linear(12, 64), nn.Linear(20, 64)
+
+        def forward(self, batch):
+            return self.t(batch["t"]), self.i(batch["i"])
+
+    torch.manual_seed(0)
+    moco = rmcl_b200.MoCo({}, dim=64, K=256, m=0.9, T=0.07, encoder_q=Enc(), encoder_k=Enc(), infonce_path="simt").to(DEV)
+    for pq, pk in zip(moco.encoder_q.parameters(), moco.encoder_k.parameters()):
+        assert torch.equal(pq, pk) and not pk.requires_grad
+    with torch.no_grad():
+        for p in moco.encoder_q.parameters():
+            p.add_(0.1)
+    k0 = [p.clone() for p in moco.encoder_k.parameters()]
+    batch = {"t": torch.randn(8, 12, device=DEV), "i": torch.randn(8, 20, device=DEV)}
+    out, labels, logs, _ = moco(batch, materialize_logits=True)
+    (out["loss_txt"] + out["loss_img"]).backward()
+    assert moco.txt_img_queue_ptr.item() == 16                                    # text keys then image keys
+    for a, b, q in zip(k0, moco.encoder_k.parameters(), moco.encoder_q.parameters()):
+        assert torch.equal(b, a * 0.9 + q.detach() * (1.0 - 0.9))                # _momentum_update_key_encoder
+    ce = torch.nn.functional.cross_entropy(out["txt"], labels["txt"])
+    assert abs(ce.item() - out["loss_txt"].item()) < 1e-4 * abs(ce.item())
+    assert moco.encoder_q.t.weight.grad is not None
