@@ -153,7 +153,9 @@ int rmcl_pgd_step(void* delta, rmcl_dtype delta_dtype, const void* grad, rmcl_dt
  * Host-buffer convenience used for the end-to-end measurement: one kernels-only RMCL step
  * (EMA -> InfoNCE fwd+bwd -> enqueue) with q, k in HOST memory and loss/dq returned to HOST
  * memory.  Parameters, queue and pointer stay resident on the device (they are model state).
- * Copies are issued on `stream`; the call returns after the D2H copies completed.
+ * Kernels are issued on `stream`; the host<->device copies ride a library-owned side stream so that
+ * they overlap the EMA and the enqueue.  The call returns after everything it issued has completed
+ * (this one entry point does synchronise: its results are host-visible on return).
  */
 int rmcl_step_host(const rmcl_ema_chunk* chunks_dev, int64_t n_chunks, double m, rmcl_dtype param_dtype,
                    const void* q_host, const void* k_host, rmcl_dtype qk_dtype,

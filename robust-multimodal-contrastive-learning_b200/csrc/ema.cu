@@ -133,7 +133,9 @@ extern "C" int rmcl_ema_multi(const rmcl_ema_chunk* chunks_dev, int64_t n_chunks
   const int sms = rmcl::sm_count();
   if (sms <= 0) return RMCL_E_CUDA;
   const float mf = (float)m, omf = (float)(1.0 - m);  // Python evaluates 1.0-em in double first
-  long long grid = (long long)sms * 8;
+  // 16 CTAs per SM = two waves of the 8 that are resident: measured 208-210 us for the 1.34 GB ViLT-B/32
+  // update (98 % of the measured copy peak) against 220 us with exactly one resident wave
+  long long grid = (long long)sms * 16;
   if (grid > n_chunks) grid = n_chunks;
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == RMCL_F32)

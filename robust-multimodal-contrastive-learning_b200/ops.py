@@ -43,7 +43,7 @@ class EmaPlan:
     ``zip(q_layer.parameters(), k_layer.parameters())`` — for any number of layers.
     """
 
-    def __init__(self, params_k, params_q, chunk_elems=16384):
+    def __init__(self, params_k, params_q, chunk_elems=8192):
         params_k, params_q = list(params_k), list(params_q)
         if len(params_k) != len(params_q):
             raise ValueError("key/query parameter lists differ in length")

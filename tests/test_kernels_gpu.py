@@ -424,3 +424,36 @@ def test_infonce_tcgen05_strided_queue_and_auto_dispatch(ops):
     from rmcl_b200._lib import RmclError
     with pytest.raises(RmclError):                     # fp32 queue cannot take the tcgen05 path
         ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.float().to(DEV), 0.07, path="tcgen05")
+
+
+# ======================================================== host-buffer step (C-ABI rmcl_step_host)
+@pytest.mark.parametrize("qdt", [torch.float32, torch.bfloat16])
+def test_step_host_matches_separate_ops_and_oracle(ops, qdt):
+    """rmcl_step_host = EMA -> InfoNCE -> enqueue with q/k coming from pinned host memory and loss/dq
+    going back to it; must equal the three ops called one by one, and the oracle."""
+    B, C, K = 64, 128, 1024
+    g = torch.Generator().manual_seed(9)
+    shapes = [(300, 7), (1025,), (64, 64)]
+    pk = [torch.randn(s, generator=g) for s in shapes]
+    pq = [torch.randn(s, generator=g) for s in shapes]
+    q = torch.randn(B, C, generator=g).to(qdt)
+    k_raw = torch.randn(B, C, generator=g).to(qdt)
+    queue = torch.randn(C, K, generator=g)
+    for steps_done, ptr0 in ((0, 0), (1, K - B)):
+        qd, pd = queue.to(DEV), torch.tensor([ptr0], dtype=torch.int64, device=DEV)
+        kd, qpd = [t.to(DEV) for t in pk], [t.to(DEV) for t in pq]
+        plan = ops.EmaPlan(kd, qpd)
+        hs = ops.HostStep(plan, qd, pd, B, C, 0.07, 0.999, qdt, "simt")
+        loss_h, dq_h = hs(q.pin_memory(), k_raw.pin_memory())
+        # oracle on the same inputs
+        want_k, want, want_queue, want_ptr = O.rmcl_kernel_step(pk, pq, 0.999, q.float(), O.l2_normalize(k_raw.float()),
+                                                                queue, ptr0, 0.07)
+        for a, b in zip(kd, want_k):
+            assert torch.equal(a.cpu(), b)
+        assert rel_err(loss_h, want["loss"]) < FP32_RTOL and rel_err(dq_h, want["dq"]) < FP32_RTOL
+        assert pd.item() == want_ptr
+        # enqueue is bit-exact on the keys the device normalised
+        k_hat_dev = hs.k_hat_dev.cpu()
+        assert rel_err(k_hat_dev, O.l2_normalize(k_raw.float())) < 1e-6
+        wq, _ = O.dequeue_and_enqueue(queue, ptr0, k_hat_dev, K)
+        assert torch.equal(qd.cpu(), wq)
