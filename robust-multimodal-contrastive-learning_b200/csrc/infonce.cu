@@ -134,10 +134,11 @@ __global__ void __launch_bounds__(128) infonce_prep_kernel(const TQ* __restrict_
 }
 
 // -------------------------------------------------------------------------------- finalize
-constexpr int kFinGroups = 4;                 // split groups streaming the partials concurrently
+constexpr int kFinGroups = 2;                 // split groups streaming the partials concurrently (512 threads:
+                                              // two CTAs per SM, so B=256 rows are one wave on 148 SMs)
 constexpr int kFinThreads = 256 * kFinGroups;
 
-__global__ void __launch_bounds__(kFinThreads) infonce_finalize_kernel(
+__global__ void __launch_bounds__(kFinThreads, 2) infonce_finalize_kernel(
     int B, int C, int splits, float inv_tau, float grad_scale /* loss_scale / B */, float loss_scale, bool bf16_mode,
     bool want_grad, const float* __restrict__ q_hat, const float* __restrict__ k_hat, const float* __restrict__ inv_norm,
     const float* __restrict__ pos2, const float* __restrict__ pm, const float* __restrict__ pl,
