@@ -19,4 +19,4 @@ for chunk in (8192, 16384, 32768, 65536):
     for _ in range(20): ops.ema_multi_(plan, 0.999)
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1)/20*1000
-    print(f"unroll/gridmul env={os.environ.get('EMA_GRIDMUL')} chunk={chunk}: {us:.1f} us  {12*n/us/1e3:.0f} GB/s ({12*n/us/1e3/6537:.3f})", flush=True)
+    print(f"chunk={chunk}: {us:.1f} us  {12*n/us/1e3:.0f} GB/s ({12*n/us/1e3/6537:.3f})", flush=True)

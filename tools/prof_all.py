@@ -1,4 +1,4 @@
-"""Short driver for ncu --set full: one call of every kernel at its bench shape."""
+"""Short driver for ncu --set full: one call of every kernel at its bench shape (see profiles/README.md)."""
 import sys, os, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import rmcl_b200
