@@ -380,9 +380,9 @@ def run_cuda(args):
     line = {
         "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16 queue/q/k operands, fp32 accumulate; fp32 EMA",
+        "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, **CFG, "per_gpu_batch": B, "global_batch": world * B, "infonce_path": path,
+        "config": {"workload": WORKLOAD, **CFG, "arithmetic": "InfoNCE: bf16 queue/q/k operands, fp32 accumulation and statistics; EMA: fp32 (bit-exact with ATen); enqueue: fp32 keys -> bf16 queue", "per_gpu_batch": B, "global_batch": world * B, "infonce_path": path,
                    "parallelism": f"dp{world}", "unit_of_value": "256-sample rank-steps per second, summed over ranks",
                    "l2": "inputs larger than L2: each step streams 1.34 GB of parameters (EMA) between InfoNCE passes; L2 is 126 MB"},
         "roofline": roofline, "kernels": kernels,
