@@ -138,11 +138,18 @@ constexpr int kFinGroups = 2;                 // split groups streaming the part
                                               // two CTAs per SM, so B=256 rows are one wave on 148 SMs)
 constexpr int kFinThreads = 256 * kFinGroups;
 
+__device__ __forceinline__ float ld_partial(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ float ld_partial(const __nv_bfloat16* p) {
+  return __bfloat162float(__ushort_as_bfloat16(__ldcs(reinterpret_cast<const unsigned short*>(p))));
+}
+
+// TP: element type of the partial accumulators (fp32 from the SIMT kernel, bf16 from the tcgen05 kernel)
+template <typename TP>
 __global__ void __launch_bounds__(kFinThreads, 2) infonce_finalize_kernel(
     int B, int C, int splits, float inv_tau, float grad_scale /* loss_scale / B */, float loss_scale, bool bf16_mode,
     bool want_grad, const float* __restrict__ q_hat, const float* __restrict__ k_hat, const float* __restrict__ inv_norm,
     const float* __restrict__ pos2, const float* __restrict__ pm, const float* __restrict__ pl,
-    const float* __restrict__ pav, const int* __restrict__ pai, const float* __restrict__ po,
+    const float* __restrict__ pav, const int* __restrict__ pai, const TP* __restrict__ po,
     float* __restrict__ row_loss, unsigned int* __restrict__ counter, float* __restrict__ loss,
     float* __restrict__ loss_per_row, float* __restrict__ lse_out, float* __restrict__ pos_out,
     long long* __restrict__ argmax_out, float* __restrict__ dq, float* __restrict__ dk) {
@@ -162,12 +169,12 @@ __global__ void __launch_bounds__(kFinThreads, 2) infonce_finalize_kernel(
   constexpr int kPre = 8;
   float pre[kPre];
   {
-    const float* pcol = po + (size_t)row * C + ct;
+    const TP* pcol = po + (size_t)row * C + ct;
     const size_t sstride = (size_t)B * C;
 #pragma unroll
     for (int u = 0; u < kPre; ++u) {
       const int s = grp + u * kFinGroups;
-      pre[u] = (want_grad && ct < C && s < splits) ? __ldcs(pcol + (size_t)s * sstride) : 0.f;
+      pre[u] = (want_grad && ct < C && s < splits) ? ld_partial(pcol + (size_t)s * sstride) : 0.f;
     }
   }
 
@@ -232,12 +239,12 @@ __global__ void __launch_bounds__(kFinThreads, 2) infonce_finalize_kernel(
     // flight per owned column; groups are then added in group order (deterministic).
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     const size_t sstride = (size_t)B * C;
-    const float* prow = po + (size_t)row * C;
+    const TP* prow = po + (size_t)row * C;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int c = ct + 256 * i;
       if (c < C) {
-        const float* pcol = prow + c;
+        const TP* pcol = prow + c;
         int s = grp;
         if (i == 0) {  // the prefetched batch
 #pragma unroll
@@ -250,11 +257,11 @@ __global__ void __launch_bounds__(kFinThreads, 2) infonce_finalize_kernel(
         for (; s + 3 * kFinGroups < splits; s += 4 * kFinGroups) {
           float v[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = __ldcs(pcol + (size_t)(s + u * kFinGroups) * sstride);
+          for (int u = 0; u < 4; ++u) v[u] = ld_partial(pcol + (size_t)(s + u * kFinGroups) * sstride);
 #pragma unroll
           for (int u = 0; u < 4; ++u) acc[i] = fmaf(v[u], sw[s + u * kFinGroups], acc[i]);
         }
-        for (; s < splits; s += kFinGroups) acc[i] = fmaf(__ldcs(pcol + (size_t)s * sstride), sw[s], acc[i]);
+        for (; s < splits; s += kFinGroups) acc[i] = fmaf(ld_partial(pcol + (size_t)s * sstride), sw[s], acc[i]);
         if (grp > 0) part[(size_t)(grp - 1) * C + c] = acc[i];
       }
     }
@@ -428,11 +435,19 @@ extern "C" int rmcl_infonce_fwd_bwd(const void* q, rmcl_dtype q_dtype, const voi
   RMCL_PROF_MARK(2);
 
   const size_t fin_smem = ((size_t)((p.splits + 3) & ~3) + (size_t)(kFinGroups - 1) * C) * sizeof(float);
-  RMCL_CUDA_OK(launch_pdl(infonce_finalize_kernel, dim3(B), dim3(kFinThreads), fin_smem, s,
-      B, C, p.splits, 1.f / tau, loss_scale / (float)B, loss_scale, bf16_mode, want_grad, (const float*)(ws + p.off_qhat),
-      (const float*)(ws + p.off_khat), (const float*)(ws + p.off_inv), (const float*)(ws + p.off_pos2), parts.m, parts.l,
-      parts.av, parts.ai, parts.o, (float*)(ws + p.off_rowloss), (unsigned int*)(ws + p.off_counter), loss, loss_per_row,
-      lse, pos, reinterpret_cast<long long*>(argmax), dq, dk));
+  if (tc) {
+    RMCL_CUDA_OK(launch_pdl(infonce_finalize_kernel<__nv_bfloat16>, dim3(B), dim3(kFinThreads), fin_smem, s,
+        B, C, p.splits, 1.f / tau, loss_scale / (float)B, loss_scale, bf16_mode, want_grad, (const float*)(ws + p.off_qhat),
+        (const float*)(ws + p.off_khat), (const float*)(ws + p.off_inv), (const float*)(ws + p.off_pos2), parts.m, parts.l,
+        parts.av, parts.ai, reinterpret_cast<const __nv_bfloat16*>(parts.o), (float*)(ws + p.off_rowloss),
+        (unsigned int*)(ws + p.off_counter), loss, loss_per_row, lse, pos, reinterpret_cast<long long*>(argmax), dq, dk));
+  } else {
+    RMCL_CUDA_OK(launch_pdl(infonce_finalize_kernel<float>, dim3(B), dim3(kFinThreads), fin_smem, s,
+        B, C, p.splits, 1.f / tau, loss_scale / (float)B, loss_scale, bf16_mode, want_grad, (const float*)(ws + p.off_qhat),
+        (const float*)(ws + p.off_khat), (const float*)(ws + p.off_inv), (const float*)(ws + p.off_pos2), parts.m, parts.l,
+        parts.av, parts.ai, (const float*)parts.o, (float*)(ws + p.off_rowloss), (unsigned int*)(ws + p.off_counter), loss,
+        loss_per_row, lse, pos, reinterpret_cast<long long*>(argmax), dq, dk));
+  }
   RMCL_PROF_MARK(3);
   if (g_prof_on) g_prof_valid = true;
   return RMCL_OK;

@@ -36,7 +36,7 @@ struct InfoNcePartials {
   float* l;         // [B][splits]
   float* av;        // [B][splits]
   int* ai;          // [B][splits]
-  float* o;         // [splits][B][C]
+  float* o;         // [splits][B][C]  fp32 (SIMT partial kernel) or bf16 (tcgen05 partial kernel) elements
 };
 
 // partial stages

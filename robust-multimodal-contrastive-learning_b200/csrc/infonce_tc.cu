@@ -198,7 +198,7 @@ template <int C, int TN>
 __global__ void __launch_bounds__(kTcThreads, 1)
     infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_queue, const __nv_bfloat16* __restrict__ q_hat, int B,
                       long long K, float scale2, long long cols_per_split, int want_argmax, float* __restrict__ pm,
-                      float* __restrict__ pl, float* __restrict__ pav, int* __restrict__ pai, float* __restrict__ po) {
+                      float* __restrict__ pl, float* __restrict__ pav, int* __restrict__ pai, __nv_bfloat16* __restrict__ po) {
   constexpr int kStageBytes = C * TN * 2;
   constexpr int kBoxBytes = C * 128;            // one TMA box: C rows x 64 bf16 columns
   constexpr int kBoxes = TN / 64;
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   static_assert(C / 2 + C + 2 * TN <= 512, "tensor memory budget");
   static_assert(TN % 64 == 0 && C % 64 == 0 && C <= 256, "tile shape");
   static_assert(kStages >= 4, "three tiles are live (S GEMM runs two ahead of the O GEMM) plus one in flight");
-  static_assert(kTcRows * (C + 4) * 4 <= kStages * kStageBytes, "epilogue staging must fit the ring");
+  static_assert(kTcRows * (2 * C + 16) <= kStages * kStageBytes, "epilogue staging must fit the ring");
   static_assert(2 * kPBytes >= kSoftmaxWarps * 4096, "Q^ transpose scratch lives in the P buffers");
   constexpr uint32_t kIdescS = make_idesc(128, TN, 1);
   constexpr uint32_t kIdescO = make_idesc(128, C, 0);
@@ -436,22 +436,31 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       pav[o] = av_raw * scale2;
       pai[o] = ai;
     }
-    // O row r, half of the columns per warp: tensor memory -> this thread's own staging segment
-    // (16-byte chunks; row stride C+4 floats keeps the 128-bit stores bank-conflict free) -> one
-    // bulk async copy to global.  No cross-thread synchronisation: every thread stores what it staged.
-    float* stage = reinterpret_cast<float*>(ring) + (size_t)r * (C + 4) + par * HC;  // every TMA write has been consumed
+    // O row r, half of the columns per warp: tensor memory -> bf16 -> this thread's own staging segment
+    // (16-byte chunks; row stride 2C+16 bytes keeps the 128-bit stores bank-conflict free) -> one bulk
+    // async copy to global.  No cross-thread synchronisation: every thread stores what it staged.
+    // The partial accumulators leave the kernel in bf16: their write-out (148 CTAs x 128 rows x C)
+    // is L2-write bound and sits on the critical path of every CTA, and the O GEMM's A operand (P)
+    // was bf16 already, so this adds one more 2^-9 relative rounding per split to dq.
+    uint8_t* stage = ring + (size_t)r * (2 * C + 16) + par * HC * 2;   // every TMA write has been consumed
 #pragma unroll 1
     for (int ch = 0; ch < HC / 32; ++ch) {
       uint32_t o[32];
       tc_ld32(tlane + kTmO + par * HC + ch * 32, o);
       tc_wait_ld();
+      uint32_t h[16];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<uint4*>(stage + ch * 32 + 4 * j) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      for (int j = 0; j < 16; ++j) {
+        const __nv_bfloat162 pk = __floats2bfloat162_rn(__uint_as_float(o[2 * j]), __uint_as_float(o[2 * j + 1]));
+        h[j] = *reinterpret_cast<const uint32_t*>(&pk);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(stage + ch * 64 + 16 * j) = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
     }
     if (row_ok) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      bulk_store_row(po + ((size_t)split * B + row0 + r) * C + par * HC, stage, HC * 4);
+      bulk_store_row(po + ((size_t)split * B + row0 + r) * C + par * HC, stage, HC * 2);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
@@ -576,7 +585,7 @@ int launch_tc(const __nv_bfloat16* q_hat, const void* queue, int B, long long K,
   RMCL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(p.splits, p.row_blocks);
   RMCL_CUDA_OK(launch_pdl(kern, grid, dim3(kTcThreads), smem, s, tmap, q_hat, B, K, scale2, p.cols_per_split, want_argmax,
-                          out.m, out.l, out.av, out.ai, out.o));
+                          out.m, out.l, out.av, out.ai, reinterpret_cast<__nv_bfloat16*>(out.o)));
   return RMCL_OK;
 }
 
