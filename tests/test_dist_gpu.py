@@ -1,0 +1,59 @@
+"""GPU, world_size 2 over NCCL (skipped with fewer than two devices): the data-parallel exchange of the
+path — key all-gather in rank order, then the identical on-device enqueue on every replica — checked
+against the oracle, plus the silent skip on a short gathered batch (objectives.py:242-243)."""
+import os
+import sys
+import tempfile
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, init_file, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"file://{init_file}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    import rmcl_b200
+    from rmcl_b200 import objectives
+    B, C, K = 16, 64, 256
+    dev = torch.device("cuda", rank)
+    g = torch.Generator().manual_seed(100 + rank)
+    k_local = torch.nn.functional.normalize(torch.randn(B, C, generator=g), dim=1).to(dev)
+    queue0 = torch.randn(C, K, generator=torch.Generator().manual_seed(0))
+
+    class Mod:  # the attributes dequeue_and_enqueue reads (objectives.py:238-248)
+        pass
+    m = Mod()
+    m.proj_queue, m.proj_queue_ptr = queue0.to(dev), torch.tensor([K - world * B], dtype=torch.int64, device=dev)
+    m.per_step_bs = world * B
+    objectives.dequeue_and_enqueue(m, k_local)          # gather + enqueue: pointer wraps to 0
+    m.per_step_bs = world * B + 1                        # short/odd batch: silently skipped
+    objectives.dequeue_and_enqueue(m, k_local)
+    torch.cuda.synchronize()
+    gathered = rmcl_b200.concat_all_gather(k_local)
+    torch.save({"queue": m.proj_queue.cpu(), "ptr": m.proj_queue_ptr.item(), "gathered": gathered.cpu(),
+                "k_local": k_local.cpu()}, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_nccl_gather_and_replicated_enqueue_world2():
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import rmcl_oracle as O
+    world, B, C, K = 2, 16, 64, 256
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker, args=(world, os.path.join(d, "pg"), d), nprocs=world, join=True)
+        r = [torch.load(os.path.join(d, f"r{i}.pt")) for i in range(world)]
+    assert torch.equal(r[0]["gathered"], r[1]["gathered"])
+    assert torch.equal(r[0]["gathered"], O.concat_all_gather([r[0]["k_local"], r[1]["k_local"]]))   # rank order
+    queue0 = torch.randn(C, K, generator=torch.Generator().manual_seed(0))
+    want_q, want_p = O.dequeue_and_enqueue(queue0, K - world * B, r[0]["gathered"], K, per_step_bs=world * B)
+    for x in r:
+        assert x["ptr"] == want_p == 0
+        assert torch.equal(x["queue"], want_q)          # replicas bit-identical, no broadcast needed
