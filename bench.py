@@ -233,14 +233,38 @@ def run_cuda(args):
     gathered = torch.empty(world * B, C, dtype=torch.float32, device=dev) if world > 1 else None
     path = args.path
 
-    def step():
-        ops.ema_multi_(plan, m)
-        res = ops.infonce_fwd_bwd(q, k_raw, queue, tau, normalize_k=True, path=path, want=("loss", "dq", "k_hat"))
-        keys = res["k_hat"]
+    # N>1: the key exchange (NCCL all-gather, latency-bound) and the enqueue of the gathered keys ride a
+    # side stream under the HBM-bound EMA, which shares no data with them; the two streams are joined at
+    # the end of every step, so a step stays one unit.  (The EMA has no data dependency on the InfoNCE
+    # either in this kernels-only step — the link in the full step is the key-encoder forward — but
+    # running those two concurrently measured no gain: both want every SM.)
+    main_stream = torch.cuda.current_stream()
+    side_stream = torch.cuda.Stream() if world > 1 else None
+    ev_fwd, ev_side = torch.cuda.Event(), torch.cuda.Event()
+
+    def exchange_and_enqueue(keys):
         if world > 1:
             dist.all_gather_into_tensor(gathered, keys)
             keys = gathered
         ops.enqueue_(queue, keys, ptr)
+
+    def step(qq=None, kk=None, after_fwd=None):
+        qq, kk = (q, k_raw) if qq is None else (qq, kk)
+        if world == 1:
+            ops.ema_multi_(plan, m)
+            res = ops.infonce_fwd_bwd(qq, kk, queue, tau, normalize_k=True, path=path, want=("loss", "dq", "k_hat"))
+            exchange_and_enqueue(res["k_hat"])
+            return res
+        res = ops.infonce_fwd_bwd(qq, kk, queue, tau, normalize_k=True, path=path, want=("loss", "dq", "k_hat"))
+        ev_fwd.record(main_stream)
+        side_stream.wait_event(ev_fwd)
+        with torch.cuda.stream(side_stream):
+            if after_fwd is not None:
+                after_fwd(res)          # e2e: the result read-back goes out as soon as the InfoNCE is done
+            exchange_and_enqueue(res["k_hat"])
+            ev_side.record(side_stream)
+        ops.ema_multi_(plan, m)
+        main_stream.wait_event(ev_side)
         return res
 
     def barrier():
@@ -290,12 +314,10 @@ def run_cuda(args):
         def e2e_step():
             q_dev.copy_(q_host, non_blocking=True)
             k_dev.copy_(k_host, non_blocking=True)
-            ops.ema_multi_(plan, m)
-            r = ops.infonce_fwd_bwd(q_dev, k_dev, queue, tau, normalize_k=True, path=path, want=("loss", "dq", "k_hat"))
-            dist.all_gather_into_tensor(gathered, r["k_hat"])
-            ops.enqueue_(queue, gathered, ptr)
-            loss_host.copy_(r["loss"], non_blocking=True)
-            dq_host.copy_(r["dq"], non_blocking=True)
+            def read_back(r):
+                loss_host.copy_(r["loss"], non_blocking=True)
+                dq_host.copy_(r["dq"], non_blocking=True)
+            step(q_dev, k_dev, after_fwd=read_back)
             torch.cuda.current_stream().synchronize()
 
     for _ in range(3):
@@ -383,7 +405,7 @@ def run_cuda(args):
         "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, **CFG, "arithmetic": "InfoNCE: bf16 queue/q/k operands, fp32 accumulation and statistics; EMA: fp32 (bit-exact with ATen); enqueue: fp32 keys -> bf16 queue", "per_gpu_batch": B, "global_batch": world * B, "infonce_path": path,
-                   "parallelism": f"dp{world}", "unit_of_value": "256-sample rank-steps per second, summed over ranks",
+                   "parallelism": f"dp{world}", "streams": "single stream" if world == 1 else "key all-gather + enqueue on a side stream under the EMA, joined every step", "unit_of_value": "256-sample rank-steps per second, summed over ranks",
                    "l2": "inputs larger than L2: each step streams 1.34 GB of parameters (EMA) between InfoNCE passes; L2 is 126 MB"},
         "roofline": roofline, "kernels": kernels,
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
