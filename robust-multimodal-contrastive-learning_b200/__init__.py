@@ -10,7 +10,7 @@ from . import ops  # noqa: F401
 from .dist import concat_all_gather  # noqa: F401
 from .moco import MoCo  # noqa: F401
 from .objectives import (compute_moco_contrastive, compute_pgd, dequeue_and_enqueue,  # noqa: F401
-                         momentum_update_key_encoder)
+                         momentum_update_key_encoder, shadow_layer)
 from .pgd_attack import PGDAttack, PGDAttack_moco  # noqa: F401
 
 __version__ = "0.1.0"

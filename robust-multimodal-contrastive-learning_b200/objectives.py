@@ -29,6 +29,13 @@ _KEY_QUERY_LAYERS = (  # objectives.py:257-260, in this order
 )
 
 
+def shadow_layer(q_layer, k_layer):
+    """vilt_module.py:270-273 (``_shadow_layer``): initialise a key layer from its query layer and freeze it."""
+    for param_q, param_k in zip(q_layer.parameters(), k_layer.parameters()):
+        param_k.data.copy_(param_q.data)
+        param_k.requires_grad = False
+
+
 def momentum_update_key_encoder(pl_module):
     """objectives.py:219-224 + 257-260 as one launch; the chunk table is cached on the module."""
     plan = pl_module.__dict__.get("_rmcl_ema_plan")
