@@ -119,6 +119,10 @@ def infonce_fwd_bwd(q, k, queue, temperature, *, loss_scale=1.0, normalize_k=Fal
     if queue.stride(1) != 1:
         raise ValueError("queue must be [C,K] with K contiguous (reference layout)")
     q, k = q.detach().contiguous(), k.detach().contiguous()
+    if q.dtype not in _DT:      # e.g. fp16 projections under Lightning precision=16: the kernels take fp32 / bf16
+        q = q.float()
+    if k.dtype not in _DT:
+        k = k.float()
     B, Cd = q.shape
     K, ldq = queue.shape[1], queue.stride(0)
     pth = _lib.INFONCE_PATHS[path]
