@@ -22,6 +22,7 @@ the reference arithmetic itself); the CUDA arm never imports it.
 """
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -369,6 +370,40 @@ def run_cuda(args):
             ach, peak, unit = work / t / 1e12, pk_peak["tf_sust"], "TFLOP/s"
         kernels[name] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                          "ms": kern_ms[name], "traffic": traffic.get(name)}
+    # ---- the tcgen05 partial kernel over CONSECUTIVE launches (one event pair around the whole batch).
+    #      An event pair around a single launch inside a PDL chain also times ~5-10 us of launch/event
+    #      latency (tools/tc_timeline.py: %globaltimer span of the kernel 20-21 us, 3-4 us of it spent in
+    #      griddepcontrol.wait for prep, against 27-30 us between the bracketing events), so the bracketed
+    #      number above is an upper bound.  Here 8 distinct queue copies (8 x C*K*2 B > the 126 MB L2) are
+    #      cycled so that every launch streams its queue from HBM as it does in the step.
+    if world == 1 and path in ("auto", "tcgen05"):
+        gq2 = torch.Generator(device=dev).manual_seed(11)
+        n_copies = max(2, int(math.ceil(160e6 / (C * K * 2))) + 1)
+        queues = [queue] + [torch.randn(C, K, device=dev, generator=gq2).bfloat16() for _ in range(n_copies - 1)]
+        ops.infonce_fwd_bwd(q, k_raw, queue, tau, normalize_k=True, path=path, want=("loss", "dq", "k_hat"))
+        n_b2b = 8 * n_copies
+
+        def partial_batch():
+            for j in range(n_b2b):
+                ops.infonce_fwd_bwd(q, k_raw, queues[j % n_copies], tau, normalize_k=True, path=path,
+                                    want=(), _partial_only=True)
+
+        partial_batch()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()          # the launches are replayed as one graph so that the host (ctypes
+        with torch.cuda.graph(graph):           # call overhead ~ kernel duration) cannot starve the stream
+            partial_batch()
+        graph.replay()
+        ms_b2b = min(timed(graph.replay, 1) for _ in range(5)) / n_b2b
+        kp = kernels["infonce_partial"]
+        kp["ms_consecutive"] = ms_b2b
+        kp["achieved_consecutive"] = flops_infonce / (ms_b2b * 1e-3) / 1e12
+        kp["frac_consecutive"] = kp["achieved_consecutive"] / kp["peak"]
+        kp["method"] = ("ms/achieved/frac: one CUDA-event pair around the single launch inside the step (includes launch + "
+                        "event latency of a PDL-chained launch); *_consecutive: one event pair around %d back-to-back "
+                        "launches (one CUDA graph) cycling over %d queue copies (> L2), divided by the count" % (n_b2b, n_copies))
+        del graph, queues
+
     # ---- cfg3: the PGD update kernel alone (not part of the cfg2 step): B=128, 5 steps, pixel and
     #      embedding perturbations; 12 B/element (read g, read delta, write delta)
     if world == 1 and not args.no_pgd:

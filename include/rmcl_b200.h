@@ -51,6 +51,10 @@ typedef enum { RMCL_INFONCE_AUTO = 0, RMCL_INFONCE_SIMT = 1, RMCL_INFONCE_TCGEN0
 /* flags for rmcl_infonce_fwd_bwd */
 #define RMCL_INFONCE_NORMALIZE_K 1u /* k is a raw projection: L2-normalise it too (objectives.py:265) */
 #define RMCL_INFONCE_NO_GRAD 2u     /* forward only (clean-query call, objectives.py:269-275)        */
+/* Measurement aid: launch only the split-K partial kernel, on the q^/k^ a previous full call with the
+ * same shapes left in `workspace` (no prep, no finalize, outputs untouched).  bench.py uses it to time
+ * the dominant InfoNCE kernel over consecutive launches. */
+#define RMCL_INFONCE_DEBUG_PARTIAL_ONLY 4u
 
 const char* rmcl_last_error(void);
 int rmcl_version(void);      /* 1000*major + minor */
@@ -118,6 +122,12 @@ int rmcl_infonce_fwd_bwd(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_
 int rmcl_profile_enable(int on);
 int rmcl_profile_infonce_ms(float* out3);
 
+/* Measurement aid: while `dev_buf` (device memory, rmcl_debug_tc_timeline_words() int64) is set on
+ * the calling thread, CTA (0,0) of every tcgen05 InfoNCE launch stamps clock64() at its protocol
+ * points into it (layout: csrc/infonce_tc.cu, tl_stamp).  NULL switches it off (the default). */
+int rmcl_debug_tc_timeline(long long* dev_buf);
+int rmcl_debug_tc_timeline_words(void);
+
 /* ---------------------------------------------------------------------------------------------
  * Ring-buffer enqueue:  queue[:, ptr:ptr+B] = keys^T ;  ptr = (ptr + B) % K, all on the device.
  * replaces: objectives.py:244-248 (int(ptr) D2H sync, strided slice-assign, host modulo, H2D
@@ -131,11 +141,22 @@ int rmcl_profile_infonce_ms(float* out3);
 int rmcl_enqueue(void* queue, rmcl_dtype queue_dtype, const void* keys, rmcl_dtype keys_dtype,
                  int64_t* ptr_dev, int B, int C, int64_t K, int64_t ldq, void* stream);
 
+/* Same, and the same B columns are also written (rounded to bf16) into `shadow_bf16` [C,K] (row
+ * stride lds): a half-precision copy of the queue kept current at B*C*2 bytes per step, so that the
+ * tcgen05 InfoNCE path can run against a checkpoint-compatible fp32 queue.
+ * replaces: the per-call autocast cast of the whole queue under Lightning precision=16
+ *           (objectives.py:270-272, 329: `proj_queue.clone()` + half-precision einsum). */
+int rmcl_enqueue_shadow(void* queue, rmcl_dtype queue_dtype, void* shadow_bf16, int64_t lds,
+                        const void* keys, rmcl_dtype keys_dtype, int64_t* ptr_dev, int B, int C,
+                        int64_t K, int64_t ldq, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * One PGD perturbation update on delta[B,N] given grad[B,N] (per-sample norms over N).
  * replaces: attack/pgd_attack_vilt.py:162-173 (clone/float, inf-norm, clamp, scale, add, clamp:
  *           7 kernels, 5 passes).  Works on pixels [B,3,H,W] or embeddings [B,L,768] viewed [B,N].
  * REF_LINF in f32 is bit-identical to the reference: fadd(delta, fdiv(fmul(lr,g), d)).
+ * L2 with eps > 0 takes the projection scale from |delta|^2 + 2a<delta,g> + a^2|g|^2 (a = lr/|g|),
+ * so delta is written once, already projected.
  * One persistent launch; the gradient is re-read from L2, so DRAM sees 12 B/element.
  *   workspace  rmcl_pgd_workspace_bytes(B, N, grad_dtype) bytes, 256-byte aligned, caller-owned
  *              (arrival counters + per-chunk partial norms).  It must be ZERO-FILLED once before

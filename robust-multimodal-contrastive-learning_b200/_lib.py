@@ -7,17 +7,20 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librmcl_b200.so")
+# RMCL_B200_LIB selects an experiment build of the same library (csrc/build.py --out ... -D...); it must
+# exist — there is still no fallback.
+LIB_PATH = os.path.join(_HERE, os.environ.get("RMCL_B200_LIB", "librmcl_b200.so"))
 
 RMCL_F32, RMCL_BF16 = 0, 1
 PGD_MODES = {"ref_linf": 0, "sign_linf": 1, "l2": 2}
 INFONCE_PATHS = {"auto": 0, "simt": 1, "tcgen05": 2}
-FLAG_NORMALIZE_K, FLAG_NO_GRAD = 1, 2
+FLAG_NORMALIZE_K, FLAG_NO_GRAD, FLAG_DEBUG_PARTIAL_ONLY = 1, 2, 4
 
 EXPORTS = (
     "rmcl_last_error", "rmcl_version", "rmcl_sm_count", "rmcl_ema_plan", "rmcl_ema_multi",
     "rmcl_infonce_workspace_bytes", "rmcl_infonce_fwd_bwd", "rmcl_enqueue", "rmcl_pgd_workspace_bytes", "rmcl_pgd_step", "rmcl_step_host",
-    "rmcl_profile_enable", "rmcl_profile_infonce_ms",
+    "rmcl_profile_enable", "rmcl_profile_infonce_ms", "rmcl_enqueue_shadow", "rmcl_debug_tc_timeline",
+    "rmcl_debug_tc_timeline_words",
 )
 
 
@@ -58,6 +61,14 @@ def lib():
                                        vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     L.rmcl_enqueue.restype = i32
     L.rmcl_enqueue.argtypes = [vp, i32, vp, i32, vp, i32, i32, i64, i64, vp]
+    if "RMCL_B200_LIB" in os.environ and not hasattr(L, "rmcl_enqueue_shadow"):   # A/B against an older build
+        L.rmcl_enqueue_shadow = L.rmcl_debug_tc_timeline = L.rmcl_debug_tc_timeline_words = L.rmcl_version
+    L.rmcl_enqueue_shadow.restype = i32
+    L.rmcl_enqueue_shadow.argtypes = [vp, i32, vp, i64, vp, i32, vp, i32, i32, i64, i64, vp]
+    L.rmcl_debug_tc_timeline.restype = i32
+    L.rmcl_debug_tc_timeline.argtypes = [vp]
+    L.rmcl_debug_tc_timeline_words.restype = i32
+    L.rmcl_debug_tc_timeline_words.argtypes = []
     L.rmcl_pgd_step.restype = i32
     L.rmcl_pgd_step.argtypes = [vp, i32, vp, i32, i32, i64, f32, f32, i32, vp, sz, vp]
     L.rmcl_pgd_workspace_bytes.restype = sz

@@ -20,19 +20,24 @@ def needs_rebuild():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_rebuild():
+def build(force=False, verbose=False, out=OUT, defines=()):
+    """``out``/``defines`` build an experiment variant next to the product library (tools/ab_*.py)."""
+    if out == OUT and not force and not needs_rebuild():
         return OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    cmd = [nvcc] + FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES
     r = subprocess.run(cmd, cwd=HERE, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed building librmcl_b200.so")
     if verbose:
         print(r.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    out = OUT
+    if "--out" in sys.argv:
+        out = os.path.join(os.path.dirname(HERE), sys.argv[sys.argv.index("--out") + 1])
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=out, defines=defs))

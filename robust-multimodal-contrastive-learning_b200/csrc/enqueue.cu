@@ -12,6 +12,12 @@
 // DESIGN.md.  The pointer never leaves the device: every CTA reads the low word of *ptr_dev,
 // then takes a ticket in the (otherwise zero) high word; the last CTA to arrive stores the
 // advanced 64-bit pointer, which also clears the ticket.
+//
+// rmcl_enqueue_shadow writes the same columns into a second, bf16 copy of the queue in the same launch.
+// The reference keeps the queue in fp32 (checkpoint format) and, under Lightning precision=16, lets
+// autocast re-cast all C*K elements to half precision for every einsum (objectives.py:272,329).  Keeping
+// a bf16 shadow current costs B*C*2 bytes per step here and gives the tcgen05 InfoNCE kernel its operand
+// without that per-call conversion pass.
 #include "common.cuh"
 
 namespace rmcl {
@@ -19,7 +25,8 @@ namespace rmcl {
 template <typename TK, typename TQ>
 __global__ void __launch_bounds__(256) enqueue_kernel(TQ* __restrict__ queue, const TK* __restrict__ keys,
                                                       long long* ptr_dev, int B, int C, long long K,
-                                                      long long ldq) {
+                                                      long long ldq, __nv_bfloat16* __restrict__ shadow,
+                                                      long long lds) {
   __shared__ float tile[32][33];
   __shared__ long long s_ptr;
   unsigned int* ptr_words = reinterpret_cast<unsigned int*>(ptr_dev);
@@ -39,7 +46,9 @@ __global__ void __launch_bounds__(256) enqueue_kernel(TQ* __restrict__ queue, co
     if (b < B && c < C) {
       long long col = ptr + b;
       if (col >= K) col -= K;  // only reachable when ptr is not a multiple of B
-      queue[(long long)c * ldq + col] = from_f32<TQ>(tile[tx][ty + 8 * i]);
+      const float v = tile[tx][ty + 8 * i];
+      queue[(long long)c * ldq + col] = from_f32<TQ>(v);
+      if (shadow) shadow[(long long)c * lds + col] = __float2bfloat16_rn(to_f32(from_f32<TQ>(v)));   // == bf16(queue element)
     }
   }
   if (threadIdx.x == 0) {
@@ -54,12 +63,13 @@ __global__ void __launch_bounds__(256) enqueue_kernel(TQ* __restrict__ queue, co
 
 }  // namespace rmcl
 
-extern "C" int rmcl_enqueue(void* queue, rmcl_dtype queue_dtype, const void* keys, rmcl_dtype keys_dtype,
-                            int64_t* ptr_dev, int B, int C, int64_t K, int64_t ldq, void* stream) {
+static int enqueue_impl(void* queue, rmcl_dtype queue_dtype, const void* keys, rmcl_dtype keys_dtype, int64_t* ptr_dev,
+                        int B, int C, int64_t K, int64_t ldq, void* shadow, int64_t lds, void* stream) {
   RMCL_CHECK_ARG(queue && keys && ptr_dev, "rmcl_enqueue: null pointer");
   RMCL_CHECK_ARG(B > 0 && C > 0 && K > 0 && K < (1ll << 31), "rmcl_enqueue: bad sizes B=%d C=%d K=%lld", B, C,
                  (long long)K);
   RMCL_CHECK_ARG(ldq >= K, "rmcl_enqueue: ldq < K");
+  RMCL_CHECK_ARG(!shadow || lds >= K, "rmcl_enqueue_shadow: lds < K");
   RMCL_CHECK_ARG(rmcl::dtype_ok(queue_dtype) && rmcl::dtype_ok(keys_dtype), "rmcl_enqueue: bad dtype");
   RMCL_CHECK_ARG(B <= K && K % B == 0, "rmcl_enqueue: queue length %lld is not a multiple of the batch %d",
                  (long long)K, B);
@@ -68,14 +78,27 @@ extern "C" int rmcl_enqueue(void* queue, rmcl_dtype queue_dtype, const void* key
   cudaStream_t s = (cudaStream_t)stream;
   long long* p = reinterpret_cast<long long*>(ptr_dev);
   using bf16 = __nv_bfloat16;
+  bf16* sh = reinterpret_cast<bf16*>(shadow);
   if (keys_dtype == RMCL_F32 && queue_dtype == RMCL_F32)
-    rmcl::enqueue_kernel<float, float><<<grid, 256, 0, s>>>((float*)queue, (const float*)keys, p, B, C, K, ldq);
+    rmcl::enqueue_kernel<float, float><<<grid, 256, 0, s>>>((float*)queue, (const float*)keys, p, B, C, K, ldq, sh, lds);
   else if (keys_dtype == RMCL_F32 && queue_dtype == RMCL_BF16)
-    rmcl::enqueue_kernel<float, bf16><<<grid, 256, 0, s>>>((bf16*)queue, (const float*)keys, p, B, C, K, ldq);
+    rmcl::enqueue_kernel<float, bf16><<<grid, 256, 0, s>>>((bf16*)queue, (const float*)keys, p, B, C, K, ldq, sh, lds);
   else if (keys_dtype == RMCL_BF16 && queue_dtype == RMCL_F32)
-    rmcl::enqueue_kernel<bf16, float><<<grid, 256, 0, s>>>((float*)queue, (const bf16*)keys, p, B, C, K, ldq);
+    rmcl::enqueue_kernel<bf16, float><<<grid, 256, 0, s>>>((float*)queue, (const bf16*)keys, p, B, C, K, ldq, sh, lds);
   else
-    rmcl::enqueue_kernel<bf16, bf16><<<grid, 256, 0, s>>>((bf16*)queue, (const bf16*)keys, p, B, C, K, ldq);
+    rmcl::enqueue_kernel<bf16, bf16><<<grid, 256, 0, s>>>((bf16*)queue, (const bf16*)keys, p, B, C, K, ldq, sh, lds);
   RMCL_LAUNCH_OK("enqueue_kernel");
   return RMCL_OK;
+}
+
+extern "C" int rmcl_enqueue(void* queue, rmcl_dtype queue_dtype, const void* keys, rmcl_dtype keys_dtype,
+                            int64_t* ptr_dev, int B, int C, int64_t K, int64_t ldq, void* stream) {
+  return enqueue_impl(queue, queue_dtype, keys, keys_dtype, ptr_dev, B, C, K, ldq, nullptr, 0, stream);
+}
+
+extern "C" int rmcl_enqueue_shadow(void* queue, rmcl_dtype queue_dtype, void* shadow_bf16, int64_t lds, const void* keys,
+                                   rmcl_dtype keys_dtype, int64_t* ptr_dev, int B, int C, int64_t K, int64_t ldq,
+                                   void* stream) {
+  RMCL_CHECK_ARG(shadow_bf16 != nullptr, "rmcl_enqueue_shadow: null shadow");
+  return enqueue_impl(queue, queue_dtype, keys, keys_dtype, ptr_dev, B, C, K, ldq, shadow_bf16, lds, stream);
 }

@@ -63,7 +63,7 @@ int infonce_make_plan(int B, int C, long long K, int queue_dtype, int path, bool
   p->off_khat = take(Bs * C * 4);
   p->off_inv = take(Bs * 4);
   p->off_pos2 = take(Bs * 4);
-  p->off_qhat_bf16 = take((size_t)p->b_pad * C * 2);
+  p->off_qhat_bf16 = take((size_t)kQhatReplicas * p->b_pad * C * 2);
   p->off_m = take(S * Bs * 4);
   p->off_l = take(S * Bs * 4);
   p->off_av = take(S * Bs * 4);
@@ -100,8 +100,10 @@ __global__ void __launch_bounds__(128) infonce_prep_kernel(const TQ* __restrict_
   const int row = blockIdx.x;
   if (threadIdx.x == 0) pdl_trigger();   // the partial kernel may set itself up while this one runs
   if (row == 0 && threadIdx.x == 0) *counter = 0u;
-  if (row >= B) {  // padding rows of the bf16 operand (TMA reads whole 128-row boxes)
-    for (int c = threadIdx.x; c < C; c += 128) q_hat_bf16[(size_t)row * C + c] = __float2bfloat16_rn(0.f);
+  const size_t rep_stride = (size_t)b_pad * C;   // kQhatReplicas copies of the bf16 operand (infonce.cuh)
+  if (row >= B) {  // padding rows of the bf16 operand (the tcgen05 kernel reads whole 128-row blocks)
+    for (int c = threadIdx.x; c < C; c += 128)
+      for (int rep = 0; rep < kQhatReplicas; ++rep) q_hat_bf16[rep * rep_stride + (size_t)row * C + c] = __float2bfloat16_rn(0.f);
     return;
   }
   const TQ* qr = q + (size_t)row * C;
@@ -123,7 +125,11 @@ __global__ void __launch_bounds__(128) infonce_prep_kernel(const TQ* __restrict_
     q_hat[(size_t)row * C + c] = qh;
     k_hat[(size_t)row * C + c] = kh;
     if (k_hat_out) k_hat_out[(size_t)row * C + c] = kh;
-    if (q_hat_bf16) q_hat_bf16[(size_t)row * C + c] = __float2bfloat16_rn(qh);
+    if (q_hat_bf16) {
+      const __nv_bfloat16 qb = __float2bfloat16_rn(qh);
+#pragma unroll
+      for (int rep = 0; rep < kQhatReplicas; ++rep) q_hat_bf16[rep * rep_stride + (size_t)row * C + c] = qb;
+    }
     dot = fmaf(round_if(qh, bf16_mode), round_if(kh, bf16_mode), dot);
   }
   dot = block_sum_128(dot, red);
@@ -413,8 +419,11 @@ extern "C" int rmcl_infonce_fwd_bwd(const void* q, rmcl_dtype q_dtype, const voi
   const bool want_grad = (flags & RMCL_INFONCE_NO_GRAD) == 0 && (dq || dk);
   const bool tc = (p.path == RMCL_INFONCE_TCGEN05);
   using bf16 = __nv_bfloat16;
+  const bool partial_only = (flags & RMCL_INFONCE_DEBUG_PARTIAL_ONLY) != 0;   // measurement aid, see the header
   RMCL_PROF_MARK(0);
-  if (q_dtype == RMCL_F32 && k_dtype == RMCL_F32)
+  if (partial_only)
+    rc = RMCL_OK;
+  else if (q_dtype == RMCL_F32 && k_dtype == RMCL_F32)
     rc = launch_prep<float, float>(q, k, B, C, scale2, nk, bf16_mode, ws, p, k_hat_out, tc, s);
   else if (q_dtype == RMCL_F32)
     rc = launch_prep<float, bf16>(q, k, B, C, scale2, nk, bf16_mode, ws, p, k_hat_out, tc, s);
@@ -433,6 +442,7 @@ extern "C" int rmcl_infonce_fwd_bwd(const void* q, rmcl_dtype q_dtype, const voi
     rc = infonce_simt_launch((const float*)(ws + p.off_qhat), queue, queue_dtype, B, C, K, ldq, scale2, p, parts, s);
   if (rc != RMCL_OK) return rc;
   RMCL_PROF_MARK(2);
+  if (partial_only) return RMCL_OK;
 
   const size_t fin_smem = ((size_t)((p.splits + 3) & ~3) + (size_t)(kFinGroups - 1) * C) * sizeof(float);
   if (tc) {

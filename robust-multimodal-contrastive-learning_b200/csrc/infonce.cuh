@@ -15,6 +15,16 @@
 
 namespace rmcl {
 
+// The bf16 copy of Q^ is the one operand every CTA of the tcgen05 kernel reads in full at the same
+// moment (148 CTAs x 64 KB out of a 128 KB footprint at cfg2): that is ~6 cache lines per L2 slice,
+// each requested 74 times, and the slice imbalance (not the volume) set the fill time.  prep writes
+// kQhatReplicas copies and CTA `split` reads copy split % kQhatReplicas, which spreads the same traffic
+// over 8x more lines.
+#ifndef RMCL_QHAT_REPLICAS
+#define RMCL_QHAT_REPLICAS 8
+#endif
+constexpr int kQhatReplicas = RMCL_QHAT_REPLICAS;
+
 struct InfoNcePlan {
   int path;             // RMCL_INFONCE_SIMT / RMCL_INFONCE_TCGEN05 (never AUTO)
   int splits;           // number of queue-axis splits

@@ -8,14 +8,17 @@
 // operation — fadd(delta, fdiv(fmul(lr,g), d)) — so fp32 results are bit-identical.
 // SIGN_LINF and L2 are the north-star's extra modes (specified in DESIGN.md).
 //
-// HBM-bound, and the per-sample norm makes it a two-phase computation (three for the L2 projection):
-// the gradient is needed once for the norm and once for the update.  One persistent launch walks an
-// ordered list of work items (sample, 32 KB chunk) handed out by an atomic ticket:
-//     round r:   P1(batch r)    read g chunk            -> partial norm of the chunk
-//                P2(batch r-1)  re-read g, read delta   -> write delta'   (+ partial |delta'|^2 for L2)
-//                P3(batch r-2)  (L2 only, if it shrinks) re-read delta', scale, write
+// HBM-bound, and the per-sample norm makes it a two-phase computation: the gradient is needed once
+// for the norm and once for the update.  One persistent launch walks an ordered list of work items
+// (sample, 32 KB chunk) handed out by an atomic ticket:
+//     round r:   P1(batch r)    read g chunk (L2: also delta) -> partial norm(s) of the chunk
+//                P2(batch r-1)  re-read g, read delta         -> write delta'
+// The L2 projection needs |delta + a g|_2 (a = lr/|g|_2) before anything is written; it is taken from
+//     |delta + a g|^2 = |delta|^2 + 2a <delta,g> + a^2 |g|^2
+// so P1 reduces three sums and delta' is written exactly once, already projected (a first version wrote
+// the unprojected delta', reduced its norm and rescaled it in a third phase: 16 B/element, 47 % of roof).
 // A batch is a group of samples whose gradients fit in a fraction of the 126 MB L2, so that the
-// re-read of P2 (and P3) is served by L2 and DRAM sees the algorithmic minimum of 12 B/element
+// re-read of P2 is served by L2 and DRAM sees the algorithmic minimum of 12 B/element
 // (read g, read delta, write delta).  A later-phase item spins on a per-sample arrival counter; all
 // the items it waits for have smaller tickets, i.e. are already running, so the wait cannot deadlock
 // regardless of how many CTAs are resident.  Per-chunk partials are combined by a fixed-shape tree, so
@@ -24,8 +27,19 @@
 
 namespace rmcl {
 
+#ifndef RMCL_PGD_PREFETCH
+#define RMCL_PGD_PREFETCH 1
+#endif
+#ifndef RMCL_PGD_CHUNK_KB
+#define RMCL_PGD_CHUNK_KB 32
+#endif
+// resident CTAs per SM asked of ptxas for the fp32/fp32 kernel (48 registers): the loads in flight, not the
+// arithmetic, set the speed — at 64 registers / 4 CTAs the same code ran 16 % slower
+#ifndef RMCL_PGD_MIN_CTAS
+#define RMCL_PGD_MIN_CTAS 5
+#endif
 constexpr int kPgdThreads = 256;
-constexpr int kPgdChunkBytes = 32 * 1024;                 // per operand per work item
+constexpr int kPgdChunkBytes = RMCL_PGD_CHUNK_KB * 1024;                 // per operand per work item
 constexpr long long kPgdBatchBytes = 24ll * 1024 * 1024;  // gradient bytes per batch kept L2-resident
 
 __device__ __forceinline__ float block_reduce(float v, bool is_max, float* red /*[32]*/) {
@@ -77,21 +91,19 @@ struct PgdPlan {
   int chunks;            // work items per sample and phase
   int batch;             // samples per batch
   int n_batches;
-  int phases;            // 1 (sign: update only), 2 (norm, update), 3 (+ L2 projection)
+  int phases;            // 1 (sign: update only) or 2 (norm, update)
+  int n_sums;            // partial sums per chunk: 1 (max|g| or sum g^2) or 3 (+ <delta,g>, |delta|^2 for the L2 projection)
   long long total_items;
   // workspace
   unsigned int* ticket;  // [1]
   unsigned int* exits;   // [1] CTAs that have left the work loop
-  unsigned int* done1;   // [B] chunks of the sample whose first phase has finished
-  unsigned int* done2;   // [B]
-  float* part1;          // [B][chunks] per-chunk max|g| or sum g^2
-  float* norm1;          // [B] combined by the last arriving chunk of the sample
-  float* part2;          // [B][chunks] per-chunk sum delta'^2
-  float* norm2;          // [B]
+  unsigned int* done;    // [B] chunks of the sample whose norm phase has finished (+1 once the totals are published)
+  float* part;           // [3][B][chunks] per-chunk partials
+  float* norm;           // [3][B] totals, combined by the last arriving chunk of the sample
 };
 
 struct PgdItem {
-  int phase;  // 0 = norm, 1 = update, 2 = project
+  int phase;  // 0 = norm, 1 = update
   int sample;
   int chunk;
 };
@@ -121,72 +133,91 @@ __device__ __forceinline__ void spin_until(const unsigned int* counter, unsigned
   } while (v < target);
 }
 
-// Stores this item's partial; the item that arrives last for its sample combines all the sample's
+// Stores this item's partials; the item that arrives last for its sample combines all the sample's
 // partials (thread c takes chunks c, c+256, ... then a fixed-shape block tree: deterministic no matter
-// which CTA happens to be last) and publishes the sample norm, followed by one more arrival, so that
+// which CTA happens to be last) and publishes the sample totals, followed by one more arrival, so that
 // waiters need a single load.  Must be called by the whole CTA.
-__device__ __forceinline__ bool pgd_publish_partial(float* part, float* norms, unsigned int* done, const PgdItem& it,
-                                                    int chunks, float value, bool is_max, float* red) {
+__device__ __forceinline__ void pgd_publish_partials(const PgdPlan& p, const PgdItem& it, float v0, float v1, float v2,
+                                                     bool is_max, float* red) {
   __shared__ bool s_last;
+  const long long plane = (long long)p.B * p.chunks;
   if (threadIdx.x == 0) {
-    part[(long long)it.sample * chunks + it.chunk] = value;
+    float* dst = p.part + (long long)it.sample * p.chunks + it.chunk;
+    dst[0] = v0;
+    if (p.n_sums == 3) {
+      dst[plane] = v1;
+      dst[2 * plane] = v2;
+    }
     __threadfence();
-    s_last = (atomicAdd(done + it.sample, 1u) == (unsigned)chunks - 1u);
+    s_last = (atomicAdd(p.done + it.sample, 1u) == (unsigned)p.chunks - 1u);
   }
   __syncthreads();
-  if (!s_last) return false;
+  if (!s_last) return;
   __threadfence();
-  const float* pp = part + (long long)it.sample * chunks;
-  float acc = 0.f;
-  for (int c = threadIdx.x; c < chunks; c += kPgdThreads) {
-    const float v = __ldcg(pp + c);
-    acc = is_max ? fmaxf(acc, v) : acc + v;
+  for (int k = 0; k < p.n_sums; ++k) {
+    const float* pp = p.part + k * plane + (long long)it.sample * p.chunks;
+    float acc = 0.f;
+    for (int c = threadIdx.x; c < p.chunks; c += kPgdThreads) {
+      const float v = __ldcg(pp + c);
+      acc = is_max ? fmaxf(acc, v) : acc + v;
+    }
+    acc = block_reduce(acc, is_max, red);
+    if (threadIdx.x == 0) p.norm[k * p.B + it.sample] = acc;
   }
-  acc = block_reduce(acc, is_max, red);
   if (threadIdx.x == 0) {
-    norms[it.sample] = acc;
     __threadfence();
-    atomicAdd(done + it.sample, 1u);
+    atomicAdd(p.done + it.sample, 1u);
   }
-  return true;
 }
 
 template <typename TD, typename TG>
-__global__ void __launch_bounds__(kPgdThreads) pgd_ticket_kernel(TD* __restrict__ delta, const TG* __restrict__ grad,
+__global__ void __launch_bounds__(kPgdThreads, (sizeof(TD) + sizeof(TG) == 8) ? RMCL_PGD_MIN_CTAS : 4) pgd_ticket_kernel(TD* __restrict__ delta, const TG* __restrict__ grad,
                                                                  const PgdPlan p) {
   __shared__ float red[32];
   __shared__ PgdItem s_item;
-  __shared__ float s_norm;
+  __shared__ float s_norm[2];   // denominator, projection scale of the current item's sample
   constexpr int VG = 16 / sizeof(TG), VD = 16 / sizeof(TD);
   constexpr int VE = VG > VD ? VG : VD;  // elements per thread step in the vector path (8 if any bf16, else 4)
   const bool is_max = (p.mode == RMCL_PGD_REF_LINF);
   const bool vec = (p.N % VE == 0) && (p.chunk_elems % VE == 0) &&
                    (((reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(delta)) & 15u) == 0);
-  const bool l2proj = (p.mode == RMCL_PGD_L2) && (p.eps > 0.f);
+  const bool l2proj = (p.n_sums == 3);
   const bool do_clamp = (p.eps > 0.f) && (p.mode != RMCL_PGD_L2);
-  // g is read twice a few tens of MB apart: keep it (evict_last) until its second use, then let it go;
-  // delta is touched once (twice under the L2 projection) and must not push g out of L2.
+  // g (and delta under the L2 projection) is read twice a few tens of MB apart: keep it (evict_last)
+  // until its second use, then let it go; everything touched once must not push it out of L2.
   const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
 
+  // The next ticket is always requested one item ahead, so the atomic's L2 round trip overlaps the
+  // data phase of the current item.  A ticket held this way is still started only after every smaller
+  // ticket taken by this CTA has finished, so the "everything I wait for is already running or will
+  // run without waiting for me" argument (top of file) is unchanged.
+  long long t_next = 0;
+  bool first = true;
+  (void)first;
+  if (threadIdx.x == 0) t_next = (long long)atomicAdd(p.ticket, 1u);
   for (;;) {
     __syncthreads();
-    if (threadIdx.x == 0) {
-      const long long t = (long long)atomicAdd(p.ticket, 1u);
-      s_item = (t < p.total_items) ? pgd_decode(p, t) : PgdItem{-1, 0, 0};
-    }
+#if !RMCL_PGD_PREFETCH
+    if (threadIdx.x == 0 && !first) t_next = (long long)atomicAdd(p.ticket, 1u);
+    first = false;
+#endif
+    if (threadIdx.x == 0) s_item = (t_next < p.total_items) ? pgd_decode(p, t_next) : PgdItem{-1, 0, 0};
     __syncthreads();
     const PgdItem it = s_item;
     if (it.phase < 0) {
       // The last CTA to leave returns the control words to zero, so the next call needs no memset launch
       // (every item has completed by then: a CTA only gets here after finishing all its items).
       if (threadIdx.x == 0 && atomicAdd(p.exits, 1u) == gridDim.x - 1u) {
-        for (int i = 0; i < 2 * p.B; ++i) p.done1[i] = 0u;   // done1 and done2 are contiguous
+        for (int i = 0; i < p.B; ++i) p.done[i] = 0u;
         *p.exits = 0u;
         __threadfence();
         *p.ticket = 0u;
       }
       break;
     }
+#if RMCL_PGD_PREFETCH
+    if (threadIdx.x == 0) t_next = (long long)atomicAdd(p.ticket, 1u);
+#endif
     const long long e0 = (long long)it.chunk * p.chunk_elems;
     long long n = p.N - e0;
     if (n > p.chunk_elems) n = p.chunk_elems;
@@ -194,9 +225,9 @@ __global__ void __launch_bounds__(kPgdThreads) pgd_ticket_kernel(TD* __restrict_
     TD* d = delta + (long long)it.sample * p.N + e0;
 
     if (it.phase == 0) {
-      // ------------------------------------------------------------ P1: partial norm of the chunk
-      float acc = 0.f;
-      if (vec) {
+      // ------------------------------------------------------------ P1: partial norm(s) of the chunk
+      float acc = 0.f, adg = 0.f, add = 0.f;
+      if (vec && !l2proj) {
         const uint4* gv = reinterpret_cast<const uint4*>(g);
         const long long nv = n / VG;
         long long i = threadIdx.x;
@@ -223,27 +254,83 @@ __global__ void __launch_bounds__(kPgdThreads) pgd_ticket_kernel(TD* __restrict_
             acc = is_max ? fmaxf(acc, fabsf(x)) : fmaf(x, x, acc);
           }
         }
+      } else if (vec) {
+        // L2 with projection: |g|^2, <delta,g>, |delta|^2 in one sweep; both operands stay in L2 for P2
+        const long long nv = n / VE;
+        for (long long i = threadIdx.x; i < nv; i += 2 * kPgdThreads) {
+          const bool second = (i + kPgdThreads) < nv;
+          float gx[2][VE], dx[2][VE];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !second) break;
+            const long long base = (i + h * kPgdThreads) * VE;
+#pragma unroll
+            for (int q = 0; q < VE / VG; ++q) {
+              const uint4 u = ld_u4_hint(reinterpret_cast<const uint4*>(g + base) + q, keep);
+              const TG* e = reinterpret_cast<const TG*>(&u);
+#pragma unroll
+              for (int j = 0; j < VG; ++j) gx[h][q * VG + j] = to_f32(e[j]);
+            }
+#pragma unroll
+            for (int q = 0; q < VE / VD; ++q) {
+              const uint4 u = ld_u4_hint(reinterpret_cast<const uint4*>(d + base) + q, keep);
+              const TD* e = reinterpret_cast<const TD*>(&u);
+#pragma unroll
+              for (int j = 0; j < VD; ++j) dx[h][q * VD + j] = to_f32(e[j]);
+            }
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !second) break;
+#pragma unroll
+            for (int j = 0; j < VE; ++j) {
+              acc = fmaf(gx[h][j], gx[h][j], acc);
+              adg = fmaf(dx[h][j], gx[h][j], adg);
+              add = fmaf(dx[h][j], dx[h][j], add);
+            }
+          }
+        }
       } else {
         for (long long i = threadIdx.x; i < n; i += kPgdThreads) {
           const float x = to_f32(g[i]);
           acc = is_max ? fmaxf(acc, fabsf(x)) : fmaf(x, x, acc);
+          if (l2proj) {
+            const float y = to_f32(d[i]);
+            adg = fmaf(y, x, adg);
+            add = fmaf(y, y, add);
+          }
         }
       }
       acc = block_reduce(acc, is_max, red);
-      pgd_publish_partial(p.part1, p.norm1, p.done1, it, p.chunks, acc, is_max, red);
-    } else if (it.phase == 1) {
+      if (l2proj) {
+        adg = block_reduce(adg, false, red);
+        add = block_reduce(add, false, red);
+      }
+      pgd_publish_partials(p, it, acc, adg, add, is_max, red);
+    } else {
       // ------------------------------------------------------------ P2: the update
-      float denom = 1.f;
+      float denom = 1.f, proj = 1.f;
       if (p.mode != RMCL_PGD_SIGN_LINF) {
         if (threadIdx.x == 0) {
-          spin_until(p.done1 + it.sample, (unsigned)p.chunks + 1u);   // +1: the sample norm has been published
-          s_norm = __ldcg(p.norm1 + it.sample);
+          spin_until(p.done + it.sample, (unsigned)p.chunks + 1u);   // +1: the sample totals have been published
+          const float tot = __ldcg(p.norm + it.sample);
+          const float dn = fmaxf(is_max ? tot : sqrtf(tot), 1e-8f);
+          float pj = 1.f;
+          if (l2proj) {
+            // |delta + a g|^2 with a = lr/denom, combined in double (three fp32 totals; the cross term may cancel)
+            const double a = (double)p.lr / (double)dn;
+            double n2 = (double)__ldcg(p.norm + 2 * p.B + it.sample) + 2.0 * a * (double)__ldcg(p.norm + p.B + it.sample) +
+                        a * a * (double)tot;
+            if (n2 < 0.0) n2 = 0.0;
+            pj = fminf(__fdiv_rn(p.eps, fmaxf((float)sqrt(n2), 1e-12f)), 1.f);
+          }
+          s_norm[0] = dn;
+          s_norm[1] = pj;
         }
         __syncthreads();
-        const float tot = s_norm;
-        denom = fmaxf(is_max ? tot : sqrtf(tot), 1e-8f);
+        denom = s_norm[0];
+        proj = s_norm[1];
       }
-      float acc2 = 0.f;
       if (vec) {
         // one thread step = VE elements = 16 B of the narrower-typed operand
         const long long nv = n / VE;
@@ -281,10 +368,10 @@ __global__ void __launch_bounds__(kPgdThreads) pgd_ticket_kernel(TD* __restrict_
               for (int j = 0; j < VD; ++j) {
                 float v = pgd_apply<TD>(dx[h][q * VD + j], gx[h][q * VD + j], p.lr, denom, p.mode);
                 if (do_clamp) v = clamp_eps<TD>(v, p.eps);
-                acc2 = fmaf(v, v, acc2);
+                if (l2proj && proj < 1.f) v = __fmul_rn(v, proj);
                 e[j] = from_f32<TD>(v);
               }
-              st_u4_hint(reinterpret_cast<uint4*>(d + base) + q, u, l2proj ? keep : stream);  // P3 re-reads delta'
+              st_u4_hint(reinterpret_cast<uint4*>(d + base) + q, u, stream);
             }
           }
         }
@@ -292,43 +379,15 @@ __global__ void __launch_bounds__(kPgdThreads) pgd_ticket_kernel(TD* __restrict_
         for (long long i = threadIdx.x; i < n; i += kPgdThreads) {
           float v = pgd_apply<TD>(to_f32(d[i]), to_f32(g[i]), p.lr, denom, p.mode);
           if (do_clamp) v = clamp_eps<TD>(v, p.eps);
-          acc2 = fmaf(v, v, acc2);
+          if (l2proj && proj < 1.f) v = __fmul_rn(v, proj);
           d[i] = from_f32<TD>(v);
-        }
-      }
-      if (l2proj) {
-        acc2 = block_reduce(acc2, false, red);
-        pgd_publish_partial(p.part2, p.norm2, p.done2, it, p.chunks, acc2, false, red);
-      }
-    } else {
-      // ------------------------------------------------------------ P3: L2 projection onto the eps-ball
-      if (threadIdx.x == 0) {
-        spin_until(p.done2 + it.sample, (unsigned)p.chunks + 1u);
-        s_norm = __ldcg(p.norm2 + it.sample);
-      }
-      __syncthreads();
-      const float tot = s_norm;
-      const float s = fminf(__fdiv_rn(p.eps, fmaxf(sqrtf(tot), 1e-12f)), 1.f);
-      if (s < 1.f) {
-        if (vec) {
-          uint4* dv = reinterpret_cast<uint4*>(d);
-          const long long nv = n / VD;
-          for (long long i = threadIdx.x; i < nv; i += kPgdThreads) {
-            uint4 u = ld_u4_hint(dv + i, stream);
-            TD* e = reinterpret_cast<TD*>(&u);
-#pragma unroll
-            for (int j = 0; j < VD; ++j) e[j] = from_f32<TD>(__fmul_rn(to_f32(e[j]), s));
-            st_u4_hint(dv + i, u, stream);
-          }
-        } else {
-          for (long long i = threadIdx.x; i < n; i += kPgdThreads) d[i] = from_f32<TD>(__fmul_rn(to_f32(d[i]), s));
         }
       }
     }
   }
 }
 
-static int pgd_make_plan(int B, long long N, float lr, float eps, int mode, size_t gsize, PgdPlan* p) {
+static int pgd_make_plan(int B, long long N, float lr, float eps, int mode, size_t gsize, size_t dsize, PgdPlan* p) {
   p->N = N;
   p->B = B;
   p->mode = mode;
@@ -341,19 +400,22 @@ static int pgd_make_plan(int B, long long N, float lr, float eps, int mode, size
     return RMCL_E_UNSUPPORTED_DIM;
   }
   p->chunks = (int)chunks;
-  long long batch = kPgdBatchBytes / (N * (long long)gsize);
+  p->phases = (mode == RMCL_PGD_SIGN_LINF) ? 1 : 2;
+  p->n_sums = (mode == RMCL_PGD_L2 && eps > 0.f) ? 3 : 1;
+  // bytes per sample that must survive in L2 between the two phases
+  const long long resident = N * (long long)(gsize + (p->n_sums == 3 ? dsize : 0));
+  long long batch = kPgdBatchBytes / resident;
   if (batch < 1) batch = 1;
   if (batch > B) batch = B;
   p->batch = (int)batch;
   p->n_batches = (B + p->batch - 1) / p->batch;
-  p->phases = (mode == RMCL_PGD_SIGN_LINF) ? 1 : ((mode == RMCL_PGD_L2 && eps > 0.f) ? 3 : 2);
   p->total_items = (long long)p->phases * B * p->chunks;
   return RMCL_OK;
 }
 
+static size_t pgd_ctrl_bytes(const PgdPlan& p) { return ((size_t)(2 + p.B) * sizeof(unsigned int) + 255) / 256 * 256; }
 static size_t pgd_ws_bytes(const PgdPlan& p) {
-  const size_t ctrl = ((size_t)(2 + 2 * p.B) * sizeof(unsigned int) + 255) / 256 * 256;
-  return ctrl + 2 * ((size_t)p.B * p.chunks + p.B) * sizeof(float);
+  return pgd_ctrl_bytes(p) + 3 * ((size_t)p.B * p.chunks + p.B) * sizeof(float);
 }
 
 template <typename TD, typename TG>
@@ -365,16 +427,12 @@ static int launch_pgd(void* delta, const void* grad, PgdPlan p, void* ws, size_t
     set_error("rmcl_pgd_step: workspace %zu < required %zu (rmcl_pgd_workspace_bytes)", ws_bytes, need);
     return RMCL_E_WORKSPACE;
   }
-  const size_t ctrl = ((size_t)(2 + 2 * p.B) * sizeof(unsigned int) + 255) / 256 * 256;
   unsigned int* c = reinterpret_cast<unsigned int*>(ws);
   p.ticket = c;
   p.exits = c + 1;
-  p.done1 = c + 2;
-  p.done2 = c + 2 + p.B;
-  p.part1 = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ctrl);
-  p.norm1 = p.part1 + (size_t)p.B * p.chunks;
-  p.part2 = p.norm1 + p.B;
-  p.norm2 = p.part2 + (size_t)p.B * p.chunks;
+  p.done = c + 2;
+  p.part = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + pgd_ctrl_bytes(p));
+  p.norm = p.part + 3 * (size_t)p.B * p.chunks;
   long long grid = (long long)sms * 8;
   if (grid > p.total_items) grid = p.total_items;
   pgd_ticket_kernel<TD, TG><<<(unsigned)grid, kPgdThreads, 0, s>>>((TD*)delta, (const TG*)grad, p);
@@ -387,8 +445,8 @@ static int launch_pgd(void* delta, const void* grad, PgdPlan p, void* ws, size_t
 extern "C" size_t rmcl_pgd_workspace_bytes(int B, int64_t N, rmcl_dtype grad_dtype) {
   if (B <= 0 || N <= 0 || !rmcl::dtype_ok(grad_dtype)) return 0;
   rmcl::PgdPlan p;
-  // the largest layout over the modes (L2 uses both partial arrays; sizes do not depend on mode otherwise)
-  if (rmcl::pgd_make_plan(B, N, 0.f, 1.f, RMCL_PGD_L2, rmcl::dtype_size(grad_dtype), &p) != RMCL_OK) return 0;
+  // the layout does not depend on the mode (three partial planes are always reserved)
+  if (rmcl::pgd_make_plan(B, N, 0.f, 1.f, RMCL_PGD_L2, rmcl::dtype_size(grad_dtype), 4, &p) != RMCL_OK) return 0;
   return rmcl::pgd_ws_bytes(p);
 }
 
@@ -402,7 +460,7 @@ extern "C" int rmcl_pgd_step(void* delta, rmcl_dtype delta_dtype, const void* gr
   RMCL_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "rmcl_pgd_step: workspace must be 256B aligned");
   cudaStream_t s = (cudaStream_t)stream;
   rmcl::PgdPlan p;
-  const int rc = rmcl::pgd_make_plan(B, N, lr, eps, mode, rmcl::dtype_size(grad_dtype), &p);
+  const int rc = rmcl::pgd_make_plan(B, N, lr, eps, mode, rmcl::dtype_size(grad_dtype), rmcl::dtype_size(delta_dtype), &p);
   if (rc != RMCL_OK) return rc;
   using bf16 = __nv_bfloat16;
   if (delta_dtype == RMCL_F32 && grad_dtype == RMCL_F32)

@@ -51,12 +51,31 @@ def momentum_update_key_encoder(pl_module):
     ops.ema_multi_(plan, pl_module.momentum)
 
 
+def _queue_shadow(pl_module):
+    """The module's bf16 queue shadow (ops.QueueShadow) if it opted in with ``rmcl_bf16_queue=True``
+    — the analogue of running the reference under Lightning ``precision=16`` — else None."""
+    if not getattr(pl_module, "rmcl_bf16_queue", False):
+        return None
+    sh = pl_module.__dict__.get("_rmcl_queue_shadow")
+    if sh is None:
+        sh = pl_module.__dict__["_rmcl_queue_shadow"] = ops.QueueShadow()
+    return sh
+
+
+def infonce_queue(pl_module):
+    """The queue operand of the main-step InfoNCE calls: the fp32 buffer (exact reference numerics,
+    SIMT path) or its bf16 shadow (tcgen05 path) when the module opted in.  The PGD inner loss always
+    uses the fp32 buffer: the reference runs it under ``autocast(False)`` (pgd_attack_vilt.py:141)."""
+    sh = _queue_shadow(pl_module)
+    return pl_module.proj_queue if sh is None else sh.get(pl_module.proj_queue)
+
+
 def dequeue_and_enqueue(pl_module, keys):
     """objectives.py:238-248 — gather, skip on a short batch, ring-buffer write, pointer advance."""
     keys = rdist.concat_all_gather(keys)
     if not rdist.gathered_batch_matches(pl_module.per_step_bs, keys.shape[0]):
         return
-    ops.enqueue_(pl_module.proj_queue, keys, pl_module.proj_queue_ptr)
+    ops.enqueue_(pl_module.proj_queue, keys, pl_module.proj_queue_ptr, shadow=_queue_shadow(pl_module))
 
 
 def compute_pgd(pl_module, batch, loss_name, k_modality=None):
@@ -108,7 +127,7 @@ def _attacked_view(pl_module, batch, k_hat, prediction_original, suffix, rate_na
     else:
         infer = pl_module.infer(batch, mask_text=False, mask_image=False)
     q_raw = pl_module.moco_head(infer["cls_feats"])
-    loss, argmax = ops.infonce_loss(q_raw, k_hat, pl_module.proj_queue, pl_module.temperature,
+    loss, argmax = ops.infonce_loss(q_raw, k_hat, infonce_queue(pl_module), pl_module.temperature,
                                     getattr(pl_module, "infonce_path", "auto"))
     if pl_module.training:
         pl_module.log(f"moco_attack/{rate_name}_success_rate",
@@ -136,7 +155,7 @@ def compute_moco_contrastive(pl_module, batch, diagnostics=True):
     # normalises the key, so k^ comes out of it for PGD, the losses and the enqueue.
     infer = pl_module.infer(batch, mask_text=False, mask_image=False)
     q_clean = pl_module.moco_head(infer["cls_feats"])
-    clean = ops.infonce_fwd_bwd(q_clean.float(), k_raw.float(), pl_module.proj_queue, pl_module.temperature,
+    clean = ops.infonce_fwd_bwd(q_clean.float(), k_raw.float(), infonce_queue(pl_module), pl_module.temperature,
                                 normalize_k=True, need_grad=False, path=getattr(pl_module, "infonce_path", "auto"),
                                 want=("argmax", "k_hat"))
     prediction_original, k = clean["argmax"], clean["k_hat"]

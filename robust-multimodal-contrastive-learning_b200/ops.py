@@ -106,7 +106,8 @@ def _workspace(B, Cdim, K, qdt, path, device):
 
 
 def infonce_fwd_bwd(q, k, queue, temperature, *, loss_scale=1.0, normalize_k=False, need_grad=True,
-                    path="auto", want=("loss", "loss_per_row", "lse", "pos", "argmax", "dq", "dk", "k_hat")):
+                    path="auto", want=("loss", "loss_per_row", "lse", "pos", "argmax", "dq", "dk", "k_hat"),
+                    _partial_only=False):
     """Fused InfoNCE of raw projections ``q`` [B,C] against [``k`` ; ``queue`` [C,K]].
 
     Returns a dict with the requested outputs (see include/rmcl_b200.h).  ``loss`` is
@@ -143,6 +144,8 @@ def infonce_fwd_bwd(q, k, queue, temperature, *, loss_scale=1.0, normalize_k=Fal
     if "k_hat" in want:
         out["k_hat"] = torch.empty(B, Cd, **f32)
     flags = (_lib.FLAG_NORMALIZE_K if normalize_k else 0) | (0 if need_grad else _lib.FLAG_NO_GRAD)
+    if _partial_only:   # measurement aid (bench.py): the partial kernel alone, on the workspace of a previous call
+        flags |= _lib.FLAG_DEBUG_PARTIAL_ONLY
     rc = _lib.lib().rmcl_infonce_fwd_bwd(
         _p(q), _dt(q), _p(k), _dt(k), _p(queue), _dt(queue), B, Cd, K, ldq, float(temperature), float(loss_scale),
         flags, pth, _p(out.get("loss")), _p(out.get("loss_per_row")), _p(out.get("lse")), _p(out.get("pos")),
@@ -182,15 +185,50 @@ def infonce_loss(q, k, queue, temperature, path="auto", normalize_k=False):
 
 
 # -------------------------------------------------------------------------------- enqueue
-def enqueue_(queue, keys, ptr):
+class QueueShadow:
+    """bf16 copy of an fp32 queue buffer, kept current by ``enqueue_(..., shadow=...)``.
+
+    The reference's ``proj_queue`` is an fp32 buffer (vilt_module.py:92) and its half-precision
+    einsum under Lightning ``precision=16`` re-casts all C*K elements on every call
+    (objectives.py:270-272).  The shadow is that cast done once; afterwards each enqueue writes the
+    B new columns into both copies in the same launch, so the tcgen05 InfoNCE kernel has its
+    bf16 operand for B*C*2 bytes per step.  ``get()`` rebuilds the copy if the fp32 buffer was
+    replaced or modified in place by anything else (``load_state_dict``, ``.to()``)."""
+
+    def __init__(self):
+        self.tensor, self._key = None, None
+
+    @staticmethod
+    def _state(queue):
+        return (queue.data_ptr(), tuple(queue.shape), queue._version)
+
+    def get(self, queue):
+        _need_cuda(queue)
+        if self.tensor is None or self._key != self._state(queue):
+            self.tensor = queue.detach().to(torch.bfloat16).contiguous()   # one-off cast (init / checkpoint load)
+            self._key = self._state(queue)
+        return self.tensor
+
+
+def enqueue_(queue, keys, ptr, shadow=None):
     """queue[:, ptr:ptr+B] = keys.T; ptr = (ptr+B) % K — on device, no host sync
-    (objectives.py:244-248).  ``ptr`` is the int64[1] buffer ``proj_queue_ptr``."""
+    (objectives.py:244-248).  ``ptr`` is the int64[1] buffer ``proj_queue_ptr``.
+    ``shadow`` (a :class:`QueueShadow` or a bf16 [C,K] tensor) receives the same columns."""
     _need_cuda(queue, keys, ptr)
     if ptr.dtype != torch.int64 or ptr.numel() != 1:
         raise TypeError("ptr must be an int64 tensor with one element")
     if queue.stride(1) != 1 or keys.dim() != 2 or keys.shape[1] != queue.shape[0]:
         raise ValueError(f"shape mismatch: queue {tuple(queue.shape)} keys {tuple(keys.shape)}")
     keys = keys.detach().contiguous()
+    if shadow is not None:
+        sh = shadow.get(queue) if isinstance(shadow, QueueShadow) else shadow
+        _need_cuda(sh)
+        if sh.dtype != torch.bfloat16 or sh.shape != queue.shape or sh.stride(1) != 1:
+            raise ValueError("shadow must be a bf16 [C,K] tensor with K contiguous")
+        rc = _lib.lib().rmcl_enqueue_shadow(_p(queue), _dt(queue), _p(sh), sh.stride(0), _p(keys), _dt(keys), _p(ptr),
+                                            keys.shape[0], keys.shape[1], queue.shape[1], queue.stride(0), _stream())
+        check(rc, "rmcl_enqueue_shadow")
+        return
     rc = _lib.lib().rmcl_enqueue(_p(queue), _dt(queue), _p(keys), _dt(keys), _p(ptr), keys.shape[0], keys.shape[1],
                                  queue.shape[1], queue.stride(0), _stream())
     check(rc, "rmcl_enqueue")
@@ -259,6 +297,20 @@ class HostStep:
             C.c_void_p(self.ws.data_ptr() + self.ws_off), self.ws.numel() - self.ws_off, _stream())
         check(rc, "rmcl_step_host")
         return self.loss_host, self.dq_host
+
+
+def tc_timeline(fn):
+    """Run ``fn()`` (which must launch the tcgen05 InfoNCE kernel) with the in-kernel timeline of
+    CTA (0,0) switched on; returns the raw int64 clock stamps (layout: csrc/infonce_tc.cu)."""
+    L = _lib.lib()
+    buf = torch.zeros(L.rmcl_debug_tc_timeline_words(), dtype=torch.int64, device="cuda")
+    check(L.rmcl_debug_tc_timeline(C.c_void_p(buf.data_ptr())), "rmcl_debug_tc_timeline")
+    try:
+        fn()
+        torch.cuda.synchronize()
+    finally:
+        L.rmcl_debug_tc_timeline(C.c_void_p(0))
+    return buf.cpu()
 
 
 def profile_enable(on=True):

@@ -130,6 +130,28 @@ def test_enqueue_sequence_wraps_and_rejects_bad_k(ops):
         ops.enqueue_(torch.zeros(C, 30, device=DEV), torch.zeros(B, C, device=DEV), pd)  # K % B != 0
 
 
+def test_enqueue_shadow_tracks_the_fp32_queue(ops):
+    """fp32 queue + bf16 shadow written by the same launch: the shadow always equals queue.bfloat16(),
+    and QueueShadow rebuilds itself when the fp32 buffer is modified behind its back."""
+    B, C, K = 16, 64, 128
+    g = torch.Generator().manual_seed(1)
+    queue = torch.randn(C, K, generator=g)
+    qd, pd = queue.to(DEV), torch.zeros(1, dtype=torch.int64, device=DEV)
+    sh = ops.QueueShadow()
+    first = sh.get(qd)
+    assert torch.equal(first.cpu(), queue.bfloat16())
+    ref_q, ref_p = queue, 0
+    for step in range(10):   # wraps
+        keys = torch.randn(B, C, generator=g)
+        ops.enqueue_(qd, keys.to(DEV), pd, shadow=sh)
+        ref_q, ref_p = O.dequeue_and_enqueue(ref_q, ref_p, keys, K)
+        assert torch.equal(qd.cpu(), ref_q) and pd.item() == ref_p
+        assert sh.get(qd) is first                      # not rebuilt: kept current by the kernel
+        assert torch.equal(first.cpu(), ref_q.bfloat16())
+    qd.mul_(2.0)                                        # e.g. load_state_dict: in-place change by someone else
+    assert torch.equal(sh.get(qd).cpu(), (ref_q * 2).bfloat16())
+
+
 def test_enqueue_golden_reference(ops, golden):
     for name in ("ref_tiny_c16", "ref_tiny_c128", "ref_cfg1_vilt_b32"):
         g = golden(name)
@@ -210,6 +232,35 @@ def test_pgd_sign_and_l2_modes(ops, shape):
         signs = (torch.sign(got.cpu() - d0) == torch.sign(grad)) | (grad == 0)
         if eps == 0:
             assert signs.float().mean().item() >= 0.999
+
+
+@pytest.mark.parametrize("shape", [(4, 3, 16, 16), (3, 185, 768), (2, 3, 384, 384), (2, 900_001), (5, 1001)])
+@pytest.mark.parametrize("ddt", [torch.float32, torch.bfloat16])
+def test_pgd_l2_projection_active(ops, shape, ddt):
+    """eps small enough that every sample is projected: delta is written once, scaled by the norm taken
+    from |d|^2 + 2a<d,g> + a^2|g|^2 — must agree with the oracle's explicit two-step form."""
+    g = torch.Generator().manual_seed(11)
+    grad = torch.randn(shape, generator=g)
+    grad[0] *= 1e-3                                   # very different gradient scales per sample
+    d0 = (torch.randn(shape, generator=g) * 0.01).to(ddt)
+    d0[-1] *= 30.0                                    # a sample that starts outside the ball
+    dd = d0.to(DEV)
+    ref = d0.double()
+    for step in range(3):
+        ref = O.pgd_update(ref, grad.double(), 0.5, 0.1, mode="l2")
+        ops.pgd_step_(dd, grad.to(DEV), 0.5, 0.1, "l2")
+        if ddt == torch.float32:
+            assert rel_err(dd, ref) < FP32_RTOL, step
+            assert dd.view(shape[0], -1).norm(dim=1).max().item() <= 0.1 * (1 + 1e-5)
+        else:
+            assert rel_err(dd, ref) < BF16_RTOL, step
+            ref = dd.double().cpu()                   # bf16 storage: follow the rounded trajectory
+    # cancellation: delta' = delta + a g is (nearly) zero although |delta| and |a g| are not
+    gdir = torch.randn(2, 4096, generator=g)
+    gn = gdir / gdir.norm(dim=1, keepdim=True)
+    d_c = (-0.5 * gn).to(DEV)
+    got = ops.pgd_step_(d_c, gdir.to(DEV), 0.5, 0.1, "l2")
+    assert got.abs().max().item() < 1e-6
 
 
 def test_pgd_bf16_delta(ops):
@@ -411,6 +462,27 @@ def test_infonce_tcgen05_growing_maximum(ops, B, C, K):
     ref = _bf16_oracle(q, k, queue, 0.07)
     res = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.to(DEV), 0.07, path="tcgen05")
     assert rel_err(res["lse"], ref["lse"]) < 1e-4
+    assert rel_err(res["dq"], ref["dq"]) < 1e-2
+
+
+@pytest.mark.parametrize("C,tn", [(256, 64), (128, 128), (64, 128)])
+def test_infonce_tcgen05_rescale_path_on_every_tile(ops, C, tn):
+    """Every tile's logits exceed the previous tile's by ~80 log2 units (more than the initial-reference
+    margin plus the lazy-rescale threshold), so the O / l read-modify-write runs on each tile of a CTA;
+    one split (B large, K small) keeps all tiles in one CTA.  Queries are scaled unit vectors, so q^ is
+    exact in bf16 and the float64 oracle sees exactly the kernel's operands even at logits of ~340."""
+    B, n_tiles = 148 * 128, 6
+    K = n_tiles * tn
+    g = torch.Generator().manual_seed(5)
+    q = torch.zeros(B, C)
+    q[torch.arange(B), torch.arange(B) % C] = 3.0
+    k = torch.nn.functional.normalize(torch.randn(B, C, generator=g), dim=1)
+    step = torch.arange(K) // tn                                        # tile index of a column
+    queue = (4.0 * (step + 1)[None, :] + 0.25 * torch.randn(C, K, generator=g)).bfloat16()
+    ref = _bf16_oracle(q, k, queue, 0.07)
+    res = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.to(DEV), 0.07, path="tcgen05")
+    assert rel_err(res["lse"], ref["lse"]) < 1e-5
+    assert rel_err(res["loss"], ref["loss"]) < 1e-5
     assert rel_err(res["dq"], ref["dq"]) < 1e-2
 
 
