@@ -115,6 +115,32 @@ int rmcl_infonce_fwd_bwd(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_
                          float* dq, float* dk, float* k_hat_out, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Per-view diagnostics of compute_moco_contrastive from the same fused pass.
+ * replaces: objectives.py:337-349 (and 300-312, 375-387): pos/neg L2 distance, cosine and dot means —
+ *           in the reference a Python loop over the B samples, each iteration reducing the whole
+ *           [K,C] queue three times.
+ * rmcl_queue_stats reduces the queue once per step (it changes by B columns per step):
+ *     colnorm2 f32[K]  |queue_j|^2          sum_vec f32[C]  sum_j queue[:,j]
+ *     sum_unit f32[C]  sum_j queue[:,j] / max(|queue_j|, cos_eps)      (cos_eps = 1e-6 in the reference)
+ * rmcl_infonce_fwd_bwd_diag is rmcl_infonce_fwd_bwd plus
+ *     diag_out f32[6]  means over the B rows of
+ *        [0] |q^-k^|_2   [1] cos(q^,k^)   [2] q^.k^   [3] mean_j |q^-queue_j|_2   [4] mean_j cos(q^,queue_j)
+ *        [5] mean_j q^.queue_j
+ *   (the reference's pos_dist, pos_cosine, pos_dot, neg_dist, neg_cosine, neg_dot of one view).
+ *   k must be the normalised key here (the reference passes the normalised k).
+ */
+int rmcl_queue_stats(const void* queue, rmcl_dtype queue_dtype, int C, int64_t K, int64_t ldq,
+                     float cos_eps, float* colnorm2, float* sum_vec, float* sum_unit, void* stream);
+
+int rmcl_infonce_fwd_bwd_diag(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_dtype k_dtype,
+                              const void* queue, rmcl_dtype queue_dtype, int B, int C, int64_t K,
+                              int64_t ldq, float tau, float loss_scale, unsigned flags, int path,
+                              float* loss, float* loss_per_row, float* lse, float* pos, int64_t* argmax,
+                              float* dq, float* dk, float* k_hat_out, const float* colnorm2,
+                              const float* sum_vec, const float* sum_unit, float cos_eps,
+                              float* diag_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Measurement aid (off by default): when enabled on the calling thread, rmcl_infonce_fwd_bwd
  * records CUDA events on its stream around its three launches (prep, split-K partial, finalize);
  * rmcl_profile_infonce_ms waits for the last of them and returns the three durations of the most

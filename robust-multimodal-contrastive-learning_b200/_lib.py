@@ -20,7 +20,7 @@ EXPORTS = (
     "rmcl_last_error", "rmcl_version", "rmcl_sm_count", "rmcl_ema_plan", "rmcl_ema_multi",
     "rmcl_infonce_workspace_bytes", "rmcl_infonce_fwd_bwd", "rmcl_enqueue", "rmcl_pgd_workspace_bytes", "rmcl_pgd_step", "rmcl_step_host",
     "rmcl_profile_enable", "rmcl_profile_infonce_ms", "rmcl_enqueue_shadow", "rmcl_debug_tc_timeline",
-    "rmcl_debug_tc_timeline_words",
+    "rmcl_debug_tc_timeline_words", "rmcl_queue_stats", "rmcl_infonce_fwd_bwd_diag",
 )
 
 
@@ -69,6 +69,12 @@ def lib():
     L.rmcl_debug_tc_timeline.argtypes = [vp]
     L.rmcl_debug_tc_timeline_words.restype = i32
     L.rmcl_debug_tc_timeline_words.argtypes = []
+    if hasattr(L, "rmcl_queue_stats"):
+        L.rmcl_queue_stats.restype = i32
+        L.rmcl_queue_stats.argtypes = [vp, i32, i32, i64, i64, f32, vp, vp, vp, vp]
+        L.rmcl_infonce_fwd_bwd_diag.restype = i32
+        L.rmcl_infonce_fwd_bwd_diag.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i64, i64, f32, f32, u32, i32,
+                                                vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, sz, vp]
     L.rmcl_pgd_step.restype = i32
     L.rmcl_pgd_step.argtypes = [vp, i32, vp, i32, i32, i64, f32, f32, i32, vp, sz, vp]
     L.rmcl_pgd_workspace_bytes.restype = sz

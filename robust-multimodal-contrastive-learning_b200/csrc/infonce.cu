@@ -71,6 +71,9 @@ int infonce_make_plan(int B, int C, long long K, int queue_dtype, int path, bool
   p->off_o = take(S * Bs * C * 4);
   p->off_rowloss = take(Bs * 4);
   p->off_counter = take(256);
+  p->off_qn2 = take(Bs * 4);
+  p->off_pdist = take(S * Bs * 4);
+  p->off_diagrows = take(Bs * kDiagValues * 4);
   p->total = off;
   return RMCL_OK;
 }
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(128) infonce_prep_kernel(const TQ* __restrict_
                                                            int C, float scale2, bool normalize_k, bool bf16_mode,
                                                            float* __restrict__ q_hat, float* __restrict__ k_hat,
                                                            float* __restrict__ k_hat_out, float* __restrict__ inv_norm,
-                                                           float* __restrict__ pos2,
+                                                           float* __restrict__ pos2, float* __restrict__ qn2,
                                                            __nv_bfloat16* __restrict__ q_hat_bf16, int b_pad,
                                                            unsigned int* __restrict__ counter) {
   __shared__ float red[4];
@@ -118,9 +121,10 @@ __global__ void __launch_bounds__(128) infonce_prep_kernel(const TQ* __restrict_
   sk = block_sum_128(sk, red);
   const float qn = fmaxf(sqrtf(sq), 1e-12f);
   const float kn = normalize_k ? fmaxf(sqrtf(sk), 1e-12f) : 1.f;
-  float dot = 0.f;
+  float dot = 0.f, qq = 0.f;
   for (int c = threadIdx.x; c < C; c += 128) {
     const float qh = __fdiv_rn(to_f32(qr[c]), qn);
+    qq = fmaf(qh, qh, qq);
     const float kh = normalize_k ? __fdiv_rn(to_f32(kr[c]), kn) : to_f32(kr[c]);
     q_hat[(size_t)row * C + c] = qh;
     k_hat[(size_t)row * C + c] = kh;
@@ -133,9 +137,11 @@ __global__ void __launch_bounds__(128) infonce_prep_kernel(const TQ* __restrict_
     dot = fmaf(round_if(qh, bf16_mode), round_if(kh, bf16_mode), dot);
   }
   dot = block_sum_128(dot, red);
+  qq = block_sum_128(qq, red);
   if (threadIdx.x == 0) {
     inv_norm[row] = __fdiv_rn(1.f, qn);
     pos2[row] = dot * scale2;
+    qn2[row] = qq;
   }
 }
 
@@ -158,12 +164,14 @@ __global__ void __launch_bounds__(kFinThreads, 2) infonce_finalize_kernel(
     const float* __restrict__ pav, const int* __restrict__ pai, const TP* __restrict__ po,
     float* __restrict__ row_loss, unsigned int* __restrict__ counter, float* __restrict__ loss,
     float* __restrict__ loss_per_row, float* __restrict__ lse_out, float* __restrict__ pos_out,
-    long long* __restrict__ argmax_out, float* __restrict__ dq, float* __restrict__ dk) {
+    long long* __restrict__ argmax_out, float* __restrict__ dq, float* __restrict__ dk, const float* __restrict__ pdist,
+    const float* __restrict__ qn2, float inv_K, const InfoNceDiag diag) {
   extern __shared__ float fin_smem[];
   float* sw = fin_smem;                       // [splits] merge weights
   float* part = fin_smem + ((splits + 3) & ~3);  // [kFinGroups-1][C] partial column sums of groups 1..
   __shared__ float red[8];
-  __shared__ float s_stats[4];   // 0: scale applied to O  1: p_pos - 1
+  __shared__ float dred[kFinThreads / 32][5];
+  __shared__ float s_stats[4];   // 0: scale applied to O  1: p_pos - 1  2: sum over the queue of |q^ - queue_j|
   __shared__ bool s_last;
   const int row = blockIdx.x;
   const int tid = threadIdx.x;
@@ -204,6 +212,12 @@ __global__ void __launch_bounds__(kFinThreads, 2) infonce_finalize_kernel(
     float lsum = 0.f;
     float bv = -INFINITY;
     int bi = 0x7fffffff;
+    if (diag.out) {   // the split sums of the L2 distances: plain sum, in fixed lane order
+      float dsum = 0.f;
+      for (int s = tid; s < splits; s += 32) dsum += __ldcg(pdist + (size_t)row * splits + s);
+      dsum = warp_sum(dsum);
+      if (tid == 0) s_stats[2] = dsum;
+    }
     for (int s = tid; s < splits; s += 32) {
       const float ms = __ldcg(rm + s), ls = __ldcg(rl + s), v = __ldcg(rav + s);
       const int i = __ldcg(rai + s);
@@ -310,25 +324,65 @@ __global__ void __launch_bounds__(kFinThreads, 2) infonce_finalize_kernel(
     }
   }
 
-  // deterministic loss reduction by the last row-CTA
-  if (loss) {
+  // ---- diagnostics of this row (objectives.py:337-349): five dot products over C, then closed forms
+  if (diag.out) {
+    float a[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // q.k, |q-k|^2, |k|^2, q.sum_vec, q.sum_unit
+    for (int c = tid; c < C; c += kFinThreads) {
+      const float qh = q_hat[(size_t)row * C + c], kh = k_hat[(size_t)row * C + c];
+      const float df = qh - kh;
+      a[0] = fmaf(qh, kh, a[0]);
+      a[1] = fmaf(df, df, a[1]);
+      a[2] = fmaf(kh, kh, a[2]);
+      a[3] = fmaf(qh, diag.sum_vec[c], a[3]);
+      a[4] = fmaf(qh, diag.sum_unit[c], a[4]);
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) a[i] = warp_sum(a[i]);
+    if ((tid & 31) == 0) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) dred[tid >> 5][i] = a[i];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float t[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int w = 0; w < kFinThreads / 32; ++w)
+#pragma unroll
+        for (int i = 0; i < 5; ++i) t[i] += dred[w][i];
+      const float qn = sqrtf(qn2[row]), kn = sqrtf(t[2]);
+      float* o = diag.rows + (size_t)row * kDiagValues;
+      o[0] = sqrtf(t[1]);                                                       // |q^ - k^|
+      o[1] = t[0] / (fmaxf(qn, diag.cos_eps) * fmaxf(kn, diag.cos_eps));        // cosine(q^, k^)
+      o[2] = t[0];                                                              // q^ . k^
+      o[3] = s_stats[2] * inv_K;                                                // mean_j |q^ - queue_j|
+      o[4] = t[4] * inv_K / fmaxf(qn, diag.cos_eps);                            // mean_j cosine(q^, queue_j)
+      o[5] = t[3] * inv_K;                                                      // mean_j q^ . queue_j
+    }
+  }
+
+  // deterministic loss (and diagnostics) reduction by the last row-CTA
+  if (loss || diag.out) {
     __threadfence();
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(counter, 1u) == (unsigned)B - 1u);
     __syncthreads();
     if (s_last && tid < 256) {
       __threadfence();
-      float acc = 0.f;
-      for (int r = tid; r < B; r += 256) acc += __ldcg(row_loss + r);
-      // fixed-shape tree: warp shuffle then 8 partials in order
-      acc = warp_sum(acc);
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      if ((tid & 31) == 0) red[tid >> 5] = acc;
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      if (tid == 0) {
-        float t = 0.f;
-        for (int w = 0; w < 8; ++w) t += red[w];
-        *loss = t * (loss_scale / (float)B);
+      const int n_red = diag.out ? 1 + kDiagValues : 1;
+      for (int which = loss ? 0 : 1; which < n_red; ++which) {
+        float acc = 0.f;
+        for (int r = tid; r < B; r += 256)
+          acc += (which == 0) ? __ldcg(row_loss + r) : __ldcg(diag.rows + (size_t)r * kDiagValues + (which - 1));
+        // fixed-shape tree: warp shuffle then 8 partials in order
+        acc = warp_sum(acc);
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if ((tid & 31) == 0) red[tid >> 5] = acc;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (tid == 0) {
+          float t = 0.f;
+          for (int w = 0; w < 8; ++w) t += red[w];
+          if (which == 0) *loss = t * (loss_scale / (float)B);
+          else diag.out[which - 1] = t / (float)B;
+        }
       }
     }
   }
@@ -340,7 +394,7 @@ static int launch_prep(const void* q, const void* k, int B, int C, float scale2,
   const int rows = want_bf16 ? p.b_pad : B;
   infonce_prep_kernel<TQ, TKK><<<rows, 128, 0, s>>>(
       (const TQ*)q, (const TKK*)k, B, C, scale2, nk, bf16_mode, (float*)(ws + p.off_qhat), (float*)(ws + p.off_khat),
-      k_hat_out, (float*)(ws + p.off_inv), (float*)(ws + p.off_pos2),
+      k_hat_out, (float*)(ws + p.off_inv), (float*)(ws + p.off_pos2), (float*)(ws + p.off_qn2),
       want_bf16 ? (__nv_bfloat16*)(ws + p.off_qhat_bf16) : nullptr, p.b_pad, (unsigned int*)(ws + p.off_counter));
   RMCL_LAUNCH_OK("infonce_prep_kernel");
   return RMCL_OK;
@@ -393,11 +447,11 @@ extern "C" size_t rmcl_infonce_workspace_bytes(int B, int C, int64_t K, rmcl_dty
   return best;
 }
 
-extern "C" int rmcl_infonce_fwd_bwd(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_dtype k_dtype,
-                                    const void* queue, rmcl_dtype queue_dtype, int B, int C, int64_t K, int64_t ldq,
-                                    float tau, float loss_scale, unsigned flags, int path, float* loss,
-                                    float* loss_per_row, float* lse, float* pos, int64_t* argmax, float* dq, float* dk,
-                                    float* k_hat_out, void* workspace, size_t workspace_bytes, void* stream) {
+static int infonce_impl(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_dtype k_dtype, const void* queue,
+                        rmcl_dtype queue_dtype, int B, int C, int64_t K, int64_t ldq, float tau, float loss_scale,
+                        unsigned flags, int path, float* loss, float* loss_per_row, float* lse, float* pos,
+                        int64_t* argmax, float* dq, float* dk, float* k_hat_out, void* workspace, size_t workspace_bytes,
+                        void* stream, InfoNceDiag diag) {
   RMCL_CHECK_ARG(q && k && queue && workspace, "rmcl_infonce_fwd_bwd: null pointer");
   RMCL_CHECK_ARG(B > 0 && C > 0 && K > 0 && K < (1ll << 31) && ldq >= K, "rmcl_infonce_fwd_bwd: bad sizes B=%d C=%d K=%lld ldq=%lld",
                  B, C, (long long)K, (long long)ldq);
@@ -434,8 +488,10 @@ extern "C" int rmcl_infonce_fwd_bwd(const void* q, rmcl_dtype q_dtype, const voi
   if (rc != RMCL_OK) return rc;
   RMCL_PROF_MARK(1);
 
+  diag.rows = diag.out ? (float*)(ws + p.off_diagrows) : nullptr;
   InfoNcePartials parts{(float*)(ws + p.off_m), (float*)(ws + p.off_l), (float*)(ws + p.off_av), (int*)(ws + p.off_ai),
-                        (float*)(ws + p.off_o)};
+                        (float*)(ws + p.off_o), diag.out ? diag.colnorm2 : nullptr, (const float*)(ws + p.off_qn2),
+                        (float*)(ws + p.off_pdist)};
   if (tc)
     rc = infonce_tc_launch((const bf16*)(ws + p.off_qhat_bf16), queue, B, C, K, ldq, scale2, p, parts, argmax != nullptr, s);
   else
@@ -450,15 +506,41 @@ extern "C" int rmcl_infonce_fwd_bwd(const void* q, rmcl_dtype q_dtype, const voi
         B, C, p.splits, 1.f / tau, loss_scale / (float)B, loss_scale, bf16_mode, want_grad, (const float*)(ws + p.off_qhat),
         (const float*)(ws + p.off_khat), (const float*)(ws + p.off_inv), (const float*)(ws + p.off_pos2), parts.m, parts.l,
         parts.av, parts.ai, reinterpret_cast<const __nv_bfloat16*>(parts.o), (float*)(ws + p.off_rowloss),
-        (unsigned int*)(ws + p.off_counter), loss, loss_per_row, lse, pos, reinterpret_cast<long long*>(argmax), dq, dk));
+        (unsigned int*)(ws + p.off_counter), loss, loss_per_row, lse, pos, reinterpret_cast<long long*>(argmax), dq, dk,
+        (const float*)parts.dist, parts.qn2, 1.f / (float)K, diag));
   } else {
     RMCL_CUDA_OK(launch_pdl(infonce_finalize_kernel<float>, dim3(B), dim3(kFinThreads), fin_smem, s,
         B, C, p.splits, 1.f / tau, loss_scale / (float)B, loss_scale, bf16_mode, want_grad, (const float*)(ws + p.off_qhat),
         (const float*)(ws + p.off_khat), (const float*)(ws + p.off_inv), (const float*)(ws + p.off_pos2), parts.m, parts.l,
         parts.av, parts.ai, (const float*)parts.o, (float*)(ws + p.off_rowloss), (unsigned int*)(ws + p.off_counter), loss,
-        loss_per_row, lse, pos, reinterpret_cast<long long*>(argmax), dq, dk));
+        loss_per_row, lse, pos, reinterpret_cast<long long*>(argmax), dq, dk, (const float*)parts.dist, parts.qn2,
+        1.f / (float)K, diag));
   }
   RMCL_PROF_MARK(3);
   if (g_prof_on) g_prof_valid = true;
   return RMCL_OK;
+}
+
+extern "C" int rmcl_infonce_fwd_bwd(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_dtype k_dtype,
+                                    const void* queue, rmcl_dtype queue_dtype, int B, int C, int64_t K, int64_t ldq,
+                                    float tau, float loss_scale, unsigned flags, int path, float* loss,
+                                    float* loss_per_row, float* lse, float* pos, int64_t* argmax, float* dq, float* dk,
+                                    float* k_hat_out, void* workspace, size_t workspace_bytes, void* stream) {
+  InfoNceDiag none{nullptr, nullptr, nullptr, 0.f, nullptr, nullptr};
+  return infonce_impl(q, q_dtype, k, k_dtype, queue, queue_dtype, B, C, K, ldq, tau, loss_scale, flags, path, loss,
+                      loss_per_row, lse, pos, argmax, dq, dk, k_hat_out, workspace, workspace_bytes, stream, none);
+}
+
+extern "C" int rmcl_infonce_fwd_bwd_diag(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_dtype k_dtype,
+                                         const void* queue, rmcl_dtype queue_dtype, int B, int C, int64_t K, int64_t ldq,
+                                         float tau, float loss_scale, unsigned flags, int path, float* loss,
+                                         float* loss_per_row, float* lse, float* pos, int64_t* argmax, float* dq,
+                                         float* dk, float* k_hat_out, const float* colnorm2, const float* sum_vec,
+                                         const float* sum_unit, float cos_eps, float* diag_out, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  RMCL_CHECK_ARG(colnorm2 && sum_vec && sum_unit && diag_out, "rmcl_infonce_fwd_bwd_diag: null diagnostics pointer");
+  RMCL_CHECK_ARG((reinterpret_cast<uintptr_t>(colnorm2) & 15u) == 0, "rmcl_infonce_fwd_bwd_diag: colnorm2 must be 16B aligned");
+  InfoNceDiag dg{colnorm2, sum_vec, sum_unit, cos_eps, diag_out, nullptr};
+  return infonce_impl(q, q_dtype, k, k_dtype, queue, queue_dtype, B, C, K, ldq, tau, loss_scale, flags, path, loss,
+                      loss_per_row, lse, pos, argmax, dq, dk, k_hat_out, workspace, workspace_bytes, stream, dg);
 }

@@ -35,8 +35,22 @@ struct InfoNcePlan {
   int b_pad;            // B rounded up to rows_per_cta
   // workspace carve-up (byte offsets)
   size_t off_qhat, off_khat, off_inv, off_pos2, off_qhat_bf16, off_m, off_l, off_av, off_ai, off_o, off_rowloss,
-      off_counter, total;
+      off_counter, off_qn2, off_pdist, off_diagrows, total;
 };
+
+// Optional: the reference's per-view diagnostics (vilt/modules/objectives.py:337-349) from the same
+// pass.  dot and cosine against the queue are linear in the queue, so they reduce to two [C] vectors
+// (rmcl_queue_stats); the mean L2 distance is not, and is accumulated from S inside the partial
+// kernels as sum_j sqrt(|q^|^2 - 2 q^.queue_j + |queue_j|^2).
+struct InfoNceDiag {
+  const float* colnorm2;   // [K]  |queue_j|^2
+  const float* sum_vec;    // [C]  sum_j queue[:, j]
+  const float* sum_unit;   // [C]  sum_j queue[:, j] / max(|queue_j|, cos_eps)
+  float cos_eps;
+  float* out;              // [6]  means over rows: pos_dist, pos_cosine, pos_dot, neg_dist, neg_cosine, neg_dot
+  float* rows;             // [B][6] per-row values (workspace)
+};
+constexpr int kDiagValues = 6;
 
 // Fills plan; returns RMCL_OK or an error (unsupported shape for a forced path).
 int infonce_make_plan(int B, int C, long long K, int queue_dtype, int path, bool aligned_for_tc, InfoNcePlan* plan);
@@ -47,6 +61,10 @@ struct InfoNcePartials {
   float* av;        // [B][splits]
   int* ai;          // [B][splits]
   float* o;         // [splits][B][C]  fp32 (SIMT partial kernel) or bf16 (tcgen05 partial kernel) elements
+  // diagnostics (n2 == nullptr: off)
+  const float* n2;  // [K] squared column norms of the queue
+  const float* qn2; // [B] |q^|^2
+  float* dist;      // [B][splits] sum over the split's columns of |q^ - queue_j|
 };
 
 // partial stages

@@ -21,7 +21,8 @@ template <typename TQ, int TK>
 __global__ void __launch_bounds__(kSimtThreads) infonce_simt_kernel(
     const float* __restrict__ q_hat, const TQ* __restrict__ queue, int B, int C, long long K, long long ldq,
     float scale2, bool bf16_mode, long long cols_per_split, float* __restrict__ pm, float* __restrict__ pl,
-    float* __restrict__ pav, int* __restrict__ pai, float* __restrict__ po) {
+    float* __restrict__ pav, int* __restrict__ pai, float* __restrict__ po, const float* __restrict__ n2,
+    const float* __restrict__ qn2, float* __restrict__ pdist) {
   extern __shared__ __align__(16) float smem[];
   float* qs = smem;                               // [16][C]
   float* tile = qs + kSimtRows * C;               // [C][TK+1]
@@ -31,6 +32,8 @@ __global__ void __launch_bounds__(kSimtThreads) infonce_simt_kernel(
   float* s_alpha = s_l + kSimtRows;
   float* s_av = s_alpha + kSimtRows;
   int* s_ai = reinterpret_cast<int*>(s_av + kSimtRows);
+  float* s_qn2 = reinterpret_cast<float*>(s_ai + kSimtRows);   // diagnostics: |q^|^2 and the distance sums per row
+  float* s_dist = s_qn2 + kSimtRows;
 
   const int tid = threadIdx.x;
   const int split = blockIdx.x;
@@ -49,6 +52,8 @@ __global__ void __launch_bounds__(kSimtThreads) infonce_simt_kernel(
     s_l[tid] = 0.f;
     s_av[tid] = -INFINITY;
     s_ai[tid] = 0;
+    s_qn2[tid] = (n2 != nullptr && row0 + tid < B) ? qn2[row0 + tid] : 0.f;
+    s_dist[tid] = 0.f;
   }
   float acc[kSimtMaxCPerThread][kSimtRows];
 #pragma unroll
@@ -61,6 +66,9 @@ __global__ void __launch_bounds__(kSimtThreads) infonce_simt_kernel(
   constexpr int kRpt = kSimtRows / kGroups;         // rows per thread in the S phase
   const int j1 = tid % TK, rg = tid / TK;
   const int srow = tid >> 4, ssub = tid & 15;       // stats phase: 16 lanes per row
+  float dacc[kRpt];                                 // diagnostics: sum_j |q^_r - queue_j| over this thread's columns
+#pragma unroll
+  for (int r = 0; r < kRpt; ++r) dacc[r] = 0.f;
 
   for (long long k0 = k_begin; k0 < k_end; k0 += TK) {
     // ---- load tile
@@ -96,6 +104,12 @@ __global__ void __launch_bounds__(kSimtThreads) infonce_simt_kernel(
         for (int r = 0; r < kRpt; ++r) s[r] = fmaf(qrow[(size_t)r * C + c], t, s[r]);
       }
       const bool valid = (k0 + j1 < k_end);
+      if (n2 != nullptr && valid) {   // |q^ - queue_j|^2 = |q^|^2 - 2 q^.queue_j + |queue_j|^2
+        const float nj = n2[k0 + j1];
+#pragma unroll
+        for (int r = 0; r < kRpt; ++r)
+          dacc[r] += sqrtf(fmaxf(fmaf(-2.f, s[r], s_qn2[rg * kRpt + r] + nj), 0.f));
+      }
 #pragma unroll
       for (int r = 0; r < kRpt; ++r) sp[(rg * kRpt + r) * TK + j1] = valid ? s[r] * scale2 : -INFINITY;
     }
@@ -162,6 +176,17 @@ __global__ void __launch_bounds__(kSimtThreads) infonce_simt_kernel(
   }
 
   // ---- emit partials
+  if (n2 != nullptr) {
+    // a row's columns live in TK consecutive threads = TK/32 warps: at most two shared-memory adds per
+    // row, and a two-term floating-point sum does not depend on the order => deterministic
+#pragma unroll
+    for (int r = 0; r < kRpt; ++r) {
+      const float v = warp_sum(dacc[r]);
+      if ((tid & 31) == 0) atomicAdd(&s_dist[rg * kRpt + r], v);
+    }
+    __syncthreads();
+    if (tid < kSimtRows && row0 + tid < B) pdist[(size_t)(row0 + tid) * gridDim.x + split] = s_dist[tid];
+  }
   if (tid < kSimtRows && row0 + tid < B) {
     const size_t o = (size_t)(row0 + tid) * gridDim.x + split;
     pm[o] = s_m[tid];
@@ -184,12 +209,12 @@ template <typename TQ, int TK>
 static int launch_simt(const float* q_hat, const void* queue, int B, int C, long long K, long long ldq, float scale2,
                        bool bf16_mode, const InfoNcePlan& p, InfoNcePartials out, cudaStream_t s) {
   const size_t smem =
-      ((size_t)kSimtRows * C + (((size_t)C * (TK + 1) + 3) & ~(size_t)3) + (size_t)kSimtRows * TK + 5 * kSimtRows) * 4;
+      ((size_t)kSimtRows * C + (((size_t)C * (TK + 1) + 3) & ~(size_t)3) + (size_t)kSimtRows * TK + 7 * kSimtRows) * 4;
   auto kern = infonce_simt_kernel<TQ, TK>;
   RMCL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(p.splits, p.row_blocks);
   kern<<<grid, kSimtThreads, smem, s>>>(q_hat, (const TQ*)queue, B, C, K, ldq, scale2, bf16_mode, p.cols_per_split,
-                                        out.m, out.l, out.av, out.ai, out.o);
+                                        out.m, out.l, out.av, out.ai, out.o, out.n2, out.qn2, out.dist);
   RMCL_LAUNCH_OK("infonce_simt_kernel");
   return RMCL_OK;
 }

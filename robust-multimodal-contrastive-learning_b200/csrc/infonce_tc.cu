@@ -194,6 +194,7 @@ struct TcShared {
   float xl[kTcRows];
   float xav[kTcRows];
   int xai[kTcRows];
+  float xd[kTcRows];           // diagnostics: the odd-tile warp's distance sum
 };
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n) {
@@ -233,12 +234,13 @@ __device__ __forceinline__ void tl_stamp(long long* tl, int idx) {
 }
 
 // ----------------------------------------------------------------------------------- kernel
-template <int C, int TN>
+template <int C, int TN, bool DIAG>
 __global__ void __launch_bounds__(kTcThreads, 1)
     infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_queue, const __nv_bfloat16* __restrict__ q_hat, int B,
                       long long K, float scale2, long long cols_per_split, int want_argmax, float* __restrict__ pm,
                       float* __restrict__ pl, float* __restrict__ pav, int* __restrict__ pai, __nv_bfloat16* __restrict__ po,
-                      long long* __restrict__ timeline) {
+                      long long* __restrict__ timeline, const float* __restrict__ n2, const float* __restrict__ qn2,
+                      float* __restrict__ pdist) {
   constexpr int kStageBytes = C * TN * 2;
   constexpr int kBoxBytes = C * 128;            // one TMA box: C rows x 64 bf16 columns
   constexpr int kBoxes = TN / 64;
@@ -317,6 +319,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // m_mine: the reference maximum this warp's row sum l_run is expressed in
     float m_mine = -INFINITY, l_run = 0.f, av_raw = -INFINITY;
     int ai = 0;
+    float dsum = 0.f, qn2_r = 0.f;                        // diagnostics: sum_j |q^_r - queue_j|, |q^_r|^2
     // Pass it = -1 is a DRY run of the tile body on whatever tensor memory holds, with every side effect
     // (barriers, shared-memory and m_ref writes) switched off.  This kernel is launched early (PDL) and
     // would otherwise idle in griddepcontrol.wait for the ~3 us the prep kernel takes; the first execution
@@ -381,6 +384,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
 
         m_mine = -INFINITY; l_run = 0.f; av_raw = -INFINITY; ai = 0;   // discard the dry pass
+        dsum = 0.f;
+        if (DIAG) qn2_r = (row0 + r < B) ? qn2[row0 + r] : 0.f;   // after pdl_wait: written by the prep kernel
       }
       if (live && i >= n_tiles) break;
       const int b = par;                                  // == i & 1
@@ -401,6 +406,22 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         if (quad == 0) tl_stamp(tl, 8 + 8 * i + 6);
       }
       const long long col0 = k_begin + (long long)i * TN;
+      if (DIAG && live) {
+        // mean L2 distance to the negatives (objectives.py:343): |q^ - queue_j|^2 = |q^|^2 - 2 S_j + |queue_j|^2.
+        // The column norms are the same for every lane: uniform 16-byte loads, one transaction each.
+        const float4* nv = reinterpret_cast<const float4*>(n2 + col0);
+#pragma unroll
+        for (int c4 = 0; c4 < TN / 4; ++c4) {
+          if (col0 + 4 * c4 < k_end) {                    // k_end is a multiple of 8 on this path
+            const float4 nn = __ldg(nv + c4);
+            const float d0 = fmaf(-2.f, __uint_as_float(sv[4 * c4 + 0]), qn2_r + nn.x);
+            const float d1 = fmaf(-2.f, __uint_as_float(sv[4 * c4 + 1]), qn2_r + nn.y);
+            const float d2 = fmaf(-2.f, __uint_as_float(sv[4 * c4 + 2]), qn2_r + nn.z);
+            const float d3 = fmaf(-2.f, __uint_as_float(sv[4 * c4 + 3]), qn2_r + nn.w);
+            dsum += (sqrtf(fmaxf(d0, 0.f)) + sqrtf(fmaxf(d1, 0.f))) + (sqrtf(fmaxf(d2, 0.f)) + sqrtf(fmaxf(d3, 0.f)));
+          }
+        }
+      }
       if (live && col0 + TN > k_end) {  // ragged last tile: TMA zero-filled the columns past K
         const int valid = (int)(k_end - col0);
 #pragma unroll
@@ -501,6 +522,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       sh.xl[r] = l_run;
       sh.xav[r] = av_raw;
       sh.xai[r] = ai;
+      if (DIAG) sh.xd[r] = dsum;
     }
     named_bar_sync(9 + quad, 64);
     if (par == 0 && row_ok) {
@@ -515,6 +537,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       pl[o] = l_tot;
       pav[o] = av_raw * scale2;
       pai[o] = ai;
+      if (DIAG) pdist[o] = dsum + sh.xd[r];
     }
     if (tid == 0) tl_stamp(tl, 5);
     // O row r, half of the columns per warp: tensor memory -> bf16 -> this thread's own staging segment
@@ -671,7 +694,7 @@ EncodeTiledFn encode_tiled_fn() {
 
 thread_local long long* g_tc_timeline = nullptr;
 
-template <int C, int TN>
+template <int C, int TN, bool DIAG>
 int launch_tc(const __nv_bfloat16* q_hat, const void* queue, int B, long long K, long long ldq, float scale2,
               const InfoNcePlan& p, InfoNcePartials out, int want_argmax, cudaStream_t s) {
   EncodeTiledFn enc = encode_tiled_fn();
@@ -695,11 +718,12 @@ int launch_tc(const __nv_bfloat16* q_hat, const void* queue, int B, long long K,
   constexpr int kPBytes = (TN / 64) * 16384;
   constexpr int kStages = ((kSmemBudget - 2 * kPBytes) / kStageBytes) < 8 ? ((kSmemBudget - 2 * kPBytes) / kStageBytes) : 8;
   const size_t smem = (size_t)kStages * kStageBytes + 2 * kPBytes + 1024;
-  auto kern = infonce_tc_kernel<C, TN>;
+  auto kern = infonce_tc_kernel<C, TN, DIAG>;
   RMCL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(p.splits, p.row_blocks);
   RMCL_CUDA_OK(launch_pdl(kern, grid, dim3(kTcThreads), smem, s, tmap, q_hat, B, K, scale2, p.cols_per_split, want_argmax,
-                          out.m, out.l, out.av, out.ai, reinterpret_cast<__nv_bfloat16*>(out.o), g_tc_timeline));
+                          out.m, out.l, out.av, out.ai, reinterpret_cast<__nv_bfloat16*>(out.o), g_tc_timeline, out.n2,
+                          out.qn2, out.dist));
   return RMCL_OK;
 }
 
@@ -732,10 +756,17 @@ int infonce_tc_launch(const __nv_bfloat16* q_hat, const void* queue, int B, int 
     set_error("InfoNCE: too many rows (%d)", B);
     return RMCL_E_UNSUPPORTED_DIM;
   }
+  const bool dg = out.n2 != nullptr;
   switch (C) {
-    case 256: return launch_tc<256, 64>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s);
-    case 128: return launch_tc<128, 128>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s);
-    case 64: return launch_tc<64, 128>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s);
+    case 256:
+      return dg ? launch_tc<256, 64, true>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s)
+                : launch_tc<256, 64, false>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s);
+    case 128:
+      return dg ? launch_tc<128, 128, true>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s)
+                : launch_tc<128, 128, false>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s);
+    case 64:
+      return dg ? launch_tc<64, 128, true>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s)
+                : launch_tc<64, 128, false>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s);
   }
   set_error("tcgen05 InfoNCE supports C in {64,128,256} (got %d)", C);
   return RMCL_E_UNSUPPORTED_DIM;

@@ -16,7 +16,6 @@ torch; what changes is everything between them:
 from copy import deepcopy
 
 import torch
-import torch.nn.functional as F
 
 from . import dist as rdist
 from . import ops
@@ -92,32 +91,9 @@ def compute_pgd(pl_module, batch, loss_name, k_modality=None):
     return batch
 
 
-@torch.no_grad()
-def queue_diagnostics(q_hat, k_hat, queue, cosine, chunk=8192):
-    """pos/neg L2, cosine and dot means of objectives.py:337-349 without the per-sample Python
-    loop: dot and cosine collapse to one [C] reduction of the queue; the L2 term is chunked."""
-    qf = queue.float()
-    out = {
-        "pos_dist": torch.linalg.norm(q_hat - k_hat, dim=1).mean(),
-        "pos_cosine": cosine(q_hat, k_hat).mean(),
-        "pos_dot": torch.sum(q_hat * k_hat, dim=1).mean(),
-    }
-    col_norm = qf.norm(dim=0)                                         # [K]
-    out["neg_dot"] = (q_hat @ qf.mean(dim=1)).mean()
-    qn = q_hat.norm(dim=1).clamp_min(1e-6)
-    out["neg_cosine"] = ((q_hat / qn[:, None]) @ (qf / col_norm.clamp_min(1e-6)).mean(dim=1)).mean()
-    q2 = (q_hat * q_hat).sum(1, keepdim=True)
-    acc = torch.zeros((), device=q_hat.device)
-    for s in range(0, qf.shape[1], chunk):
-        blk = qf[:, s:s + chunk]
-        d2 = q2 - 2.0 * (q_hat @ blk) + (col_norm[s:s + chunk] ** 2)[None, :]
-        acc = acc + d2.clamp_min(0).sqrt().sum()
-    out["neg_dist"] = acc / (q_hat.shape[0] * qf.shape[1])
-    return out
-
-
-def _attacked_view(pl_module, batch, k_hat, prediction_original, suffix, rate_name, ret, diagnostics):
-    """One attacked/augmented view: forward, fused InfoNCE loss (+argmax), diagnostics."""
+def _attacked_view(pl_module, batch, k_hat, prediction_original, suffix, rate_name, ret, stats):
+    """One attacked/augmented view: forward, then ONE fused launch chain for the InfoNCE loss, its
+    gradient, the row argmax and (``stats``: ops.QueueStats) the six pos/neg diagnostics."""
     if "image_embeds_delta" in batch:  # embedding-space PGD (extension)
         tr = pl_module.transformer
         emb, masks, _, _ = tr.visual_embed(batch["image"][0], max_image_len=pl_module.hparams.config["max_image_len"],
@@ -127,15 +103,15 @@ def _attacked_view(pl_module, batch, k_hat, prediction_original, suffix, rate_na
     else:
         infer = pl_module.infer(batch, mask_text=False, mask_image=False)
     q_raw = pl_module.moco_head(infer["cls_feats"])
-    loss, argmax = ops.infonce_loss(q_raw, k_hat, infonce_queue(pl_module), pl_module.temperature,
-                                    getattr(pl_module, "infonce_path", "auto"))
+    out = ops.infonce_loss(q_raw, k_hat, infonce_queue(pl_module), pl_module.temperature,
+                           getattr(pl_module, "infonce_path", "auto"), diag=stats)
+    loss, argmax = out[0], out[1]
     if pl_module.training:
         pl_module.log(f"moco_attack/{rate_name}_success_rate",
                       (~(argmax == prediction_original)).sum() / argmax.shape[0])
-    if diagnostics:
-        d = queue_diagnostics(F.normalize(q_raw.detach().float(), dim=1), k_hat, pl_module.proj_queue, pl_module.cosine)
-        for name, v in d.items():
-            ret[f"{name}_attacked_{suffix}"] = v
+    if stats is not None:
+        for i, name in enumerate(ops.DIAG_NAMES):
+            ret[f"{name}_attacked_{suffix}"] = out[2][i]
     pl_module.log(f"moco_loss/attacked_{suffix}_loss", loss)
     return loss
 
@@ -159,6 +135,9 @@ def compute_moco_contrastive(pl_module, batch, diagnostics=True):
                                 normalize_k=True, need_grad=False, path=getattr(pl_module, "infonce_path", "auto"),
                                 want=("argmax", "k_hat"))
     prediction_original, k = clean["argmax"], clean["k_hat"]
+    # |queue_j|^2 and the two [C] sums behind the neg_* diagnostics: one reduction of the queue per step,
+    # shared by every view (the reference re-reduces the queue 3*B times per view, objectives.py:341-346)
+    stats = ops.QueueStats(pl_module.proj_queue, cos_eps=getattr(pl_module.cosine, "eps", 1e-6)) if diagnostics else None
 
     attacked_words = None
     if pl_module.text_view:
@@ -167,7 +146,7 @@ def compute_moco_contrastive(pl_module, batch, diagnostics=True):
         else:
             augmented_batch = compute_geometric(pl_module, deepcopy(batch), "moco", k_modality=k)
             attacked_words = {n: deepcopy(augmented_batch[n]) for n in ("text", "text_ids", "text_masks")}
-        loss = loss + _attacked_view(pl_module, augmented_batch, k, prediction_original, "txt", "Geom", ret, diagnostics)
+        loss = loss + _attacked_view(pl_module, augmented_batch, k, prediction_original, "txt", "Geom", ret, stats)
         loss_num += 1
 
     if pl_module.image_view:
@@ -175,13 +154,13 @@ def compute_moco_contrastive(pl_module, batch, diagnostics=True):
             augmented_batch = pl_module.image_augmentation_fn(pl_module, deepcopy(batch))
         else:
             augmented_batch = compute_pgd(pl_module, deepcopy(batch), "moco", k_modality=k)
-        loss = loss + _attacked_view(pl_module, augmented_batch, k, prediction_original, "img", "PGD", ret, diagnostics)
+        loss = loss + _attacked_view(pl_module, augmented_batch, k, prediction_original, "img", "PGD", ret, stats)
         loss_num += 1
 
     if pl_module.image_view and pl_module.text_view and not pl_module.augmentation:
         for n in ("text", "text_ids", "text_masks"):
             augmented_batch[n] = attacked_words[n]
-        loss = loss + _attacked_view(pl_module, augmented_batch, k, prediction_original, "both", "Both", ret, diagnostics)
+        loss = loss + _attacked_view(pl_module, augmented_batch, k, prediction_original, "both", "Both", ret, stats)
         loss_num += 1
 
     if pl_module.training:

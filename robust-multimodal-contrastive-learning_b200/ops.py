@@ -105,14 +105,39 @@ def _workspace(B, Cdim, K, qdt, path, device):
     return ws, off
 
 
+DIAG_NAMES = ("pos_dist", "pos_cosine", "pos_dot", "neg_dist", "neg_cosine", "neg_dot")
+
+
+class QueueStats:
+    """|queue_j|^2 per column and the two [C] sums the per-view diagnostics need (include/rmcl_b200.h,
+    rmcl_queue_stats) — computed once per step, shared by every view's ``infonce_fwd_bwd(..., diag=...)``."""
+
+    def __init__(self, queue, cos_eps=1e-6):
+        _need_cuda(queue)
+        if queue.dim() != 2 or queue.stride(1) != 1:
+            raise ValueError("queue must be [C,K] with K contiguous (reference layout)")
+        Cd, K = queue.shape
+        f32 = dict(dtype=torch.float32, device=queue.device)
+        self.cos_eps = float(cos_eps)
+        self.colnorm2 = torch.empty(K, **f32)
+        self.sum_vec = torch.empty(Cd, **f32)
+        self.sum_unit = torch.empty(Cd, **f32)
+        self.shape = (Cd, K)
+        rc = _lib.lib().rmcl_queue_stats(_p(queue), _dt(queue), Cd, K, queue.stride(0), self.cos_eps, _p(self.colnorm2),
+                                         _p(self.sum_vec), _p(self.sum_unit), _stream())
+        check(rc, "rmcl_queue_stats")
+
+
 def infonce_fwd_bwd(q, k, queue, temperature, *, loss_scale=1.0, normalize_k=False, need_grad=True,
                     path="auto", want=("loss", "loss_per_row", "lse", "pos", "argmax", "dq", "dk", "k_hat"),
-                    _partial_only=False):
+                    diag=None, _partial_only=False):
     """Fused InfoNCE of raw projections ``q`` [B,C] against [``k`` ; ``queue`` [C,K]].
 
     Returns a dict with the requested outputs (see include/rmcl_b200.h).  ``loss`` is
     ``loss_scale * mean_i(lse_i - pos_i)`` — CrossEntropyLoss against label 0
-    (vilt/modules/objectives.py:333-334,351).
+    (vilt/modules/objectives.py:333-334,351).  With ``diag`` (a :class:`QueueStats` of ``queue`` — or of the
+    fp32 buffer a bf16 shadow mirrors) the result also holds ``"diag"``: the six means of
+    objectives.py:337-349 in the order of ``DIAG_NAMES``; ``k`` must then be the normalised key.
     """
     _need_cuda(q, k, queue)
     if q.dim() != 2 or k.shape != q.shape or queue.dim() != 2 or queue.shape[0] != q.shape[1]:
@@ -146,6 +171,18 @@ def infonce_fwd_bwd(q, k, queue, temperature, *, loss_scale=1.0, normalize_k=Fal
     flags = (_lib.FLAG_NORMALIZE_K if normalize_k else 0) | (0 if need_grad else _lib.FLAG_NO_GRAD)
     if _partial_only:   # measurement aid (bench.py): the partial kernel alone, on the workspace of a previous call
         flags |= _lib.FLAG_DEBUG_PARTIAL_ONLY
+    if diag is not None:
+        if diag.shape != (Cd, K):
+            raise ValueError(f"QueueStats of a {diag.shape} queue used with a {(Cd, K)} queue")
+        out["diag"] = torch.empty(len(DIAG_NAMES), **f32)
+        rc = _lib.lib().rmcl_infonce_fwd_bwd_diag(
+            _p(q), _dt(q), _p(k), _dt(k), _p(queue), _dt(queue), B, Cd, K, ldq, float(temperature), float(loss_scale),
+            flags, pth, _p(out.get("loss")), _p(out.get("loss_per_row")), _p(out.get("lse")), _p(out.get("pos")),
+            _p(out.get("argmax")), _p(out.get("dq")), _p(out.get("dk")), _p(out.get("k_hat")),
+            _p(diag.colnorm2), _p(diag.sum_vec), _p(diag.sum_unit), diag.cos_eps, _p(out["diag"]),
+            C.c_void_p(ws.data_ptr() + off), ws.numel() - off, _stream())
+        check(rc, "rmcl_infonce_fwd_bwd_diag")
+        return out
     rc = _lib.lib().rmcl_infonce_fwd_bwd(
         _p(q), _dt(q), _p(k), _dt(k), _p(queue), _dt(queue), B, Cd, K, ldq, float(temperature), float(loss_scale),
         flags, pth, _p(out.get("loss")), _p(out.get("loss_per_row")), _p(out.get("lse")), _p(out.get("pos")),
@@ -164,24 +201,27 @@ class InfoNCE(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, q, k, queue, temperature, path="auto", normalize_k=False):
+    def forward(ctx, q, k, queue, temperature, path="auto", normalize_k=False, diag=None):
         res = infonce_fwd_bwd(q, k, queue, temperature, normalize_k=normalize_k, path=path,
-                              want=("loss", "dq", "argmax", "pos", "lse"))
+                              want=("loss", "dq", "argmax", "pos", "lse"), diag=diag)
         ctx.save_for_backward(res["dq"])
         ctx.q_dtype = q.dtype
         ctx.extra = res
-        ctx.mark_non_differentiable(res["argmax"])
-        return res["loss"], res["argmax"]
+        dg = res["diag"] if diag is not None else torch.empty(0, device=q.device)
+        ctx.mark_non_differentiable(res["argmax"], dg)
+        return res["loss"], res["argmax"], dg
 
     @staticmethod
-    def backward(ctx, grad_loss, _grad_argmax):
+    def backward(ctx, grad_loss, _grad_argmax, _grad_diag):
         (dq,) = ctx.saved_tensors
-        return (dq * grad_loss).to(ctx.q_dtype), None, None, None, None, None
+        return (dq * grad_loss).to(ctx.q_dtype), None, None, None, None, None, None
 
 
-def infonce_loss(q, k, queue, temperature, path="auto", normalize_k=False):
-    """(loss, argmax) with autograd support for ``q``."""
-    return InfoNCE.apply(q, k, queue, temperature, path, normalize_k)
+def infonce_loss(q, k, queue, temperature, path="auto", normalize_k=False, diag=None):
+    """(loss, argmax) — or (loss, argmax, diag[6]) when ``diag`` (QueueStats) is given — with autograd
+    support for ``q``."""
+    loss, argmax, dg = InfoNCE.apply(q, k, queue, temperature, path, normalize_k, diag)
+    return (loss, argmax) if diag is None else (loss, argmax, dg)
 
 
 # -------------------------------------------------------------------------------- enqueue

@@ -392,6 +392,51 @@ def test_cpu_tensors_raise(ops):
 
 
 # ================================================================ InfoNCE, tcgen05 path
+# ----------------------------------------------------------------- fused per-view diagnostics
+@pytest.mark.parametrize("B,C,K,qdt,path", [
+    (8, 128, 4096, torch.float32, "simt"), (37, 70, 1000, torch.float32, "simt"), (16, 768, 520, torch.float32, "simt"),
+    (24, 128, 4096, torch.bfloat16, "simt"), (128, 128, 4096, torch.bfloat16, "tcgen05"),
+    (200, 256, 8192, torch.bfloat16, "tcgen05"), (64, 64, 1000, torch.bfloat16, "tcgen05")])
+def test_infonce_diagnostics_vs_oracle(ops, B, C, K, qdt, path):
+    """pos/neg L2, cosine and dot means of objectives.py:337-349 out of the fused pass, against the
+    oracle's restatement of the reference's per-sample loop (un-normalised randn queue, as initialised)."""
+    q, k, queue = _infonce_inputs(B, C, K, seed=B + C, queue_dtype=qdt)
+    want = O.queue_diagnostics(O.l2_normalize(q), k, queue.float())
+    qd = queue.to(DEV)
+    stats = ops.QueueStats(qd)
+    qf = queue.float()
+    assert rel_err(stats.colnorm2, (qf * qf).sum(0)) < 1e-5
+    assert rel_err(stats.sum_vec, qf.sum(1)) < 1e-4
+    assert rel_err(stats.sum_unit, (qf / qf.norm(dim=0).clamp_min(1e-6)).sum(1)) < 1e-4
+    res = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), qd, 0.07, path=path, diag=stats)
+    tol = 1e-4 if (qdt == torch.float32) else 2e-3      # bf16 path: S from bf16-rounded q^
+    for i, name in enumerate(ops.DIAG_NAMES):
+        got, ref = res["diag"][i].item(), want[name].item()
+        assert abs(got - ref) <= tol * max(1.0, abs(ref)), (name, got, ref)
+    # the rest of the call is unaffected by the diagnostics
+    plain = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), qd, 0.07, path=path)
+    assert torch.equal(plain["dq"], res["dq"]) and torch.equal(plain["loss"], res["loss"])
+
+
+def test_infonce_diagnostics_full_size_properties(ops):
+    """cfg2 size: the linear diagnostics must equal their closed forms and the distance mean must obey
+    the triangle bounds | |queue_j| - 1 | <= |q^ - queue_j| <= |queue_j| + 1 averaged over the queue."""
+    B, C, K = 256, 256, 65536
+    q, k, queue = _infonce_inputs(B, C, K, seed=9, queue_dtype=torch.bfloat16)
+    qd = queue.to(DEV)
+    stats = ops.QueueStats(qd)
+    res = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), qd, 0.07, path="tcgen05", diag=stats)
+    qh = O.l2_normalize(q).to(DEV)
+    qf = qd.float()
+    assert abs(res["diag"][5].item() - (qh @ qf.mean(1)).mean().item()) < 1e-4
+    assert abs(res["diag"][2].item() - (qh * k.to(DEV)).sum(1).mean().item()) < 1e-5
+    cn = qf.norm(dim=0)
+    assert (cn - 1).abs().mean().item() - 1e-3 <= res["diag"][3].item() <= (cn + 1).mean().item() + 1e-3
+    exact = torch.cdist(qh[:16], qf.T).mean().item()                       # 16 rows exactly
+    rows16 = ops.infonce_fwd_bwd(q[:16].to(DEV), k[:16].to(DEV), qd, 0.07, path="tcgen05", diag=stats)["diag"][3].item()
+    assert abs(rows16 - exact) < 2e-3 * exact
+
+
 def _bf16_oracle(q, k, queue, T, grad_out=1.0):
     """float64 oracle fed the operands the bf16 path sees: q^ and k^ rounded to bf16 before the
     dot products (autocast semantics), bf16 queue, exact accumulation."""
