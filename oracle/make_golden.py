@@ -391,6 +391,58 @@ def make_pgd_direct(ref):
         print(f"wrote {path}: {os.path.getsize(path) / 1e3:.1f} kB")
 
 
+def make_pgd_others(ref):
+    """The other attackers of attack/pgd_attack_vilt.py (bartlowtwins 178-239, nlvr2 241-342, vqa 418-483)
+    driven directly on the tiny module with stand-in heads; PGDAttack_irtr cannot run in the reference
+    (undefined name at line 391) and has no vector."""
+    B, hidden, D, n_ans = 4, 32, 24, 11
+    mod = build_tiny_module(ref, B, 16, 64, hidden=hidden, n_pgd=3, lr=0.05, eps=8.0 / 255.0, T=0.07, m=0.999, seed=9)
+    torch.manual_seed(91)
+    mod.token_type_embeddings = nn.Embedding(3, hidden)          # nlvr2 uses image token type 2
+    mod.barlowtwins_head = nn.Sequential(nn.Linear(hidden, D), nn.ReLU(), nn.Linear(D, D))
+    mod.nlvr2_classifier = nn.Sequential(nn.Linear(2 * hidden, hidden), nn.GELU(), nn.Linear(hidden, 2))
+    mod.vqa_classifier = nn.Sequential(nn.Linear(hidden, hidden), nn.GELU(), nn.Linear(hidden, n_ans))
+    mod.adv_lr = 0.0051
+    mod.hparams = type(mod.hparams)(config={"vqav2_label_size": n_ans}) if hasattr(mod, "hparams") else None
+    if mod.hparams is None:
+        class _H(dict):
+            __getattr__ = dict.__getitem__
+        mod.hparams = _H(config={"vqav2_label_size": n_ans})
+    cfg = dict(adv_steps_img=3, adv_lr_img=0.05, adv_max_norm_img=8.0 / 255.0, max_image_len=200, attack_idx=[True, True])
+    out = {"meta/B": np.int64(B), "meta/hidden": np.int64(hidden), "meta/D": np.int64(D), "meta/n_ans": np.int64(n_ans),
+           "meta/adv_lr": np.float64(mod.adv_lr), "meta/n_pgd": np.int64(3), "meta/lr": np.float64(0.05),
+           "meta/eps": np.float64(8.0 / 255.0)}
+    for k, v in mod.state_dict().items():
+        out[f"state/{k}"] = _np(v)
+    batch = tiny_batch(B, 16, 6, 901)
+    g = torch.Generator().manual_seed(902)
+    # (PGDAttack.infer reads batch["image_0"] whenever that key exists, pgd_attack_vilt.py:38-41, so the
+    #  two-image NLVR2 batch is a separate dict)
+    batch2 = dict(batch)
+    batch2["image_0"] = [torch.randn(B, 3, 16, 16, generator=g)]
+    batch2["image_1"] = [torch.randn(B, 3, 16, 16, generator=g)]
+    batch2["answers"] = [0, 1, 1, 0]
+    batch["vqa_labels"] = [[1, 3], [0], [5, 6, 7], [10]]
+    batch["vqa_scores"] = [[1.0, 0.3], [0.6], [0.3, 0.3, 1.0], [0.9]]
+    k_bt = torch.randn(B, D, generator=g)
+    for n in ("image", "image_0", "image_1"):
+        out[f"batch/{n}"] = _np(batch2[n][0])
+    out["batch/text_ids"] = _np(batch["text_ids"])
+    out["k_barlowtwins"] = _np(k_bt)
+    d = ref.pgd.PGDAttack_bartlowtwins(cfg).pgd_attack(mod, deepcopy(batch), k_modality=k_bt)
+    out["delta/barlowtwins"] = _np(d)
+    d0, d1 = ref.pgd.PGDAttack_nlvr2(cfg).pgd_attack(mod, deepcopy(batch2))
+    out["delta/nlvr2_0"], out["delta/nlvr2_1"] = _np(d0), _np(d1)
+    d0, d1 = ref.pgd.PGDAttack_nlvr2(dict(cfg, attack_idx=[False, True])).pgd_attack(mod, deepcopy(batch2))
+    out["delta/nlvr2_only1_0"], out["delta/nlvr2_only1_1"] = _np(d0), _np(d1)
+    d = ref.pgd.PGDAttack_vqa(cfg).pgd_attack(mod, deepcopy(batch))
+    out["delta/vqa"] = _np(d)
+    path = os.path.join(GOLDEN_DIR, "ref_pgd_others.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {os.path.getsize(path) / 1e3:.1f} kB; |delta| "
+          + ", ".join(f"{k[6:]}={float(np.abs(v).mean()):.4f}" for k, v in out.items() if k.startswith("delta/")))
+
+
 def make_facade(ref):
     """Whole-step golden for the drop-in facade: the tiny module's complete state, the batch, and
     everything the reference's compute_moco_contrastive + backward produced (loss, diagnostics,
@@ -436,6 +488,7 @@ def main():
     ap.add_argument("--cfg1", action="store_true")
     ap.add_argument("--only-cfg1", action="store_true")
     ap.add_argument("--only-facade", action="store_true")
+    ap.add_argument("--only-pgd-others", action="store_true")
     args = ap.parse_args()
     ref = ref_harness.load_reference()
     ref_harness.ensure_process_group()
@@ -443,11 +496,15 @@ def main():
     if args.only_facade:
         make_facade(ref)
         return
+    if args.only_pgd_others:
+        make_pgd_others(ref)
+        return
     if not args.only_cfg1:
         make_facade(ref)
         make_tiny(ref, "ref_tiny_c16", B=4, C=16, K=64, n_pgd=1, lr=0.05, eps=8.0 / 255.0, steps=3)
         make_tiny(ref, "ref_tiny_c128", B=8, C=128, K=256, n_pgd=3, lr=0.05, eps=0.005, steps=2, seed=1)
         make_pgd_direct(ref)
+        make_pgd_others(ref)
     if args.cfg1 or args.only_cfg1:
         make_cfg1(ref)
 

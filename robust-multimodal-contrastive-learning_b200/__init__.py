@@ -3,6 +3,7 @@
 Public surface (reference names):
   compute_moco_contrastive, compute_pgd          vilt/modules/objectives.py:217-447, 160-188
   PGDAttack, PGDAttack_moco                      attack/pgd_attack_vilt.py:7-175
+  PGDAttack_{bartlowtwins,nlvr2,irtr,vqa}        attack/pgd_attack_vilt.py:178-483 (same update kernel)
   MoCo, concat_all_gather                        MoCo/MoCo_RMCL.py
   ops.{ema_multi_, infonce_fwd_bwd, infonce_loss, enqueue_, pgd_step_}   the kernels themselves
 """
@@ -11,6 +12,7 @@ from .dist import concat_all_gather  # noqa: F401
 from .moco import MoCo  # noqa: F401
 from .objectives import (compute_moco_contrastive, compute_pgd, dequeue_and_enqueue,  # noqa: F401
                          momentum_update_key_encoder, shadow_layer)
-from .pgd_attack import PGDAttack, PGDAttack_moco  # noqa: F401
+from .pgd_attack import (PGDAttack, PGDAttack_bartlowtwins, PGDAttack_irtr, PGDAttack_moco,  # noqa: F401
+                         PGDAttack_nlvr2, PGDAttack_vqa)
 
 __version__ = "0.1.0"

@@ -11,6 +11,12 @@ effect on ``batch['image'][0]``.  What changes underneath:
     restores the reference's deepcopy (identical numbers, just slower).
 Extensions (defaults = reference behaviour): ``mode`` in {"ref_linf","sign_linf","l2"},
 ``space`` in {"pixel","embed"}.
+
+The other attackers of the reference file — ``PGDAttack_bartlowtwins`` (178-239), ``PGDAttack_nlvr2``
+(241-342), ``PGDAttack_irtr`` (344-415), ``PGDAttack_vqa`` (418-483) — repeat the same seven-kernel
+update on a different inner loss; here they share ``PGDAttack._pgd_loop`` and the same
+``rmcl_pgd_step`` launch.  Their inner losses (a classifier head + cross-entropy / BCE, the
+Barlow-Twins cross-correlation) stay on torch: they are B x {2, 3129, D} sized.
 """
 from copy import deepcopy
 
@@ -40,6 +46,45 @@ class PGDAttack:
 
     def pgd_attack(self, pl_module, batch, k_image):
         raise NotImplementedError(f"pgd_attack of {self.contrastive_framework} isn't implemented.")
+
+    mode = "ref_linf"
+    copy_modules = False
+    _extra_modules = ()
+
+    def _grab(self, pl_module, names):
+        """build_mini_vilt of every subclass: the reference deep-copies 112 M parameters per call
+        (pgd_attack_vilt.py:115-121); by default the live modules are used (the gradient is only taken
+        w.r.t. the perturbation, so nothing accumulates in them)."""
+        grab = deepcopy if self.copy_modules else (lambda m: m)
+        self.pl_module = pl_module
+        for n in ("text_embeddings", "token_type_embeddings", "transformer", "pooler") + tuple(names):
+            setattr(self, n, grab(getattr(pl_module, n)))
+        self._extra_modules = tuple(names)
+
+    def _zero_grad_all(self):
+        if not self.copy_modules:
+            return  # nothing accumulates: gradients are taken w.r.t. the perturbation only
+        for n in ("text_embeddings", "token_type_embeddings", "transformer", "pooler") + self._extra_modules:
+            getattr(self, n).zero_grad()
+
+    def _pgd_loop(self, deltas, loss_fn):
+        """The loop every attacker of pgd_attack_vilt.py repeats: ``loss_fn(deltas)`` under
+        ``autocast(False)`` + ``enable_grad`` (141-142), gradient w.r.t. the perturbation(s) (160-162), then
+        the update 162-173 as one ``rmcl_pgd_step`` launch per perturbation.  ``deltas[i] is None`` = not
+        attacked (nlvr2 ``attack_idx``)."""
+        for _ in range(self.adv_steps_img):
+            live = [d for d in deltas if d is not None]
+            for d in live:
+                d.requires_grad_(True)
+            with torch.autocast("cuda", enabled=False), torch.enable_grad():
+                loss = loss_fn(deltas)
+                grads = torch.autograd.grad(loss, live)
+            grads = list(grads)
+            deltas = [None if d is None else d.detach() for d in deltas]
+            for d in deltas:
+                if d is not None:
+                    ops.pgd_step_(d, grads.pop(0).contiguous(), self.adv_lr_img, self.adv_max_norm_img, self.mode)
+        return deltas
 
     def infer(self, batch, mask_text=False, mask_image=False, image_token_type_idx=1, image_embeds=None,
               image_masks=None):
@@ -78,19 +123,10 @@ class PGDAttack_moco(PGDAttack):
         self.mode, self.space, self.copy_modules, self.infonce_path = mode, space, copy_modules, infonce_path
 
     def build_mini_vilt(self, pl_module):
-        grab = deepcopy if self.copy_modules else (lambda m: m)
-        self.pl_module = pl_module
-        self.text_embeddings = grab(pl_module.text_embeddings)
-        self.token_type_embeddings = grab(pl_module.token_type_embeddings)
-        self.transformer = grab(pl_module.transformer)
-        self.moco_head = grab(pl_module.moco_head)
-        self.pooler = grab(pl_module.pooler)
+        self._grab(pl_module, ("moco_head",))
 
     def vilt_zero_grad(self):
-        if not self.copy_modules:
-            return  # nothing accumulates: gradients are taken w.r.t. the perturbation only
-        for m in (self.text_embeddings, self.transformer, self.token_type_embeddings, self.moco_head, self.pooler):
-            m.zero_grad()
+        self._zero_grad_all()
 
     def pgd_attack(self, pl_module, batch, k_modality=None):
         self.build_mini_vilt(pl_module)
@@ -103,19 +139,152 @@ class PGDAttack_moco(PGDAttack):
                     img_init, max_image_len=self.max_image_len, mask_it=False)
         else:
             base, image_masks = img_init, None
-        delta = torch.zeros_like(base)
-        for _ in range(self.adv_steps_img):
-            delta.requires_grad_(True)
-            with torch.autocast("cuda", enabled=False), torch.enable_grad():
-                if self.space == "embed":
-                    infer = self.infer(batch, image_embeds=base + delta, image_masks=image_masks)
-                else:
-                    batch["image"][0] = img_init + delta  # reference side effect (pgd_attack_vilt.py:144)
-                    infer = self.infer(batch)
-                q_raw = self.moco_head(infer["cls_feats"])
-                loss, _ = ops.infonce_loss(q_raw.float(), k_modality, queue, temperature, self.infonce_path)
-                loss = loss / (1.0 * self.adv_steps_img)
-                (grad,) = torch.autograd.grad(loss, delta)
-            delta = delta.detach()
-            ops.pgd_step_(delta, grad.contiguous(), self.adv_lr_img, self.adv_max_norm_img, self.mode)
-        return delta
+
+        def loss_fn(deltas):
+            if self.space == "embed":
+                infer = self.infer(batch, image_embeds=base + deltas[0], image_masks=image_masks)
+            else:
+                batch["image"][0] = img_init + deltas[0]  # reference side effect (pgd_attack_vilt.py:144)
+                infer = self.infer(batch)
+            q_raw = self.moco_head(infer["cls_feats"])
+            loss, _ = ops.infonce_loss(q_raw.float(), k_modality, queue, temperature, self.infonce_path)
+            return loss / (1.0 * self.adv_steps_img)
+
+        return self._pgd_loop([torch.zeros_like(base)], loss_fn)[0]
+
+
+class PGDAttack_bartlowtwins(PGDAttack):
+    """pgd_attack_vilt.py:178-239 (the class name keeps the reference's spelling): maximise the
+    Barlow-Twins loss of the perturbed image's projection against ``k_modality``."""
+
+    def __init__(self, config, mode="ref_linf", copy_modules=False):
+        super().__init__(config, "barlowtwins")
+        self.barlowtwins_head = None
+        self.mode, self.copy_modules = mode, copy_modules
+
+    def build_mini_vilt(self, pl_module):
+        self._grab(pl_module, ("barlowtwins_head",))
+
+    def vilt_zero_grad(self):
+        self._zero_grad_all()
+
+    @staticmethod
+    def off_diagonal(x):
+        n, m = x.shape
+        assert n == m
+        return x.flatten()[:-1].view(n - 1, n + 1)[:, 1:].flatten()
+
+    def pgd_attack(self, pl_module, batch, k_modality=None):
+        self.build_mini_vilt(pl_module)
+        self.vilt_zero_grad()
+        img_init = batch["image"][0]
+
+        def loss_fn(deltas):
+            batch["image"][0] = img_init + deltas[0]
+            q_image = self.barlowtwins_head(self.infer(batch)["cls_feats"])
+            c = torch.mm(q_image.to(torch.float32).T, k_modality.to(torch.float32)) / q_image.shape[0]
+            on_diag = torch.diagonal(c).add(-1).pow(2).sum()
+            off_diag = self.off_diagonal(c).pow(2).sum()
+            return (on_diag + pl_module.adv_lr * off_diag) / self.adv_steps_img
+
+        return self._pgd_loop([torch.zeros_like(img_init)], loss_fn)[0]
+
+
+class PGDAttack_nlvr2(PGDAttack):
+    """pgd_attack_vilt.py:241-342: two images per sample, either or both attacked (``attack_idx``);
+    returns ``(img_delta_0, img_delta_1)``."""
+
+    def __init__(self, config, mode="ref_linf", copy_modules=False):
+        super().__init__(config, "nlvr2")
+        self.attack_idx = config["attack_idx"]
+        self.nlvr2_classifier = None
+        self.mode, self.copy_modules = mode, copy_modules
+
+    def build_mini_vilt(self, pl_module):
+        self._grab(pl_module, ("nlvr2_classifier",))
+
+    def vilt_zero_grad(self):
+        self._zero_grad_all()
+
+    def pgd_attack(self, pl_module, batch, k_modality=None):
+        self.build_mini_vilt(pl_module)
+        self.vilt_zero_grad()
+        init = [batch["image_0"][0], batch["image_1"][0]]
+        labels = torch.as_tensor(batch["answers"], device=init[0].device).long()
+
+        def loss_fn(deltas):
+            for j in (0, 1):
+                batch[f"image_{j}"][0] = init[j] + (deltas[j] if deltas[j] is not None else 0)
+            infer1 = self.infer(batch, image_token_type_idx=1)
+            infer2 = self.infer(batch, image_token_type_idx=2)
+            logits = self.nlvr2_classifier(torch.cat([infer1["cls_feats"], infer2["cls_feats"]], dim=-1))
+            return torch.nn.functional.cross_entropy(logits, labels) / self.adv_steps_img
+
+        deltas = self._pgd_loop([torch.zeros_like(init[j]) if self.attack_idx[j] else None for j in (0, 1)], loss_fn)
+        return tuple(d if d is not None else torch.zeros_like(init[j]) for j, d in enumerate(deltas))
+
+
+class PGDAttack_irtr(PGDAttack):
+    """pgd_attack_vilt.py:344-415.  The reference body reads an undefined name (``text_representation``,
+    line 391) and cannot run; the evident intent — in-batch retrieval logits of the attacked image
+    projections against the text representations handed in as ``k_modality``, label = own index — is
+    what this implements."""
+
+    def __init__(self, config, mode="ref_linf", copy_modules=False):
+        super().__init__(config, "moco")
+        self.moco_head = None
+        self.mode, self.copy_modules = mode, copy_modules
+
+    def build_mini_vilt(self, pl_module):
+        self._grab(pl_module, ("moco_head",))
+
+    def vilt_zero_grad(self):
+        self._zero_grad_all()
+
+    def pgd_attack(self, pl_module, batch, k_modality):
+        self.build_mini_vilt(pl_module)
+        self.vilt_zero_grad()
+        img_init = batch["image"][0]
+        labels = torch.arange(img_init.shape[0], device=img_init.device)
+
+        def loss_fn(deltas):
+            batch["image"][0] = img_init + deltas[0]
+            q = torch.nn.functional.normalize(self.moco_head(self.infer(batch)["cls_feats"]), dim=1)
+            logits = torch.einsum("nc,ck->nk", [q, k_modality.T])
+            return torch.nn.functional.cross_entropy(logits.float(), labels) / (1.0 * self.adv_steps_img)
+
+        return self._pgd_loop([torch.zeros_like(img_init)], loss_fn)[0]
+
+
+class PGDAttack_vqa(PGDAttack):
+    """pgd_attack_vilt.py:418-483: BCE-with-logits against the soft VQA targets, forward through the
+    module's own ``infer`` (as the reference does, 453) and — unlike the others — no division by the
+    number of steps (466-468)."""
+
+    def __init__(self, config, mode="ref_linf", copy_modules=False):
+        super().__init__(config, "vqa")
+        self.vqa_classifier = None
+        self.mode, self.copy_modules = mode, copy_modules
+
+    def build_mini_vilt(self, pl_module):
+        self._grab(pl_module, ("vqa_classifier",))
+
+    def vilt_zero_grad(self):
+        self._zero_grad_all()
+
+    def pgd_attack(self, pl_module, batch, k_modality=None):
+        self.build_mini_vilt(pl_module)
+        self.vilt_zero_grad()
+        img_init = batch["image"][0]
+        n_labels = pl_module.hparams.config["vqav2_label_size"]
+        targets = torch.zeros(img_init.shape[0], n_labels, device=img_init.device)
+        for i, (_label, _score) in enumerate(zip(batch["vqa_labels"], batch["vqa_scores"])):
+            for l, sc in zip(_label, _score):
+                targets[i, l] = sc
+
+        def loss_fn(deltas):
+            batch["image"][0] = img_init + deltas[0]
+            logits = pl_module.vqa_classifier(pl_module.infer(batch, mask_text=False, mask_image=False)["cls_feats"])
+            return torch.nn.functional.binary_cross_entropy_with_logits(logits, targets) * targets.shape[1]
+
+        return self._pgd_loop([torch.zeros_like(img_init)], loss_fn)[0]

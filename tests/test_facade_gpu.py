@@ -214,3 +214,81 @@ def test_moco_module_api(golden):
     ce = torch.nn.functional.cross_entropy(out["txt"], labels["txt"])
     assert abs(ce.item() - out["loss_txt"].item()) < 1e-4 * abs(ce.item())
     assert moco.encoder_q.t.weight.grad is not None
+
+
+# ------------------------------------------------- the other attackers of attack/pgd_attack_vilt.py
+class OthersModule(nn.Module):
+    """Stand-in of oracle/make_golden.py:make_pgd_others — toy encoder plus stand-in task heads."""
+
+    def __init__(self, g):
+        super().__init__()
+        h, D, n_ans = g.i("meta/hidden"), g.i("meta/D"), g.i("meta/n_ans")
+        self.text_embeddings = nn.Embedding(50, h)
+        self.token_type_embeddings = nn.Embedding(3, h)
+        self.transformer = ToyTransformer(h, 8)
+        self.pooler = ToyPooler(h)
+        self.barlowtwins_head = nn.Sequential(nn.Linear(h, D), nn.ReLU(), nn.Linear(D, D))
+        self.nlvr2_classifier = nn.Sequential(nn.Linear(2 * h, h), nn.GELU(), nn.Linear(h, 2))
+        self.vqa_classifier = nn.Sequential(nn.Linear(h, h), nn.GELU(), nn.Linear(h, n_ans))
+        self.adv_lr = g.f("meta/adv_lr")
+        self.max_image_len = 200
+
+        class _H(dict):
+            __getattr__ = dict.__getitem__
+        self.hparams = _H(config={"vqav2_label_size": n_ans})
+        own = self.state_dict()
+        self.load_state_dict({k[len("state/"):]: g.t(k) for k in g.z.files
+                              if k.startswith("state/") and k[len("state/"):] in own})
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def infer(self, batch, mask_text=False, mask_image=False, **kw):
+        import rmcl_b200
+        return rmcl_b200.PGDAttack.infer(self, batch, mask_text, mask_image, **kw)
+
+
+def test_other_pgd_attackers_match_reference(golden):
+    """PGDAttack_bartlowtwins / _nlvr2 / _vqa (pgd_attack_vilt.py:178-483) on the shared update kernel:
+    perturbations after 3 steps against the unmodified reference classes run on CPU.  The update is
+    bit-exact given the gradient; the gradient itself comes from torch on another device, hence 1e-4 of
+    eps (elements sitting on the +-eps clamp are identical)."""
+    import rmcl_b200
+    from rmcl_b200 import pgd_attack as P
+    g = golden("ref_pgd_others")
+    mod = OthersModule(g).to(DEV).train()
+    cfg = dict(adv_steps_img=g.i("meta/n_pgd"), adv_lr_img=g.f("meta/lr"), adv_max_norm_img=g.f("meta/eps"),
+               max_image_len=200, attack_idx=[True, True])
+    ids = g.t("batch/text_ids").to(DEV)
+    base = {"text": ["x"] * ids.shape[0], "text_ids": ids, "text_labels": torch.full_like(ids, -100),
+            "text_masks": torch.ones_like(ids), "vqa_labels": [[1, 3], [0], [5, 6, 7], [10]],
+            "vqa_scores": [[1.0, 0.3], [0.6], [0.3, 0.3, 1.0], [0.9]]}
+    eps = g.f("meta/eps")
+
+    def close(got, name):
+        want = g.t(f"delta/{name}")
+        err = (got.detach().cpu() - want).abs().max().item()
+        assert err <= 1e-4 * eps + 1e-7, f"{name}: max |delta - ref| = {err:.3e}"
+        assert got.abs().max().item() <= float(np.float32(eps))
+
+    one = dict(base, image=[g.t("batch/image").to(DEV)])
+    close(P.PGDAttack_bartlowtwins(cfg).pgd_attack(mod, deepcopy(one), k_modality=g.t("k_barlowtwins").to(DEV)), "barlowtwins")
+    close(P.PGDAttack_vqa(cfg).pgd_attack(mod, deepcopy(one)), "vqa")
+    two = dict(base, image=[g.t("batch/image").to(DEV)], image_0=[g.t("batch/image_0").to(DEV)],
+               image_1=[g.t("batch/image_1").to(DEV)], answers=[0, 1, 1, 0])
+    d0, d1 = P.PGDAttack_nlvr2(cfg).pgd_attack(mod, deepcopy(two))
+    close(d0, "nlvr2_0")
+    close(d1, "nlvr2_1")
+    d0, d1 = P.PGDAttack_nlvr2(dict(cfg, attack_idx=[False, True])).pgd_attack(mod, deepcopy(two))
+    assert d0.abs().max().item() == 0.0
+    close(d1, "nlvr2_only1_1")
+    # irtr: the reference body cannot run (undefined name); check the documented intent on its own terms
+    k_txt = torch.nn.functional.normalize(torch.randn(ids.shape[0], 16, device=DEV), dim=1)
+    mod.moco_head = MOCOHead(g.i("meta/hidden"), g.i("meta/hidden"), 16).to(DEV)
+    d = P.PGDAttack_irtr(cfg).pgd_attack(mod, deepcopy(one), k_txt)
+    assert d.shape == one["image"][0].shape and 0 < d.abs().max().item() <= float(np.float32(eps))
+    # the copy_modules=True variant (the reference's deepcopy) gives the same perturbation
+    a = P.PGDAttack_vqa(cfg, copy_modules=True).pgd_attack(mod, deepcopy(one))
+    b = P.PGDAttack_vqa(cfg).pgd_attack(mod, deepcopy(one))
+    assert torch.equal(a, b)
