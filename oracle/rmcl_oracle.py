@@ -34,7 +34,7 @@ import torch.nn.functional as F
 __all__ = [
     "momentum_update", "l2_normalize", "info_nce", "info_nce_logits",
     "concat_all_gather", "dequeue_and_enqueue", "pgd_update", "queue_diagnostics",
-    "rmcl_kernel_step",
+    "rmcl_kernel_step", "greedy_split_forward",
 ]
 
 
@@ -195,6 +195,31 @@ def rmcl_kernel_step(params_k, params_q, em, q_raw, k_hat, queue, ptr, temperatu
     keys = k_hat if gathered_keys is None else gathered_keys
     new_queue, new_ptr = dequeue_and_enqueue(queue, ptr, keys, queue.shape[1])
     return new_k, res, new_queue, new_ptr
+
+
+def greedy_split_forward(ori_z, cand_z, all_num, k_modality, queue, temperature):
+    """attack/greedy_attack_vilt.py:461-484 restated: for every sample i and candidate j put the
+    candidate's representation in row i, recompute the whole batch-mean InfoNCE loss, track the first
+    candidate that beats everything before it.  Returns [(losses, best_idx)] like the reference."""
+    def batch_loss(z):
+        logits = info_nce_logits(z, k_modality, queue, temperature)
+        return F.cross_entropy(logits.float() if logits.dtype != torch.float64 else logits,
+                               torch.zeros(z.shape[0], dtype=torch.long))
+    ori_z = ori_z.clone()
+    ori_loss = batch_loss(ori_z)
+    out = []
+    for i, cls_split in enumerate(torch.split(cand_z, all_num)):
+        cur, cur_max, cur_idx = [], ori_loss, -1
+        saved = ori_z[i].clone()
+        for j, cls in enumerate(cls_split):
+            ori_z[i] = cls
+            loss = batch_loss(ori_z)
+            cur.append(loss)
+            if loss > cur_max:
+                cur_max, cur_idx = loss, j
+        out.append((cur, cur_idx))
+        ori_z[i] = saved
+    return out
 
 
 def closed_form_single_negative(s_pos, s_neg, temperature):

@@ -7,7 +7,7 @@ Public surface (reference names):
   MoCo, concat_all_gather                        MoCo/MoCo_RMCL.py
   ops.{ema_multi_, infonce_fwd_bwd, infonce_loss, enqueue_, pgd_step_}   the kernels themselves
 """
-from . import ops  # noqa: F401
+from . import greedy, ops  # noqa: F401
 from .dist import concat_all_gather  # noqa: F401
 from .moco import MoCo  # noqa: F401
 from .objectives import (compute_moco_contrastive, compute_pgd, dequeue_and_enqueue,  # noqa: F401

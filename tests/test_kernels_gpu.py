@@ -392,6 +392,27 @@ def test_cpu_tensors_raise(ops):
 
 
 # ================================================================ InfoNCE, tcgen05 path
+# -------------------------------------------------- greedy text attack: candidate losses (N2)
+@pytest.mark.parametrize("B,C,K,all_num", [(4, 128, 4096, [3, 0, 5, 1]), (6, 64, 520, [2, 2, 2, 2, 2, 2])])
+def test_greedy_split_forward_losses(ops, B, C, K, all_num):
+    """split_forward of attack/greedy_attack_vilt.py:461-484: every candidate's batch loss from two
+    row-wise fused passes equals the reference's recompute-everything loop (oracle restatement)."""
+    from rmcl_b200 import greedy
+    g = torch.Generator().manual_seed(B)
+    nrm = torch.nn.functional.normalize
+    ori = nrm(torch.randn(B, C, generator=g), dim=1)
+    cand = nrm(torch.randn(sum(all_num), C, generator=g), dim=1)
+    k = nrm(torch.randn(B, C, generator=g), dim=1)
+    queue = nrm(torch.randn(C, K, generator=g), dim=0)
+    want = O.greedy_split_forward(ori.double(), cand.double(), all_num, k.double(), queue.double(), 0.07)
+    got = greedy.split_forward_losses(ori.to(DEV), cand.to(DEV), all_num, k.to(DEV), queue.to(DEV), 0.07)
+    assert len(got) == len(want) == B
+    for (gl, gi), (wl, wi) in zip(got, want):
+        assert gi == wi and len(gl) == len(wl)
+        for a, b in zip(gl, wl):
+            assert abs(a.item() - b.item()) <= 1e-5 * abs(b.item())
+
+
 # ----------------------------------------------------------------- fused per-view diagnostics
 @pytest.mark.parametrize("B,C,K,qdt,path", [
     (8, 128, 4096, torch.float32, "simt"), (37, 70, 1000, torch.float32, "simt"), (16, 768, 520, torch.float32, "simt"),
