@@ -27,10 +27,12 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 int infonce_make_plan(int B, int C, long long K, int queue_dtype, int path, bool aligned_for_tc, InfoNcePlan* p) {
   const int sms = sm_count();
   if (sms <= 0) return RMCL_E_CUDA;
-  const bool tc_ok = infonce_tc_built() && aligned_for_tc && queue_dtype == RMCL_BF16 && (C == 64 || C == 128 || C == 256) && (K % 8 == 0);
+  const bool wide = infonce_tc2_supports(C);   // two-pass tcgen05 variant (infonce_tc2.cu)
+  const bool tc_ok = infonce_tc_built() && aligned_for_tc && queue_dtype == RMCL_BF16 &&
+                     (C == 64 || C == 128 || C == 256 || wide) && (K % 8 == 0);
   if (path == RMCL_INFONCE_AUTO) path = tc_ok ? RMCL_INFONCE_TCGEN05 : RMCL_INFONCE_SIMT;
   if (path == RMCL_INFONCE_TCGEN05 && !tc_ok) {
-    set_error("tcgen05 InfoNCE needs a 16B-aligned bf16 queue, C in {64,128,256}, K %% 8 == 0 (got C=%d K=%lld)", C, K);
+    set_error("tcgen05 InfoNCE needs a 16B-aligned bf16 queue, C in {64,128,256,512,768}, K %% 8 == 0 (got C=%d K=%lld)", C, K);
     return RMCL_E_UNSUPPORTED_DIM;
   }
   if (path == RMCL_INFONCE_SIMT && C > 1024) {
@@ -43,8 +45,9 @@ int infonce_make_plan(int B, int C, long long K, int queue_dtype, int path, bool
     p->tile_cols = (C <= 512) ? 64 : 32;
   } else {
     p->rows_per_cta = 128;
-    p->tile_cols = infonce_tc_tile_cols(C);
+    p->tile_cols = wide ? 64 : infonce_tc_tile_cols(C);
   }
+  p->two_pass = (path == RMCL_INFONCE_TCGEN05) && wide;
   p->row_blocks = (B + p->rows_per_cta - 1) / p->rows_per_cta;
   p->b_pad = p->row_blocks * p->rows_per_cta;
   const long long tiles = (K + p->tile_cols - 1) / p->tile_cols;
@@ -74,6 +77,8 @@ int infonce_make_plan(int B, int C, long long K, int queue_dtype, int path, bool
   p->off_qn2 = take(Bs * 4);
   p->off_pdist = take(S * Bs * 4);
   p->off_diagrows = take(Bs * kDiagValues * 4);
+  p->k_pad = (K + 63) / 64 * 64;
+  p->off_ptilde = take(p->two_pass ? (size_t)p->b_pad * (size_t)p->k_pad * 2 : 0);
   p->total = off;
   return RMCL_OK;
 }
@@ -102,7 +107,10 @@ __global__ void __launch_bounds__(128) infonce_prep_kernel(const TQ* __restrict_
   __shared__ float red[4];
   const int row = blockIdx.x;
   if (threadIdx.x == 0) pdl_trigger();   // the partial kernel may set itself up while this one runs
-  if (row == 0 && threadIdx.x == 0) *counter = 0u;
+  if (row == 0 && threadIdx.x == 0) {
+    counter[0] = 0u;
+    counter[1] = 0u;   // overflow flag of the two-pass tcgen05 variant
+  }
   const size_t rep_stride = (size_t)b_pad * C;   // kQhatReplicas copies of the bf16 operand (infonce.cuh)
   if (row >= B) {  // padding rows of the bf16 operand (the tcgen05 kernel reads whole 128-row blocks)
     for (int c = threadIdx.x; c < C; c += 128)
@@ -166,6 +174,8 @@ __global__ void __launch_bounds__(kFinThreads, 2) infonce_finalize_kernel(
     float* __restrict__ loss_per_row, float* __restrict__ lse_out, float* __restrict__ pos_out,
     long long* __restrict__ argmax_out, float* __restrict__ dq, float* __restrict__ dk, const float* __restrict__ pdist,
     const float* __restrict__ qn2, float inv_K, const InfoNceDiag diag) {
+  // counter[1]: raised by the two-pass tcgen05 S kernel when a fixed split reference could not hold the
+  // row maximum; nothing computed from those partials is meaningful, so every output becomes NaN.
   extern __shared__ float fin_smem[];
   float* sw = fin_smem;                       // [splits] merge weights
   float* part = fin_smem + ((splits + 3) & ~3);  // [kFinGroups-1][C] partial column sums of groups 1..
@@ -242,14 +252,15 @@ __global__ void __launch_bounds__(kFinThreads, 2) infonce_finalize_kernel(
       const float pos = p2 * kLn2;
       // lse - pos cancels catastrophically when the positive dominates (p_pos -> 1); take the
       // difference before the log instead: positive is the max -> log1p of the remaining mass.
-      const float lrow = (p2 >= mmax) ? log1pf(lsum * wneg) : fmaf(M - p2, kLn2, logf(L));
+      const float poison = (__ldcg(counter + 1) != 0u) ? __int_as_float(0x7fc00000) : 0.f;
+      const float lrow = ((p2 >= mmax) ? log1pf(lsum * wneg) : fmaf(M - p2, kLn2, logf(L))) + poison;
       row_loss[row] = lrow;
       if (loss_per_row) loss_per_row[row] = lrow;
       if (lse_out) lse_out[row] = lse;
       if (pos_out) pos_out[row] = pos;
       if (argmax_out) argmax_out[row] = (p2 >= bv) ? 0ll : (long long)bi + 1;
-      s_stats[0] = wneg / L;
-      s_stats[1] = -(lsum * wneg) / L;  // p_pos - 1 without the cancellation of wpos/L - 1
+      s_stats[0] = wneg / L + poison;
+      s_stats[1] = -(lsum * wneg) / L + poison;  // p_pos - 1 without the cancellation of wpos/L - 1
     }
   }
   __syncthreads();
@@ -459,8 +470,14 @@ static int infonce_impl(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_d
   RMCL_CHECK_ARG(dtype_ok(q_dtype) && dtype_ok(k_dtype) && dtype_ok(queue_dtype), "rmcl_infonce_fwd_bwd: bad dtype");
   RMCL_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "rmcl_infonce_fwd_bwd: workspace must be 256B aligned");
   InfoNcePlan p;
+  // the per-view diagnostics are fused into the single-pass kernels only
+  if (diag.out && path == RMCL_INFONCE_AUTO && infonce_tc2_supports(C)) path = RMCL_INFONCE_SIMT;
   int rc = infonce_make_plan(B, C, K, queue_dtype, path, tc_alignment_ok(queue, ldq), &p);
   if (rc != RMCL_OK) return rc;
+  if (diag.out && p.two_pass) {
+    set_error("rmcl_infonce_fwd_bwd_diag: the two-pass tcgen05 path (C=%d) has no fused diagnostics; use AUTO or SIMT", C);
+    return RMCL_E_UNSUPPORTED_DIM;
+  }
   if (workspace_bytes < p.total) {
     set_error("rmcl_infonce_fwd_bwd: workspace %zu < required %zu", workspace_bytes, p.total);
     return RMCL_E_WORKSPACE;
@@ -492,7 +509,10 @@ static int infonce_impl(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_d
   InfoNcePartials parts{(float*)(ws + p.off_m), (float*)(ws + p.off_l), (float*)(ws + p.off_av), (int*)(ws + p.off_ai),
                         (float*)(ws + p.off_o), diag.out ? diag.colnorm2 : nullptr, (const float*)(ws + p.off_qn2),
                         (float*)(ws + p.off_pdist)};
-  if (tc)
+  if (tc && p.two_pass)
+    rc = infonce_tc2_launch((const bf16*)(ws + p.off_qhat_bf16), queue, B, C, K, ldq, scale2, p, parts,
+                            (bf16*)(ws + p.off_ptilde), p.k_pad, (unsigned int*)(ws + p.off_counter) + 1, argmax != nullptr, s);
+  else if (tc)
     rc = infonce_tc_launch((const bf16*)(ws + p.off_qhat_bf16), queue, B, C, K, ldq, scale2, p, parts, argmax != nullptr, s);
   else
     rc = infonce_simt_launch((const float*)(ws + p.off_qhat), queue, queue_dtype, B, C, K, ldq, scale2, p, parts, s);

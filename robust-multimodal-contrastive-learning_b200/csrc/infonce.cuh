@@ -10,6 +10,7 @@
 // Two partial-stage implementations write this same format:
 //   infonce_simt.cu  — fp32 CUDA-core kernel, any dtype/shape (fp32 parity path, C<=1024)
 //   infonce_tc.cu    — tcgen05/TMEM/TMA kernel for bf16 queues (C in {64,128,256})
+//   infonce_tc2.cu   — two tcgen05 kernels (S pass, PV pass) for bf16 queues with C in {512,768}
 #pragma once
 #include "common.cuh"
 
@@ -33,9 +34,11 @@ struct InfoNcePlan {
   int row_blocks;
   int tile_cols;        // queue columns per inner tile
   int b_pad;            // B rounded up to rows_per_cta
+  bool two_pass;        // tcgen05 with C > 256: S pass + PV pass through P~ (infonce_tc2.cu)
+  long long k_pad;      // K rounded up to 64: row stride of P~
   // workspace carve-up (byte offsets)
   size_t off_qhat, off_khat, off_inv, off_pos2, off_qhat_bf16, off_m, off_l, off_av, off_ai, off_o, off_rowloss,
-      off_counter, off_qn2, off_pdist, off_diagrows, total;
+      off_counter, off_qn2, off_pdist, off_diagrows, off_ptilde, total;
 };
 
 // Optional: the reference's per-view diagnostics (vilt/modules/objectives.py:337-349) from the same
@@ -73,6 +76,10 @@ int infonce_simt_launch(const float* q_hat, const void* queue, int queue_dtype, 
 int infonce_tc_launch(const __nv_bfloat16* q_hat_bf16, const void* queue, int B, int C, long long K, long long ldq,
                       float scale2, const InfoNcePlan& plan, InfoNcePartials out, int want_argmax, cudaStream_t s);
 int infonce_tc_tile_cols(int C);
+bool infonce_tc2_supports(int C);
+int infonce_tc2_launch(const __nv_bfloat16* q_hat_bf16, const void* queue, int B, int C, long long K, long long ldq,
+                       float scale2, const InfoNcePlan& plan, InfoNcePartials out, __nv_bfloat16* ptilde, long long k_pad,
+                       unsigned int* overflow_flag, int want_argmax, cudaStream_t s);
 bool infonce_tc_built();
 
 }  // namespace rmcl

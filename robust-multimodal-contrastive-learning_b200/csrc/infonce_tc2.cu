@@ -1,0 +1,453 @@
+// K1 partial stage for wide projections (C = 512 or 768: BASELINE cfg5, dim 768 / queue 262144), tcgen05.
+//
+// The fused single-pass kernel (infonce_tc.cu) keeps Q^ (C/2 columns) and the fp32 accumulator O (C columns)
+// of its 128 rows in tensor memory; at C = 768 that is 384 + 768 of the 512 columns an SM has, and no
+// split over a CTA pair removes the need for the full-C contraction in S.  Here the two GEMMs run as two
+// tensor-core kernels with the (unnormalised, bf16) probabilities as the only intermediate:
+//
+//   S pass   infonce_s_kernel<C>:  CTA = 128 rows x one split of the queue, tiles of 64 columns.
+//            S = Q^ . tile over C in chunks of 256 rows (TMA ring of 32 KB chunk stages, Q^ in TMEM);
+//            P~ = 2^(S*log2e/tau - m_ref) with ONE reference per (row, split), fixed after the first tile
+//            (its row maximum + 24): no rescaling can be needed downstream.  Emits the split statistics
+//            (m_ref, l, argmax) of infonce.cuh and P~ [B_pad, K_pad] in bf16.
+//   PV pass  infonce_pv_kernel:    CTA = 128 rows x the same split x one 256-wide slice of C.
+//            O[:, slice] = sum_tiles P~_tile . queue[slice, tile]^T — a plain split-K tcgen05 GEMM with both
+//            operands staged by TMA (P~ K-major, the queue slice K-major), O (256 columns) in TMEM,
+//            bf16 partials written exactly like the fused kernel's.
+//
+// The logits are still never materialised in fp32 and never leave the chip in a form the reference has
+// (B x K bf16 of P~ instead of 3-4 fp32 copies of the logits, objectives.py:272-274,333).  A fixed reference
+// cannot follow a row maximum that grows by more than 2^100 inside one split; that cannot happen for
+// normalised keys (|logit| <= 1/tau) and is caught, not ignored: the S pass raises a flag that makes the
+// finalize kernel return NaN.
+#include "infonce.cuh"
+#include "tc_ptx.cuh"
+
+namespace rmcl {
+
+namespace {
+
+using namespace tcx;
+
+constexpr int kThreads = 320;          // warps 0-7 softmax / epilogue, warp 8 TMA producer + TMEM allocator, warp 9 MMA issuer
+constexpr int kRows = 128;
+constexpr int kTN = 64;                // queue columns per tile
+constexpr int kChunkRows = 256;        // rows of C per TMA chunk stage / per PV slice
+constexpr int kChunkBytes = kChunkRows * kTN * 2;   // 32 KB
+constexpr float kMargin = 24.f;        // initial reference = first tile's row maximum + 2^24 (see infonce_tc.cu)
+constexpr float kOverflow = 100.f;     // P~ would exceed 2^100 (bf16 tops out at 2^127): flag it
+
+struct SShared {
+  uint64_t k_full[8];
+  uint64_t k_empty[8];
+  uint64_t s_full[2];
+  uint64_t s_free[2];
+  uint64_t q_full;
+  uint32_t tmem_base;
+  float m_ref[kRows];
+  float xl[kRows];
+  float xav[kRows];
+  int xai[kRows];
+};
+
+// =========================================================================================== S pass
+template <int C>
+__global__ void __launch_bounds__(kThreads, 1)
+    infonce_s_kernel(const __grid_constant__ CUtensorMap tmap_queue, const __nv_bfloat16* __restrict__ q_hat, int B,
+                     long long K, long long k_pad, float scale2, long long cols_per_split, int want_argmax,
+                     float* __restrict__ pm, float* __restrict__ pl, float* __restrict__ pav, int* __restrict__ pai,
+                     __nv_bfloat16* __restrict__ ptilde, unsigned int* __restrict__ overflow_flag) {
+  constexpr int kChunks = C / kChunkRows;              // ring stages consumed per tile
+  constexpr int kStages = 5;
+  constexpr uint32_t kTmQ = 0, kTmS = C / 2;
+  static_assert(C % kChunkRows == 0 && C / 2 + 2 * kTN <= 512, "tensor memory budget");
+  constexpr uint32_t kIdescS = make_idesc(128, kTN, 1);
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ SShared sh;
+  uint8_t* stage_buf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ring = stage_buf + 8 * 4096;                // 8 warps x 4 KB of P~ / Q^ transposing scratch first
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x;
+  const int row0 = blockIdx.y * kRows;
+  const long long k_begin = (long long)split * cols_per_split;
+  const long long k_end = (k_begin + cols_per_split < K) ? k_begin + cols_per_split : K;
+  const int n_tiles = (int)((k_end - k_begin + kTN - 1) / kTN);
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&sh.k_full[i], 1);
+      mbar_init(&sh.k_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sh.s_full[i], 1);
+      mbar_init(&sh.s_free[i], kRows);
+    }
+    mbar_init(&sh.q_full, 8 * 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_queue) : "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh.tmem_base)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh.tmem_base;
+
+  if (warp < 8) {
+    // ===================================================================== softmax warps
+    const int quad = warp & 3, par = warp >> 2;           // TMEM lane quadrant; even / odd tiles
+    const int r = quad * 32 + lane;
+    const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
+    uint8_t* scratch = stage_buf + warp * 4096;           // this warp's 32 rows x 128 B
+
+    // ---- Q^ rows -> tensor memory, 64-column chunks transposed through the warp's scratch (see infonce_tc.cu)
+    pdl_wait();
+    {
+      constexpr int kQChunks = C / 64;
+      const __nv_bfloat16* qw = q_hat + (size_t)(split % kQhatReplicas) * ((size_t)gridDim.y * kRows * C) +
+                                (size_t)(row0 + quad * 32) * C;
+#pragma unroll 1
+      for (int ch = par; ch < kQChunks; ch += 2) {
+        uint4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          v[j] = __ldg(reinterpret_cast<const uint4*>(qw + (size_t)(4 * j + (lane >> 3)) * C + ch * 64) + (lane & 7));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int rr = 4 * j + (lane >> 3), pc = lane & 7;
+          *reinterpret_cast<uint4*>(scratch + rr * 128 + ((pc ^ (rr & 7)) << 4)) = v[j];
+        }
+        __syncwarp();
+        uint32_t w[32];
+#pragma unroll
+        for (int pc = 0; pc < 8; ++pc) {
+          const uint4 u = *reinterpret_cast<const uint4*>(scratch + lane * 128 + ((pc ^ (lane & 7)) << 4));
+          w[4 * pc + 0] = u.x; w[4 * pc + 1] = u.y; w[4 * pc + 2] = u.z; w[4 * pc + 3] = u.w;
+        }
+        __syncwarp();
+        tc_st32(tlane + kTmQ + ch * 32, w);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&sh.q_full);
+    }
+
+    float m_ref = 0.f, l_run = 0.f, av_raw = -INFINITY;
+    int ai = 0;
+    bool overflow = false;
+    for (int i = par; i < n_tiles; i += 2) {
+      const int b = par;
+      const uint32_t ts = tlane + kTmS + b * kTN;
+      mbar_wait(&sh.s_full[b], (i >> 1) & 1);
+      tc_fence_after();
+      uint32_t sv[kTN];
+      tc_ld32(ts, sv);
+      tc_ld32(ts + 32, sv + 32);
+      tc_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&sh.s_free[b]);
+      const long long col0 = k_begin + (long long)i * kTN;
+      if (col0 + kTN > k_end) {
+        const int valid = (int)(k_end - col0);
+#pragma unroll
+        for (int j = 0; j < kTN; ++j)
+          if (j >= valid) sv[j] = 0xff800000u;
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < kTN; ++j) mx = fmaxf(mx, __uint_as_float(sv[j]));
+      if (want_argmax && mx > av_raw) {
+        av_raw = mx;
+        int idx = 0;
+#pragma unroll
+        for (int j = kTN - 1; j >= 0; --j)
+          if (__uint_as_float(sv[j]) == mx) idx = j;
+        ai = (int)col0 + idx;
+      }
+      // one reference per (row, split): fixed by tile 0 (even-tile warp), read once by the odd-tile warp
+      if (i == 0) {
+        m_ref = mx * scale2 + kMargin;
+        sh.m_ref[r] = m_ref;
+        __threadfence_block();
+        if (n_tiles > 1) named_bar_arrive(1 + quad, 64);
+      } else if (i == 1) {
+        named_bar_sync(1 + quad, 64);
+        m_ref = sh.m_ref[r];
+      }
+      overflow |= (mx * scale2 - m_ref > kOverflow);
+
+      const float neg_m = -m_ref;
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t pw[kTN / 2];
+#pragma unroll
+      for (int j = 0; j < kTN / 2; ++j) {
+        const float p0 = ex2_ftz(fmaf(__uint_as_float(sv[2 * j]), scale2, neg_m));
+        const float p1 = ex2_ftz(fmaf(__uint_as_float(sv[2 * j + 1]), scale2, neg_m));
+        ls[j & 3] += p0 + p1;
+        const __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
+        pw[j] = *reinterpret_cast<const uint32_t*>(&pk);
+      }
+      l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      // P~ row r -> scratch (16-byte chunks XOR-swizzled), then the warp stores its 32 rows coalesced:
+      // 8 lanes cover the 128-byte segment of one row, 4 rows per instruction
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(scratch + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+            make_uint4(pw[4 * c], pw[4 * c + 1], pw[4 * c + 2], pw[4 * c + 3]);
+      __syncwarp();
+      __nv_bfloat16* prow = ptilde + (size_t)(row0 + quad * 32) * k_pad + col0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int rr = 4 * j + (lane >> 3), pc = lane & 7;
+        const uint4 u = *reinterpret_cast<const uint4*>(scratch + rr * 128 + ((pc ^ (rr & 7)) << 4));
+        *reinterpret_cast<uint4*>(prow + (size_t)rr * k_pad + pc * 8) = u;
+      }
+    }
+
+    // ---- split statistics: both warps used the same reference, so the sums just add
+    if (__any_sync(0xffffffffu, overflow) && lane == 0) atomicExch(overflow_flag, 1u);
+    if (par == 1) {
+      sh.xl[r] = l_run;
+      sh.xav[r] = av_raw;
+      sh.xai[r] = ai;
+    }
+    named_bar_sync(9 + quad, 64);
+    if (par == 0 && row0 + r < B) {
+      const float l_tot = l_run + sh.xl[r];
+      const float av1 = sh.xav[r];
+      const int ai1 = sh.xai[r];
+      if (av1 > av_raw || (av1 == av_raw && ai1 < ai)) { av_raw = av1; ai = ai1; }
+      const size_t o = (size_t)(row0 + r) * gridDim.x + split;
+      pm[o] = m_ref;
+      pl[o] = l_tot;
+      pav[o] = av_raw * scale2;
+      pai[o] = ai;
+    }
+    tc_fence_before();
+  } else if (warp == 8) {
+    // ===================================================================== TMA producer
+    for (int i = 0; i < n_tiles; ++i) {
+      const long long col0 = k_begin + (long long)i * kTN;
+      for (int c = 0; c < kChunks; ++c) {
+        const int it = i * kChunks + c, st = it % kStages;
+        mbar_wait(&sh.k_empty[st], ((it / kStages) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&sh.k_full[st], kChunkBytes);
+          tma_load_2d(ring + (size_t)st * kChunkBytes, &tmap_queue, &sh.k_full[st], (int)col0, c * kChunkRows);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================================================================== MMA issuer
+    mbar_wait(&sh.q_full, 0);
+    tc_fence_after();
+    for (int i = 0; i < n_tiles; ++i) {
+      if (i >= 2) mbar_wait(&sh.s_free[i & 1], ((i - 2) >> 1) & 1);
+      tc_fence_after();
+      const uint32_t d = tmem + kTmS + (i & 1) * kTN;
+      for (int c = 0; c < kChunks; ++c) {
+        const int it = i * kChunks + c, st = it % kStages;
+        mbar_wait(&sh.k_full[st], (it / kStages) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sbase = smem_u32(ring + (size_t)st * kChunkBytes);
+#pragma unroll
+          for (int s = 0; s < kChunkRows / 16; ++s) {
+            // B = chunk as [N=64 columns][K=16 rows of C], MN-major: 8-row groups 1024 B apart
+            const uint64_t bd = make_sw128_desc(sbase + s * 2048, kChunkBytes, 1024);
+            tc_mma_ts(d, tmem + kTmQ + c * (kChunkRows / 2) + s * 8, bd, kIdescS, (c > 0 || s > 0) ? 1u : 0u);
+          }
+          tc_commit(&sh.k_empty[st]);                       // this chunk stage may be refilled
+          if (c == kChunks - 1) tc_commit(&sh.s_full[i & 1]);
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  __syncthreads();
+  if (tid == 0) pdl_trigger();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+// ========================================================================================== PV pass
+struct PvShared {
+  uint64_t full[4];
+  uint64_t empty[4];
+  uint64_t o_done;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+    infonce_pv_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant__ CUtensorMap tmap_queue, int B, int C,
+                      long long K, long long cols_per_split, __nv_bfloat16* __restrict__ po) {
+  constexpr int kSlice = kChunkRows;                     // 256 output columns per CTA
+  constexpr int kPBytes = kRows * kTN * 2;               // 16 KB: P~ tile, K-major SWIZZLE_128B rows
+  constexpr int kStageBytes = kPBytes + kChunkBytes;     // + 32 KB queue slice tile
+  constexpr int kStages = 4;
+  constexpr int HC = kSlice / 2;
+  constexpr uint32_t kIdescO = make_idesc(128, kSlice, 0);
+  static_assert(kRows * (2 * kSlice + 16) <= kStages * kStageBytes, "epilogue staging must fit the ring");
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ PvShared sh;
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // slice fastest, then row block, then split: the CTAs resident together share their P~ tiles (C/256
+  // slices) and their queue tiles (all row blocks) through L2
+  const int slice = blockIdx.x, split = blockIdx.z;
+  const int row0 = blockIdx.y * kRows;
+  const long long k_begin = (long long)split * cols_per_split;
+  const long long k_end = (k_begin + cols_per_split < K) ? k_begin + cols_per_split : K;
+  const int n_tiles = (int)((k_end - k_begin + kTN - 1) / kTN);
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&sh.full[i], 1);
+      mbar_init(&sh.empty[i], 1);
+    }
+    mbar_init(&sh.o_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_p) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_queue) : "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh.tmem_base)), "r"(256)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh.tmem_base;
+  pdl_wait();   // P~ is written by the S pass
+
+  if (warp == 8) {
+    for (int i = 0; i < n_tiles; ++i) {
+      const int st = i % kStages;
+      mbar_wait(&sh.empty[st], ((i / kStages) & 1) ^ 1);
+      if (elect_one()) {
+        const long long col0 = k_begin + (long long)i * kTN;
+        uint8_t* base = ring + (size_t)st * kStageBytes;
+        mbar_expect_tx(&sh.full[st], kStageBytes);
+        tma_load_2d(base, &tmap_p, &sh.full[st], (int)col0, row0);
+        tma_load_2d(base + kPBytes, &tmap_queue, &sh.full[st], (int)col0, slice * kSlice);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 9) {
+    for (int i = 0; i < n_tiles; ++i) {
+      const int st = i % kStages;
+      mbar_wait(&sh.full[st], (i / kStages) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t pa = smem_u32(ring + (size_t)st * kStageBytes);
+        const uint32_t qb = pa + kPBytes;
+#pragma unroll
+        for (int s = 0; s < kTN / 16; ++s) {
+          // A = P~ tile [M=128 rows][K=16 columns], B = queue slice [N=256 rows of C][K=16 columns]; both K-major
+          const uint64_t ad = make_sw128_desc(pa + s * 32, 16, 1024);
+          const uint64_t bd = make_sw128_desc(qb + s * 32, 16, 1024);
+          tc_mma_ss(tmem, ad, bd, kIdescO, (i > 0 || s > 0) ? 1u : 0u);
+        }
+        tc_commit(&sh.empty[st]);
+        if (i == n_tiles - 1) tc_commit(&sh.o_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // epilogue warps: O rows -> bf16 -> own staging segment -> one bulk copy per row half (as infonce_tc.cu)
+    const int quad = warp & 3, par = warp >> 2;
+    const int r = quad * 32 + lane;
+    const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
+    mbar_wait(&sh.o_done, 0);
+    tc_fence_after();
+    uint8_t* stage = ring + (size_t)r * (2 * kSlice + 16) + par * HC * 2;
+#pragma unroll 1
+    for (int ch = 0; ch < HC / 32; ++ch) {
+      uint32_t o[32];
+      tc_ld32(tlane + par * HC + ch * 32, o);
+      tc_wait_ld();
+      uint32_t h[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const __nv_bfloat162 pk = __floats2bfloat162_rn(__uint_as_float(o[2 * j]), __uint_as_float(o[2 * j + 1]));
+        h[j] = *reinterpret_cast<const uint32_t*>(&pk);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(stage + ch * 64 + 16 * j) = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+    }
+    if (row0 + r < B) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      bulk_store_row(po + ((size_t)split * B + row0 + r) * C + slice * kSlice + par * HC, stage, HC * 2);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (tid == 0) pdl_trigger();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
+  }
+}
+
+template <int C>
+int launch_s(const CUtensorMap& tq, const __nv_bfloat16* q_hat, int B, long long K, long long k_pad, float scale2,
+             const InfoNcePlan& p, InfoNcePartials out, __nv_bfloat16* ptilde, unsigned int* flag, int want_argmax,
+             cudaStream_t s) {
+  const size_t smem = 8 * 4096 + 5 * (size_t)kChunkBytes + 1024;
+  auto kern = infonce_s_kernel<C>;
+  RMCL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RMCL_CUDA_OK(launch_pdl(kern, dim3(p.splits, p.row_blocks), dim3(kThreads), smem, s, tq, q_hat, B, K, k_pad, scale2,
+                          p.cols_per_split, want_argmax, out.m, out.l, out.av, out.ai, ptilde, flag));
+  return RMCL_OK;
+}
+
+}  // namespace
+
+bool infonce_tc2_supports(int C) { return C == 512 || C == 768; }
+
+int infonce_tc2_launch(const __nv_bfloat16* q_hat, const void* queue, int B, int C, long long K, long long ldq, float scale2,
+                       const InfoNcePlan& p, InfoNcePartials out, __nv_bfloat16* ptilde, long long k_pad,
+                       unsigned int* overflow_flag, int want_argmax, cudaStream_t s) {
+  if (p.row_blocks > 65535 || p.splits > 65535) {
+    set_error("InfoNCE: too many rows (%d)", B);
+    return RMCL_E_UNSUPPORTED_DIM;
+  }
+  alignas(64) CUtensorMap tq, tp;
+  int rc = make_tmap_bf16(&tq, queue, (uint64_t)C, (uint64_t)K, (uint64_t)ldq, kChunkRows);
+  if (rc != RMCL_OK) return rc;
+  rc = make_tmap_bf16(&tp, ptilde, (uint64_t)p.b_pad, (uint64_t)k_pad, (uint64_t)k_pad, kRows);
+  if (rc != RMCL_OK) return rc;
+  if (C == 768)
+    rc = launch_s<768>(tq, q_hat, B, K, k_pad, scale2, p, out, ptilde, overflow_flag, want_argmax, s);
+  else if (C == 512)
+    rc = launch_s<512>(tq, q_hat, B, K, k_pad, scale2, p, out, ptilde, overflow_flag, want_argmax, s);
+  else {
+    set_error("two-pass tcgen05 InfoNCE supports C in {512, 768} (got %d)", C);
+    return RMCL_E_UNSUPPORTED_DIM;
+  }
+  if (rc != RMCL_OK) return rc;
+  const size_t smem = 4 * (size_t)(kRows * kTN * 2 + kChunkBytes) + 1024;
+  RMCL_CUDA_OK(cudaFuncSetAttribute(infonce_pv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RMCL_CUDA_OK(launch_pdl(infonce_pv_kernel, dim3(C / kChunkRows, p.row_blocks, p.splits), dim3(kThreads), smem, s, tp, tq, B,
+                          C, K, p.cols_per_split, reinterpret_cast<__nv_bfloat16*>(out.o)));
+  return RMCL_OK;
+}
+
+}  // namespace rmcl

@@ -552,6 +552,66 @@ def test_infonce_tcgen05_rescale_path_on_every_tile(ops, C, tn):
     assert rel_err(res["dq"], ref["dq"]) < 1e-2
 
 
+# ---- two-pass tcgen05 variant for wide projections (infonce_tc2.cu: C in {512, 768}, BASELINE cfg5's dim 768)
+TC2_SHAPES = [(128, 512, 1024), (256, 768, 4096), (130, 768, 1000), (8, 512, 520), (1, 768, 8), (300, 768, 8192 + 72),
+              (512, 768, 32768)]
+
+
+@pytest.mark.parametrize("B,C,K", TC2_SHAPES)
+@pytest.mark.parametrize("normalized_queue", [True, False])
+def test_infonce_tcgen05_two_pass_vs_oracle(ops, B, C, K, normalized_queue):
+    q, k, queue = _infonce_inputs(B, C, K, seed=B + C + K, queue_dtype=torch.bfloat16, normalized_queue=normalized_queue)
+    ref = _bf16_oracle(q, k, queue, 0.07)
+    res = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.to(DEV), 0.07, path="tcgen05")
+    torch.cuda.synchronize()
+    assert rel_err(res["lse"], ref["lse"]) < 1e-4
+    assert rel_err(res["loss"], ref["loss"]) < 1e-4
+    assert (res["loss_per_row"].double().cpu() - ref["loss_per_row"]).abs().max() < BF16_RTOL * ref["logits"].abs().max()
+    assert rel_err(res["dq"], ref["dq"]) < 1e-2
+    top2 = ref["logits"].topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-3
+    assert torch.equal(res["argmax"].cpu()[clear], ref["argmax"][clear])
+
+
+@pytest.mark.parametrize("C", [512, 768])
+def test_infonce_tcgen05_two_pass_matches_simt_path(ops, C):
+    q, k, queue = _infonce_inputs(96, C, 3000 // 8 * 8, seed=C, queue_dtype=torch.bfloat16)
+    a = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.to(DEV), 0.07, path="simt")
+    b = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.to(DEV), 0.07, path="auto")     # auto -> two-pass tcgen05
+    assert rel_err(b["lse"], a["lse"]) < 1e-5
+    assert rel_err(b["loss"], a["loss"]) < 1e-5
+    assert rel_err(b["dq"], a["dq"]) < 1e-2
+    assert rel_err(b["dk"], a["dk"]) < 1e-2
+
+
+def test_infonce_tcgen05_two_pass_growing_maximum_and_overflow_flag(ops):
+    """The two-pass variant fixes one reference per (row, split) after its first tile (+2^24 margin).
+    Growth of the row maximum by < 2^100 inside a split stays exact; beyond that the S pass raises a flag
+    and every output is NaN instead of silently wrong."""
+    B, C, K = 1024, 512, 4096                          # 8 row blocks -> 18 splits of 4 tiles
+    g = torch.Generator().manual_seed(11)
+    q = torch.randn(B, C, generator=g)
+    k = torch.nn.functional.normalize(torch.randn(B, C, generator=g), dim=1)
+    base = torch.nn.functional.normalize(torch.randn(C, K, generator=g), dim=0)
+    qbar = torch.nn.functional.normalize(q, dim=1).mean(0)
+    ramp = torch.linspace(0.05, 3.0, K)[None, :]
+    queue = ((base + 0.5 * qbar[:, None]) * ramp).bfloat16()
+    ref = _bf16_oracle(q, k, queue, 0.07)
+    res = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.to(DEV), 0.07, path="tcgen05")
+    assert rel_err(res["lse"], ref["lse"]) < 1e-4
+    assert rel_err(res["dq"], ref["dq"]) < 1e-2
+    # logits jump by ~8/0.07*log2(e) = 165 log2 units from one tile to the next: beyond any fixed reference
+    q1 = torch.zeros(B, C)
+    q1[torch.arange(B), torch.arange(B) % C] = 1.0
+    step = torch.arange(K) // 64
+    queue1 = (8.0 * (step % 4 + 1)[None, :] + 0.25 * torch.randn(C, K, generator=g)).bfloat16()
+    bad = ops.infonce_fwd_bwd(q1.to(DEV), k.to(DEV), queue1.to(DEV), 0.07, path="tcgen05")
+    assert torch.isnan(bad["loss"]).all() and torch.isnan(bad["dq"]).all()
+    # ... and the next call on the same workspace is clean again (the flag is re-armed by the prep kernel)
+    res2 = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.to(DEV), 0.07, path="tcgen05")
+    assert torch.equal(res2["lse"], res["lse"])
+
+
 def test_infonce_tcgen05_strided_queue_and_auto_dispatch(ops):
     B, C, K = 64, 128, 2048
     q, k, queue = _infonce_inputs(B, C, K + 64, seed=3, queue_dtype=torch.bfloat16)
