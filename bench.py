@@ -428,6 +428,25 @@ def run_cuda(args):
                             "frac": nbytes / t / 1e9 / pk_peak["hbm"], "ms": t * 1e3, "traffic": traffic.get(tag),
                             "shape": list(shape)}
             del grad, delta
+    # ---- cfg5 per-GPU InfoNCE (B512 C768 K262144 bf16: the two-pass tcgen05 variant, prep + S pass + PV pass +
+    #      finalize timed as one call; queue 403 MB + P~ 268 MB > L2, so every call streams from HBM)
+    if world == 1 and not args.no_pgd and path in ("auto", "tcgen05"):
+        B5, C5, K5 = 512, 768, 262144
+        g5 = torch.Generator(device=dev).manual_seed(5)
+        q5 = torch.randn(B5, C5, device=dev, generator=g5).bfloat16()
+        k5 = torch.randn(B5, C5, device=dev, generator=g5).bfloat16()
+        queue5 = torch.nn.functional.normalize(torch.randn(C5, K5, device=dev, generator=g5), dim=0).bfloat16()
+        for _ in range(3):
+            ops.infonce_fwd_bwd(q5, k5, queue5, tau, normalize_k=True, path=path, want=("loss", "dq", "k_hat"))
+        ms5 = timed(lambda: ops.infonce_fwd_bwd(q5, k5, queue5, tau, normalize_k=True, path=path,
+                                                want=("loss", "dq", "k_hat")), 10) / 10
+        f5 = 4.0 * B5 * C5 * (K5 + 1)
+        kernels["infonce_cfg5_two_pass"] = {"bound": "tensor", "achieved": f5 / (ms5 * 1e-3) / 1e12, "peak": pk_peak["tf_sust"],
+                                            "unit": "TFLOP/s", "frac": f5 / (ms5 * 1e-3) / 1e12 / pk_peak["tf_sust"], "ms": ms5,
+                                            "traffic": traffic.get("infonce_cfg5_two_pass"), "shape": [B5, C5, K5],
+                                            "launches": ["infonce_prep_kernel", "infonce_s_kernel", "infonce_pv_kernel",
+                                                         "infonce_finalize_kernel"]}
+        del q5, k5, queue5
     for name in ("infonce_prep", "infonce_finalize"):
         kernels[name] = {"ms": kern_ms[name]}
     dominant = max(alg, key=lambda n: kern_ms[n])
@@ -466,7 +485,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--path", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-pgd", action="store_true", help="skip the cfg3 PGD-kernel roofline lines")
+    ap.add_argument("--no-pgd", action="store_true", help="skip the cfg3 PGD-kernel and cfg5 InfoNCE roofline lines")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

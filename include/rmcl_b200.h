@@ -141,6 +141,33 @@ int rmcl_infonce_fwd_bwd_diag(const void* q, rmcl_dtype q_dtype, const void* k, 
                               const float* sum_vec, const float* sum_unit, float cos_eps,
                               float* diag_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused Barlow-Twins cross-correlation loss, forward + backward.
+ * replaces: vilt/modules/objectives.py:480-486 (text view), 506-512 (image view), 533-539 (both) and the
+ *           attacker's inner loss attack/pgd_attack_vilt.py:219-224:
+ *               c = q.T @ k; c.div_(bs); all_reduce(c)
+ *               on_diag = diagonal(c).add_(-1).pow_(2).sum(); off_diag = off_diagonal(c).pow_(2).sum()
+ *               loss = on_diag + lambda * off_diag            (+ autograd backward to q)
+ *           The D x D matrix c (8192 x 8192 fp32 = 268 MB in the reference, all-reduced across ranks)
+ *           is never materialised: bf16 tcgen05 GEMMs with fp32 accumulation, tile by tile.
+ * q, k      [Bg, D] row-major (fp32 or bf16): the batch gathered over all ranks in rank order (Bg <= 256);
+ *           a single-GPU call passes its own batch, b0 = 0, Bl = Bg.
+ * b0, Bl    rows of q owned by the caller: dq is [Bl, D] and holds d(loss)/d(q[b0:b0+Bl]).
+ * inv_bs    1 / per_step_bs (objectives.py:481);  lambda = pl_module.adv_lr (objectives.py:486).
+ * w_on,w_off weights of the two sums in the gradient: dq = d(w_on*on_diag + w_off*off_diag)/dq * loss_scale.
+ *           The reference's loss is w_on = 1, w_off = lambda.
+ * outputs   on_diag, off_diag f32[1] (unweighted sums, as the reference logs them), loss f32[1] =
+ *           loss_scale * (on_diag + lambda * off_diag), dq f32[Bl, D], cdiag f32[D] = diagonal(c);
+ *           any may be NULL.  (cdiag lets a caller whose upstream gradients of the two sums differ
+ *           combine dq = g_on * 2/bs (cdiag-1) k + g_off * dq(w_on=0, w_off=1) without a second pass.)
+ * Gathered batches > 256 return RMCL_E_UNSUPPORTED_DIM.
+ */
+size_t rmcl_barlow_workspace_bytes(int Bg, int D);
+int rmcl_barlow_fwd_bwd(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_dtype k_dtype, int Bg, int D,
+                        int b0, int Bl, float inv_bs, float lambda, float w_on, float w_off,
+                        float loss_scale, float* on_diag, float* off_diag, float* loss, float* dq,
+                        float* cdiag, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Measurement aid (off by default): when enabled on the calling thread, rmcl_infonce_fwd_bwd
  * records CUDA events on its stream around its three launches (prep, split-K partial, finalize);
  * rmcl_profile_infonce_ms waits for the last of them and returns the three durations of the most

@@ -34,7 +34,7 @@ import torch.nn.functional as F
 __all__ = [
     "momentum_update", "l2_normalize", "info_nce", "info_nce_logits",
     "concat_all_gather", "dequeue_and_enqueue", "pgd_update", "queue_diagnostics",
-    "rmcl_kernel_step", "greedy_split_forward",
+    "rmcl_kernel_step", "greedy_split_forward", "barlow_twins",
 ]
 
 
@@ -225,3 +225,41 @@ def greedy_split_forward(ori_z, cand_z, all_num, k_modality, queue, temperature)
 def closed_form_single_negative(s_pos, s_neg, temperature):
     """K=1 known answer: loss = log(1 + exp((s_neg - s_pos)/T)).  SURVEY §8(c)."""
     return math.log1p(math.exp((s_neg - s_pos) / temperature))
+
+
+# ------------------------------------------------------------------ Barlow Twins
+def _off_diagonal(x):
+    """objectives.py:454-458: flattened view of the off-diagonal elements of a square matrix."""
+    n, m = x.shape
+    assert n == m
+    return x.flatten()[:-1].view(n - 1, n + 1)[:, 1:].flatten()
+
+
+def barlow_twins(q_per_rank, k_per_rank, per_step_bs, lam, grad_on=1.0, grad_offs=1.0):
+    """Barlow-Twins cross-correlation loss of one view, restated from
+    vilt/modules/objectives.py:480-486 (text view; 506-512 image view, 533-539 both) and, with one rank and
+    ``per_step_bs = B``, attack/pgd_attack_vilt.py:219-224:
+
+        c = q.T @ k;  c.div_(per_step_bs);  all_reduce(c)          # sum over ranks
+        on_diag  = diagonal(c).add_(-1).pow_(2).sum()
+        off_diag = off_diagonal(c).pow_(2).sum()
+        loss     = on_diag + lam * off_diag
+
+    ``q_per_rank`` / ``k_per_rank``: lists of [B_local, D] tensors (one rank: lists of length 1).  The all-reduce
+    is not autograd-aware: every rank's backward treats the summed ``c`` as if it were its own product, so
+    ``dq_r = k_r @ dC.T / per_step_bs`` with ``dC`` evaluated on the reduced matrix.
+    Returns on_diag, off_diag, loss, c and the per-rank gradients of
+    ``grad_on * on_diag + grad_offs * lam * off_diag`` with respect to each rank's q.
+    """
+    c = None
+    for q, k in zip(q_per_rank, k_per_rank):
+        cr = q.T @ k
+        cr = cr / per_step_bs
+        c = cr if c is None else c + cr
+    eye = torch.eye(c.shape[0], dtype=c.dtype)
+    on_diag = (torch.diagonal(c) - 1).pow(2).sum()
+    off_diag = _off_diagonal(c).pow(2).sum()
+    w = grad_offs * lam * (1 - eye) + grad_on * eye
+    dC = 2.0 * w * (c - eye)
+    dq = [(k @ dC.T) / per_step_bs for k in k_per_rank]
+    return {"on_diag": on_diag, "off_diag": off_diag, "loss": on_diag + lam * off_diag, "c": c, "dq": dq}

@@ -1,0 +1,549 @@
+// Fused Barlow-Twins cross-correlation loss, forward + backward, tcgen05/TMEM/TMA.
+//
+// Replaces, per view, vilt/modules/objectives.py:480-486 (image view 506-512, both 533-539) and the
+// attacker's inner loss attack/pgd_attack_vilt.py:219-224:
+//     c = q.T @ k;  c.div_(bs);  [all_reduce(c)]
+//     on_diag  = diagonal(c).add_(-1).pow_(2).sum()
+//     off_diag = off_diagonal(c).pow_(2).sum()
+//     loss     = on_diag + lambda * off_diag            (+ autograd backward through the D x D matrix)
+// which materialises the D x D = 8192 x 8192 fp32 matrix (268 MB) and passes over it ~10 times
+// (mm, div_, diagonal/off-diagonal gathers, pow, the same again backwards, mm for dq).
+//
+// Here c never exists.  With rows i of c as the M dimension the computation is the same two-GEMM
+// "flash" shape as the fused InfoNCE kernel (infonce_tc.cu), with the batch as the contraction:
+//     S = Qt_blk . k_tile          tcgen05.mma M128 x N=TN x K=BG   A = q^T rows (bf16) in TMEM, B = k tile (smem, MN-major)
+//     P = w (S/bs - I)             w = w_on on the diagonal, w_off elsewhere;  on/off sums of (S/bs - I)^2 in fp32
+//     O += P . k_tile^T            tcgen05.mma M128 x N=BG x K=TN   A = P (smem, bf16), B = the same k tile, K-major
+// and O[i, b] = sum_j P_ij k[b, j] is dq[b, i] up to the factor 2/bs.  One CTA = 128 rows of c x a
+// contiguous range of its columns (split over the column axis so that row blocks x splits ~ one CTA per SM).
+// There is no softmax, hence no running maximum and no rescaling: the protocol is the InfoNCE kernel's
+// without its decision handshake.
+//
+//   barlow_prep      q, k (fp32/bf16, [Bg, D]) -> q^T bf16 [D_pad, BG] and k bf16 [BG, D_ld], zero padded
+//   barlow_tc_kernel per-(row, split) on/off sums + bf16 partials O [splits][D][BG]
+//   barlow_finalize  dq[b, i] = 2/bs * scale * sum_splits O[i, b]  (transposed back), on/off/loss scalars
+//                    reduced in a fixed order by the last CTA (deterministic)
+// chained by programmatic dependent launch.  Multi-GPU (the reference all-reduces the 268 MB c): the
+// caller all-gathers q and k (2 x Bg x D, 4 MB at 2 GPUs) and every rank evaluates the full c from the
+// gathered batch, writing dq for its own rows [b0, b0+Bl) only.  Gathered batch Bg <= 256 for now.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace rmcl {
+
+namespace {
+
+using namespace tcx;
+
+constexpr int kThreads = 320;   // warps 0-7 elementwise + epilogue, warp 8 TMA producer / TMEM allocator, warp 9 MMA issuer
+constexpr int kRows = 128;
+constexpr int kSmemBudget = 208 * 1024;
+
+struct BtShared {
+  uint64_t k_full[8];
+  uint64_t k_empty[8];
+  uint64_t s_full[2];
+  uint64_t s_free[2];
+  uint64_t p_full[2];
+  uint64_t o_done[2];
+  uint64_t q_full;
+  uint32_t tmem_base;
+  float xon[kRows];
+  float xoff[kRows];
+};
+
+struct BtPlan {
+  int BG;               // gathered batch padded to 64 / 128 / 256: contraction of S, N of O
+  int TN;               // columns of c per tile
+  int row_blocks, splits;
+  long long cols_per_split;
+  int d_pad;            // D rounded up to 128 (rows of q^T)
+  long long d_ld;       // D rounded up to 8 (row stride of the bf16 k: TMA needs 16-byte strides)
+  int fin_blocks;
+  size_t off_qt, off_kb, off_on, off_off, off_po, off_blk, off_counter, total;
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int barlow_make_plan(int Bg, int D, BtPlan* p) {
+  const int sms = sm_count();
+  if (sms <= 0) return RMCL_E_CUDA;
+  if (Bg > 256) {
+    set_error("rmcl_barlow_fwd_bwd: gathered batch %d > 256 is not supported by the fused tcgen05 kernel yet", Bg);
+    return RMCL_E_UNSUPPORTED_DIM;
+  }
+  p->BG = Bg <= 64 ? 64 : (Bg <= 128 ? 128 : 256);
+  p->TN = p->BG == 256 ? 64 : 128;
+  p->row_blocks = (D + kRows - 1) / kRows;
+  p->d_pad = p->row_blocks * kRows;
+  p->d_ld = ((long long)D + 7) / 8 * 8;
+  const long long tiles = ((long long)D + p->TN - 1) / p->TN;
+  long long splits = sms / p->row_blocks;
+  if (splits < 1) splits = 1;
+  if (splits > tiles) splits = tiles;
+  const long long tps = (tiles + splits - 1) / splits;
+  p->cols_per_split = tps * p->TN;
+  p->splits = (int)(((long long)D + p->cols_per_split - 1) / p->cols_per_split);
+  p->fin_blocks = (D + 31) / 32;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  p->off_qt = take((size_t)p->d_pad * p->BG * 2);
+  p->off_kb = take((size_t)p->BG * p->d_ld * 2);
+  p->off_on = take((size_t)D * p->splits * 4);
+  p->off_off = take((size_t)D * p->splits * 4);
+  p->off_po = take((size_t)p->splits * D * p->BG * 2);
+  p->off_blk = take((size_t)p->fin_blocks * 2 * 4);
+  p->off_counter = take(256);
+  p->total = off;
+  return RMCL_OK;
+}
+
+// ------------------------------------------------------------------------------------------ prep
+// One CTA = 32 feature columns i x the whole (padded) batch: converts to bf16 and writes both layouts.
+template <typename TQ, typename TK>
+__global__ void __launch_bounds__(256) barlow_prep_kernel(const TQ* __restrict__ q, const TK* __restrict__ k, int Bg, int D,
+                                                          int BG, long long d_ld, __nv_bfloat16* __restrict__ qt,
+                                                          __nv_bfloat16* __restrict__ kb, unsigned int* __restrict__ counter) {
+  extern __shared__ __nv_bfloat16 tile[];   // [BG][33]
+  if (threadIdx.x == 0) pdl_trigger();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0u;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i0 = blockIdx.x * 32;
+  const int i = i0 + tx;
+  for (int b = ty; b < BG; b += 8) {
+    const bool ok = (b < Bg) && (i < D);
+    const float qv = ok ? to_f32(q[(size_t)b * D + i]) : 0.f;
+    const float kv = ok ? to_f32(k[(size_t)b * D + i]) : 0.f;
+    tile[b * 33 + tx] = __float2bfloat16_rn(qv);
+    if (i < d_ld) kb[(size_t)b * d_ld + i] = __float2bfloat16_rn(kv);
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)                      // q^T row i0 + r (rows up to d_pad exist: zero padding)
+    for (int b = tx; b < BG; b += 32) qt[(size_t)(i0 + r) * BG + b] = tile[b * 33 + r];
+}
+
+// ---------------------------------------------------------------------------------------- kernel
+template <int BG, int TN>
+__global__ void __launch_bounds__(kThreads, 1)
+    barlow_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __nv_bfloat16* __restrict__ qt, int D, float inv_bs,
+                     float w_on, float w_off, long long cols_per_split, float* __restrict__ pon, float* __restrict__ poff,
+                     __nv_bfloat16* __restrict__ po, float* __restrict__ cdiag) {
+  constexpr int kStageBytes = BG * TN * 2;
+  constexpr int kBoxBytes = BG * 128;           // one TMA box: BG rows x 64 bf16 columns
+  constexpr int kBoxes = TN / 64;
+  constexpr int kPBytes = kBoxes * 16384;       // one P tile: 128 rows x TN bf16 as 128-byte-row boxes
+  constexpr int kStages = ((kSmemBudget - 2 * kPBytes) / kStageBytes) < 8 ? ((kSmemBudget - 2 * kPBytes) / kStageBytes) : 8;
+  constexpr uint32_t kTmQ = 0, kTmO = BG / 2, kTmS = BG / 2 + BG;
+  constexpr int HC = BG / 2;                    // O columns per thread in the epilogue
+  static_assert(BG / 2 + BG + 2 * TN <= 512, "tensor memory budget");
+  static_assert(TN % 64 == 0 && BG % 64 == 0 && BG <= 256, "tile shape");
+  static_assert(kStages >= 4, "three tiles are live (S runs two ahead of O) plus one in flight");
+  static_assert(kRows * (2 * BG + 16) <= kStages * kStageBytes, "epilogue staging must fit the ring");
+  static_assert(2 * kPBytes >= 8 * 4096, "q^T transpose scratch lives in the P buffers");
+  constexpr uint32_t kIdescS = make_idesc(128, TN, 1);
+  constexpr uint32_t kIdescO = make_idesc(128, BG, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ BtShared sh;
+  uint8_t* pbuf = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ring = pbuf + 2 * kPBytes;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x;
+  const int row0 = blockIdx.y * kRows;
+  const long long k_begin = (long long)split * cols_per_split;
+  const long long k_end = (k_begin + cols_per_split < D) ? k_begin + cols_per_split : D;
+  const int n_tiles = (int)((k_end - k_begin + TN - 1) / TN);
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&sh.k_full[i], 1);
+      mbar_init(&sh.k_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sh.s_full[i], 1);
+      mbar_init(&sh.s_free[i], kRows);
+      mbar_init(&sh.p_full[i], kRows);
+      mbar_init(&sh.o_done[i], 1);
+    }
+    mbar_init(&sh.q_full, 8 * 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_k) : "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh.tmem_base)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh.tmem_base;
+  pdl_wait();   // both operands (q^T and the bf16 k behind the tensor map) are written by the prep kernel
+
+  if (warp < 8) {
+    // ============================================================ elementwise + epilogue warps
+    // Two warps per row quadrant alternate tiles (warp w: even, w+4: odd), as in infonce_tc.cu.
+    const int quad = warp & 3, par = warp >> 2;
+    const int r = quad * 32 + lane;                       // row inside the block == TMEM lane
+    const int row = row0 + r;                             // row of c == feature index i
+    const uint32_t tlane = tmem + ((uint32_t)(quad * 32) << 16);
+
+    // ---- q^T rows -> tensor memory (bf16 pairs): coalesced loads, transposed through 4 KB of the P buffers
+    {
+      constexpr int kChunks = BG / 64;
+      uint8_t* scratch = pbuf + warp * 4096;
+      const __nv_bfloat16* qw = qt + (size_t)(row0 + quad * 32) * BG;
+#pragma unroll 1
+      for (int ch = par; ch < kChunks; ch += 2) {
+        uint4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          v[j] = __ldg(reinterpret_cast<const uint4*>(qw + (size_t)(4 * j + (lane >> 3)) * BG + ch * 64) + (lane & 7));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int rr = 4 * j + (lane >> 3), pc = lane & 7;
+          *reinterpret_cast<uint4*>(scratch + rr * 128 + ((pc ^ (rr & 7)) << 4)) = v[j];
+        }
+        __syncwarp();
+        uint32_t w[32];
+#pragma unroll
+        for (int pc = 0; pc < 8; ++pc) {
+          const uint4 u = *reinterpret_cast<const uint4*>(scratch + lane * 128 + ((pc ^ (lane & 7)) << 4));
+          w[4 * pc + 0] = u.x; w[4 * pc + 1] = u.y; w[4 * pc + 2] = u.z; w[4 * pc + 3] = u.w;
+        }
+        __syncwarp();
+        tc_st32(tlane + kTmQ + ch * 32, w);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&sh.q_full);
+    }
+
+    float on = 0.f, off = 0.f;
+    for (int i = par; i < n_tiles; i += 2) {
+      const int b = par;
+      const uint32_t ph = (i >> 1) & 1;
+      const uint32_t ts = tlane + kTmS + b * TN;
+      mbar_wait(&sh.s_full[b], ph);
+      tc_fence_after();
+      uint32_t sv[TN];
+#pragma unroll
+      for (int ch = 0; ch < TN / 32; ++ch) tc_ld32(ts + ch * 32, sv + ch * 32);
+      tc_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&sh.s_free[b]);                         // S[b] is in registers
+
+      // Columns past D were zero-filled by TMA: c = 0 there, no contribution to either sum or to P.
+      const long long col0 = k_begin + (long long)i * TN;
+      const int dj = (int)((long long)row - col0);        // position of this row's diagonal element in the tile
+      const long long wrow0 = row0 + quad * 32;
+      const bool diag_tile = (col0 < wrow0 + 32) && (col0 + TN > wrow0);   // warp-uniform
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t pw[TN / 2];
+      if (!diag_tile) {
+#pragma unroll
+        for (int j = 0; j < TN / 2; ++j) {
+          const float c0 = __uint_as_float(sv[2 * j]) * inv_bs, c1 = __uint_as_float(sv[2 * j + 1]) * inv_bs;
+          acc[j & 3] = fmaf(c0, c0, fmaf(c1, c1, acc[j & 3]));
+          const __nv_bfloat162 pk = __floats2bfloat162_rn(w_off * c0, w_off * c1);
+          pw[j] = *reinterpret_cast<const uint32_t*>(&pk);
+        }
+      } else {
+        const int dsel = (row < D) ? dj : -1;             // padding rows have no diagonal
+#pragma unroll
+        for (int j = 0; j < TN / 2; ++j) {
+          float c0 = __uint_as_float(sv[2 * j]) * inv_bs, c1 = __uint_as_float(sv[2 * j + 1]) * inv_bs;
+          float p0 = w_off * c0, p1 = w_off * c1;
+          if (2 * j == dsel) {
+            const float t = c0 - 1.f;
+            if (cdiag) cdiag[row] = c0;
+            on = t * t;
+            p0 = w_on * t;
+            c0 = 0.f;
+          }
+          if (2 * j + 1 == dsel) {
+            const float t = c1 - 1.f;
+            if (cdiag) cdiag[row] = c1;
+            on = t * t;
+            p1 = w_on * t;
+            c1 = 0.f;
+          }
+          acc[j & 3] = fmaf(c0, c0, fmaf(c1, c1, acc[j & 3]));
+          const __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
+          pw[j] = *reinterpret_cast<const uint32_t*>(&pk);
+        }
+      }
+      off += (acc[0] + acc[1]) + (acc[2] + acc[3]);
+
+      // P buffer b was last read by the O GEMM of tile i-2: only that GEMM's own commit may be trusted
+      if (i >= 2) mbar_wait(&sh.o_done[b], ((i - 2) >> 1) & 1);
+      uint8_t* prow = pbuf + b * kPBytes + r * 128;       // K-major SWIZZLE_128B: 16-byte chunk c lands at c ^ (r & 7)
+#pragma unroll
+      for (int c = 0; c < TN / 8; ++c) {
+        uint8_t* dst = prow + (c >> 3) * 16384 + (((c & 7) ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pw[4 * c], pw[4 * c + 1], pw[4 * c + 2], pw[4 * c + 3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&sh.p_full[b]);
+    }
+
+    // ---- epilogue: row sums, then O
+    if (tid == 0) pdl_trigger();
+    if (n_tiles >= 2) mbar_wait(&sh.o_done[(n_tiles - 2) & 1], ((n_tiles - 2) >> 1) & 1);
+    mbar_wait(&sh.o_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
+    tc_fence_after();
+    const bool row_ok = row < D;
+    if (par == 1) {
+      sh.xon[r] = on;
+      sh.xoff[r] = off;
+    }
+    named_bar_sync(9 + quad, 64);
+    if (par == 0 && row_ok) {
+      const size_t o = (size_t)row * gridDim.x + split;
+      pon[o] = on + sh.xon[r];
+      poff[o] = off + sh.xoff[r];
+    }
+    uint8_t* stage = ring + (size_t)r * (2 * BG + 16) + par * HC * 2;   // every TMA write has been consumed
+#pragma unroll 1
+    for (int ch = 0; ch < HC / 32; ++ch) {
+      uint32_t o[32];
+      tc_ld32(tlane + kTmO + par * HC + ch * 32, o);
+      tc_wait_ld();
+      uint32_t h[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const __nv_bfloat162 pk = __floats2bfloat162_rn(__uint_as_float(o[2 * j]), __uint_as_float(o[2 * j + 1]));
+        h[j] = *reinterpret_cast<const uint32_t*>(&pk);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(stage + ch * 64 + 16 * j) = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+    }
+    if (row_ok) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      bulk_store_row(po + ((size_t)split * D + row) * BG + par * HC, stage, HC * 2);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    tc_fence_before();
+  } else if (warp == 8) {
+    // ========================================================================= TMA producer
+    for (int i = 0; i < n_tiles; ++i) {
+      const int st = i % kStages;
+      mbar_wait(&sh.k_empty[st], ((i / kStages) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&sh.k_full[st], kStageBytes);
+        const long long col0 = k_begin + (long long)i * TN;
+#pragma unroll
+        for (int bx = 0; bx < kBoxes; ++bx)
+          tma_load_2d(ring + (size_t)st * kStageBytes + (size_t)bx * kBoxBytes, &tmap_k, &sh.k_full[st], (int)(col0 + bx * 64), 0);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =========================================================================== MMA issuer
+    // iteration j issues the S GEMM of tile j and the O GEMM of tile j-2 (S runs two tiles ahead)
+    mbar_wait(&sh.q_full, 0);
+    tc_fence_after();
+    for (int j = 0; j < n_tiles + 2; ++j) {
+      if (j < n_tiles) {
+        const int i = j, st = i % kStages;
+        if (i >= 2) mbar_wait(&sh.s_free[i & 1], ((i - 2) >> 1) & 1);
+        mbar_wait(&sh.k_full[st], (i / kStages) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sbase = smem_u32(ring + (size_t)st * kStageBytes);
+          const uint32_t dd = tmem + kTmS + (i & 1) * TN;
+#pragma unroll
+          for (int s = 0; s < BG / 16; ++s) {
+            // B = tile as [N=TN columns][K=16 batch rows], MN-major: 8-row groups 1024 B apart, 64-column boxes kBoxBytes apart
+            const uint64_t bd = make_sw128_desc(sbase + s * 2048, kBoxBytes, 1024);
+            tc_mma_ts(dd, tmem + kTmQ + s * 8, bd, kIdescS, s > 0);
+          }
+          tc_commit(&sh.s_full[i & 1]);
+        }
+        __syncwarp();
+      }
+      if (j >= 2) {
+        const int i = j - 2, st = i % kStages;
+        mbar_wait(&sh.p_full[i & 1], (i >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sbase = smem_u32(ring + (size_t)st * kStageBytes);
+          const uint32_t pa = smem_u32(pbuf + (i & 1) * kPBytes);
+#pragma unroll
+          for (int s = 0; s < TN / 16; ++s) {
+            // A = P as [M=128 rows][K=16 columns], B = tile as [N=BG batch rows][K=16 columns]; both K-major
+            const uint64_t ad = make_sw128_desc(pa + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024);
+            const uint64_t bd = make_sw128_desc(sbase + (s >> 2) * kBoxBytes + (s & 3) * 32, 16, 1024);
+            tc_mma_ss(tmem + kTmO, ad, bd, kIdescO, (i > 0 || s > 0) ? 1u : 0u);
+          }
+          tc_commit(&sh.k_empty[st]);
+          tc_commit(&sh.o_done[i & 1]);
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
+
+// -------------------------------------------------------------------------------------- finalize
+// One CTA = 32 rows of c: sums the split partials, transposes them back to dq[b, i] for the caller's own
+// batch rows, and reduces the on/off sums; the last CTA adds the per-CTA sums in index order.
+__global__ void __launch_bounds__(256) barlow_finalize_kernel(int D, int BG, int splits, int b0, int Bl, float grad_scale,
+                                                              float lambda, float loss_scale,
+                                                              const __nv_bfloat16* __restrict__ po,
+                                                              const float* __restrict__ pon, const float* __restrict__ poff,
+                                                              float* __restrict__ blk, unsigned int* __restrict__ counter,
+                                                              float* __restrict__ dq, float* __restrict__ on_out,
+                                                              float* __restrict__ off_out, float* __restrict__ loss_out) {
+  extern __shared__ float ftile[];   // [32][BG + 1]
+  __shared__ float red[2][8];
+  __shared__ bool s_last;
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int i0 = blockIdx.x * 32;
+  const int nb = gridDim.x;
+  pdl_wait();
+  if (dq != nullptr) {
+    for (int r = ty; r < 32; r += 8) {
+      const int i = i0 + r;
+      for (int b = tx; b < BG; b += 32) {
+        float a = 0.f;
+        if (i < D)
+          for (int s = 0; s < splits; ++s) a += __bfloat162float(po[((size_t)s * D + i) * BG + b]);
+        ftile[r * (BG + 1) + b] = a;
+      }
+    }
+    __syncthreads();
+    if (i0 + tx < D)
+      for (int b = ty; b < Bl; b += 8) dq[(size_t)b * D + i0 + tx] = grad_scale * ftile[tx * (BG + 1) + b0 + b];
+  }
+  // on / off sums of this CTA's rows: thread t < 32 owns row i0 + t
+  float on = 0.f, off = 0.f;
+  if (tid < 32 && i0 + tid < D)
+    for (int s = 0; s < splits; ++s) {
+      on += pon[(size_t)(i0 + tid) * splits + s];
+      off += poff[(size_t)(i0 + tid) * splits + s];
+    }
+  if (tid < 32) {
+    on = warp_sum(on);
+    off = warp_sum(off);
+    if (tid == 0) {
+      blk[2 * blockIdx.x] = on;
+      blk[2 * blockIdx.x + 1] = off;
+      __threadfence();
+      s_last = (atomicAdd(counter, 1u) == (unsigned)nb - 1u);
+    }
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float a = 0.f, c = 0.f;
+  for (int j = tid; j < nb; j += 256) {
+    a += __ldcg(blk + 2 * j);
+    c += __ldcg(blk + 2 * j + 1);
+  }
+  a = warp_sum(a);
+  c = warp_sum(c);
+  if (tx == 0) {
+    red[0][ty] = a;
+    red[1][ty] = c;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float ta = 0.f, tc = 0.f;
+    for (int w = 0; w < 8; ++w) {
+      ta += red[0][w];
+      tc += red[1][w];
+    }
+    if (on_out) *on_out = ta;
+    if (off_out) *off_out = tc;
+    if (loss_out) *loss_out = loss_scale * (ta + lambda * tc);
+  }
+}
+
+template <int BG, int TN>
+int launch_bt(const CUtensorMap& tmap, const BtPlan& p, char* ws, int D, float inv_bs, float w_on, float w_off, float* cdiag,
+              cudaStream_t s) {
+  constexpr int kStageBytes = BG * TN * 2;
+  constexpr int kPBytes = (TN / 64) * 16384;
+  constexpr int kStages = ((kSmemBudget - 2 * kPBytes) / kStageBytes) < 8 ? ((kSmemBudget - 2 * kPBytes) / kStageBytes) : 8;
+  const size_t smem = (size_t)kStages * kStageBytes + 2 * kPBytes + 1024;
+  auto kern = barlow_tc_kernel<BG, TN>;
+  RMCL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RMCL_CUDA_OK(launch_pdl(kern, dim3(p.splits, p.row_blocks), dim3(kThreads), smem, s, tmap,
+                          (const __nv_bfloat16*)(ws + p.off_qt), D, inv_bs, w_on, w_off, p.cols_per_split,
+                          (float*)(ws + p.off_on), (float*)(ws + p.off_off), (__nv_bfloat16*)(ws + p.off_po), cdiag));
+  return RMCL_OK;
+}
+
+template <typename TQ, typename TK>
+int launch_prep(const void* q, const void* k, int Bg, int D, const BtPlan& p, char* ws, cudaStream_t s) {
+  const size_t smem = (size_t)p.BG * 33 * sizeof(__nv_bfloat16);
+  barlow_prep_kernel<TQ, TK><<<p.d_pad / 32, 256, smem, s>>>((const TQ*)q, (const TK*)k, Bg, D, p.BG, p.d_ld,
+                                                           (__nv_bfloat16*)(ws + p.off_qt), (__nv_bfloat16*)(ws + p.off_kb),
+                                                           (unsigned int*)(ws + p.off_counter));
+  RMCL_LAUNCH_OK("barlow_prep_kernel");
+  return RMCL_OK;
+}
+
+}  // namespace
+
+}  // namespace rmcl
+
+using namespace rmcl;
+
+extern "C" size_t rmcl_barlow_workspace_bytes(int Bg, int D) {
+  if (Bg <= 0 || D <= 0) return 0;
+  BtPlan p;
+  if (barlow_make_plan(Bg, D, &p) != RMCL_OK) return 0;
+  return p.total;
+}
+
+extern "C" int rmcl_barlow_fwd_bwd(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_dtype k_dtype, int Bg, int D, int b0,
+                                   int Bl, float inv_bs, float lambda, float w_on, float w_off, float loss_scale,
+                                   float* on_diag, float* off_diag, float* loss, float* dq, float* cdiag, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  RMCL_CHECK_ARG(q && k && workspace, "rmcl_barlow_fwd_bwd: null pointer");
+  RMCL_CHECK_ARG(Bg > 0 && D > 0 && b0 >= 0 && Bl > 0 && b0 + Bl <= Bg, "rmcl_barlow_fwd_bwd: bad sizes Bg=%d D=%d b0=%d Bl=%d", Bg,
+                 D, b0, Bl);
+  RMCL_CHECK_ARG(dtype_ok(q_dtype) && dtype_ok(k_dtype), "rmcl_barlow_fwd_bwd: bad dtype");
+  RMCL_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "rmcl_barlow_fwd_bwd: workspace must be 256B aligned");
+  BtPlan p;
+  int rc = barlow_make_plan(Bg, D, &p);
+  if (rc != RMCL_OK) return rc;
+  if (workspace_bytes < p.total) {
+    set_error("rmcl_barlow_fwd_bwd: workspace %zu < required %zu", workspace_bytes, p.total);
+    return RMCL_E_WORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  using bf16 = __nv_bfloat16;
+  if (q_dtype == RMCL_F32 && k_dtype == RMCL_F32) rc = launch_prep<float, float>(q, k, Bg, D, p, ws, s);
+  else if (q_dtype == RMCL_F32) rc = launch_prep<float, bf16>(q, k, Bg, D, p, ws, s);
+  else if (k_dtype == RMCL_F32) rc = launch_prep<bf16, float>(q, k, Bg, D, p, ws, s);
+  else rc = launch_prep<bf16, bf16>(q, k, Bg, D, p, ws, s);
+  if (rc != RMCL_OK) return rc;
+
+  alignas(64) CUtensorMap tmap;
+  rc = tcx::make_tmap_bf16(&tmap, ws + p.off_kb, (uint64_t)p.BG, (uint64_t)D, (uint64_t)p.d_ld, (uint32_t)p.BG);
+  if (rc != RMCL_OK) return rc;
+  if (p.BG == 256) rc = launch_bt<256, 64>(tmap, p, ws, D, inv_bs, w_on, w_off, cdiag, s);
+  else if (p.BG == 128) rc = launch_bt<128, 128>(tmap, p, ws, D, inv_bs, w_on, w_off, cdiag, s);
+  else rc = launch_bt<64, 128>(tmap, p, ws, D, inv_bs, w_on, w_off, cdiag, s);
+  if (rc != RMCL_OK) return rc;
+
+  const size_t fin_smem = (size_t)32 * (p.BG + 1) * sizeof(float);
+  RMCL_CUDA_OK(launch_pdl(barlow_finalize_kernel, dim3(p.fin_blocks), dim3(256), fin_smem, s, D, p.BG, p.splits, b0, Bl,
+                          2.f * inv_bs * loss_scale, lambda, loss_scale, (const bf16*)(ws + p.off_po),
+                          (const float*)(ws + p.off_on), (const float*)(ws + p.off_off), (float*)(ws + p.off_blk),
+                          (unsigned int*)(ws + p.off_counter), dq, on_diag, off_diag, loss));
+  return RMCL_OK;
+}

@@ -30,3 +30,18 @@ def gathered_batch_matches(per_step_bs, gathered_rows):
     """The reference silently skips the enqueue when the gathered batch differs from
     ``per_step_bs`` (objectives.py:242-243), e.g. on the last, short batch of an epoch."""
     return per_step_bs is None or int(per_step_bs) == int(gathered_rows)
+
+
+class Gather:
+    """Callable all-gather with the caller's rank attached: what ``ops.barlow_twins_loss`` needs to replace the
+    reference's all-reduce of the D x D cross-correlation (objectives.py:482) by an all-gather of the [B, D]
+    projections.  ``Gather()`` is a no-op (rank 0) outside an initialised process group."""
+
+    def __init__(self, group=None):
+        self.group = group
+        on = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if on else 0
+        self.world = dist.get_world_size(group) if on else 1
+
+    def __call__(self, tensor):
+        return concat_all_gather(tensor, self.group)

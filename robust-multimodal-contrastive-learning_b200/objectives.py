@@ -193,3 +193,76 @@ def compute_geometric(pl_module, batch, loss_name, k_modality=None):
     pl_module.log(f"{loss_name}_attack/{phase}/num_changes", attack_words["num_changes"])
     pl_module.log(f"{loss_name}_attack/{phase}/change_rate", attack_words["change_rate"])
     return batch
+
+
+# ------------------------------------------------------------------------------- Barlow Twins
+def _barlow_view(pl_module, batch, k, suffix, ret, gather):
+    """One attacked/augmented view of objectives.py:476-498 / 502-523 / 529-551: forward, the fused
+    cross-correlation loss (c is never materialised, the all-reduce of c becomes an all-gather of the two
+    [B, D] projections) and the three positive-pair diagnostics."""
+    infer = pl_module.infer(batch, mask_text=False, mask_image=False)
+    q = pl_module.barlowtwins_head(infer["cls_feats"])
+    on_diag, off_scaled = ops.barlow_twins_loss(q, k, 1.0 / float(pl_module.per_step_bs), float(pl_module.adv_lr), gather)
+    ret[f"barlowtwins_loss_invariance_{suffix}"] = on_diag
+    ret[f"barlowtwins_loss_redundancy_{suffix}"] = off_scaled
+    tag = {"text": "txt"}.get(suffix, suffix)
+    ret[f"pos_dist_attacked_{tag}"] = torch.linalg.norm(q - k, dim=1).mean()
+    ret[f"pos_cosine_attacked_{tag}"] = pl_module.cosine(q, k).mean()
+    ret[f"pos_dot_attacked_{tag}"] = torch.sum(q * k, dim=1).mean()
+    return on_diag + off_scaled
+
+
+def compute_barlowtwins_contrastive(pl_module, batch):
+    """Drop-in for vilt/modules/objectives.py:449-602: same arguments, return keys (``barlowtwins_loss`` plus the
+    per-view ``barlowtwins_loss_invariance_*`` / ``barlowtwins_loss_redundancy_*`` — all three contain "loss"
+    and are summed by training_step, vilt_module.py:475, exactly as in the reference — and ``pos_*_attacked_*``)
+    and log names.  Per view the reference builds the 8192 x 8192 matrix ``c = q.T @ k / bs``, all-reduces it
+    and differentiates through it; here one fused tcgen05 pass (ops.barlow_twins_loss) emits both sums and dq."""
+    ret = {}
+    loss, loss_num = 0, 0
+    gather = rdist.Gather()
+
+    with torch.no_grad():
+        infer = pl_module.infer(batch, mask_text=False, mask_image=False)
+        k = pl_module.barlowtwins_head(infer["cls_feats"])
+
+    attacked_words = None
+    if pl_module.text_view:
+        if pl_module.augmentation:
+            augmented_batch = pl_module.text_augmentation_fn(pl_module, deepcopy(batch))
+        else:
+            augmented_batch = compute_geometric(pl_module, deepcopy(batch), "barlowtwins", k_modality=k)
+            attacked_words = {n: deepcopy(augmented_batch[n]) for n in ("text", "text_ids", "text_masks")}
+        loss = loss + _barlow_view(pl_module, augmented_batch, k, "text", ret, gather)
+        loss_num += 1
+
+    if pl_module.image_view:
+        if pl_module.augmentation:
+            augmented_batch = pl_module.image_augmentation_fn(pl_module, deepcopy(batch))
+        else:
+            augmented_batch = compute_pgd(pl_module, deepcopy(batch), "barlowtwins", k_modality=k)
+        loss = loss + _barlow_view(pl_module, augmented_batch, k, "img", ret, gather)
+        loss_num += 1
+
+    if pl_module.image_view and pl_module.text_view and not pl_module.augmentation:
+        for n in ("text", "text_ids", "text_masks"):
+            augmented_batch[n] = attacked_words[n]
+        loss = loss + _barlow_view(pl_module, augmented_batch, k, "both", ret, gather)
+        loss_num += 1
+
+    ret["barlowtwins_loss"] = loss / loss_num
+
+    phase = "train" if pl_module.training else "val"
+    metric = getattr(pl_module, f"{phase}_barlowtwins_loss")(ret["barlowtwins_loss"])
+    pl_module.log(f"barlowtwins/{phase}/loss", metric)
+    for view, tag, on in (("img", "img", pl_module.image_view), ("text", "txt", pl_module.text_view),
+                          ("both", "both", pl_module.image_view and pl_module.text_view and not pl_module.augmentation)):
+        if not on:
+            continue
+        pl_module.log(f"barlowtwins_dist_{phase}_L2/Pos_attacked_{tag}", ret[f"pos_dist_attacked_{tag}"])
+        pl_module.log(f"barlowtwins_dist_{phase}_Cosine/Pos_attacked_{tag}", ret[f"pos_cosine_attacked_{tag}"])
+        pl_module.log(f"barlowtwins_dist_{phase}_Dot/Pos_attacked_{tag}", ret[f"pos_dot_attacked_{tag}"])
+        for part in ("invariance", "redundancy"):
+            m = getattr(pl_module, f"{phase}_barlowtwins_loss_{part}_{view}")(ret[f"barlowtwins_loss_{part}_{view}"])
+            pl_module.log(f"barlowtwins/{phase}/barlowtwins_loss_{part}_{view}", m)
+    return ret

@@ -224,6 +224,83 @@ def infonce_loss(q, k, queue, temperature, path="auto", normalize_k=False, diag=
     return (loss, argmax) if diag is None else (loss, argmax, dg)
 
 
+# -------------------------------------------------------------------------------- Barlow Twins
+_bt_ws_cache = {}
+
+
+def barlow_fwd_bwd(q, k, inv_bs, lam, *, b0=0, Bl=None, w_on=1.0, w_off=None, loss_scale=1.0,
+                   want=("on_diag", "off_diag", "loss", "dq", "cdiag")):
+    """Fused Barlow-Twins loss of ``q``, ``k`` [Bg, D] (the batch gathered over all ranks): the D x D
+    cross-correlation ``c = q.T @ k * inv_bs`` is evaluated tile by tile on the tensor cores and never stored.
+
+    Returns ``on_diag = sum_i (c_ii-1)^2``, ``off_diag = sum_{i!=j} c_ij^2`` (objectives.py:483-484),
+    ``loss = loss_scale*(on_diag + lam*off_diag)``, ``dq`` [Bl, D] = d(w_on*on_diag + w_off*off_diag)/dq[b0:b0+Bl]
+    * loss_scale (``w_off`` defaults to ``lam``) and ``cdiag`` = diagonal(c)."""
+    _need_cuda(q, k)
+    if q.dim() != 2 or q.shape != k.shape or not q.is_contiguous() or not k.is_contiguous():
+        raise ValueError("q and k must be contiguous [Bg, D] tensors of the same shape")
+    Bg, D = q.shape
+    Bl = Bg - b0 if Bl is None else Bl
+    w_off = lam if w_off is None else w_off
+    L = _lib.lib()
+    key = (Bg, D, q.device)
+    ws = _bt_ws_cache.get(key)
+    if ws is None:
+        nbytes = L.rmcl_barlow_workspace_bytes(Bg, D)
+        if nbytes == 0:
+            check(-3, "rmcl_barlow_workspace_bytes")
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=q.device)
+        _bt_ws_cache[key] = ws
+    off = (-ws.data_ptr()) % 256
+    f32 = dict(dtype=torch.float32, device=q.device)
+    out = {"on_diag": torch.empty((), **f32) if "on_diag" in want else None,
+           "off_diag": torch.empty((), **f32) if "off_diag" in want else None,
+           "loss": torch.empty((), **f32) if "loss" in want else None,
+           "dq": torch.empty(Bl, D, **f32) if "dq" in want else None,
+           "cdiag": torch.empty(D, **f32) if "cdiag" in want else None}
+    ptr = lambda t: None if t is None else _p(t)
+    rc = L.rmcl_barlow_fwd_bwd(_p(q), _dt(q), _p(k), _dt(k), Bg, D, int(b0), int(Bl), float(inv_bs), float(lam), float(w_on),
+                               float(w_off), float(loss_scale), ptr(out["on_diag"]), ptr(out["off_diag"]), ptr(out["loss"]),
+                               ptr(out["dq"]), ptr(out["cdiag"]), ws.data_ptr() + off, ws.numel() - off, _stream())
+    check(rc, "rmcl_barlow_fwd_bwd")
+    return out
+
+
+class BarlowTwins(torch.autograd.Function):
+    """(on_diag, lam * off_diag) of objectives.py:480-486 with autograd support for ``q``.
+
+    The reference all-reduces the D x D matrix between ranks (objectives.py:482); here the [B, D]
+    projections are all-gathered instead and every rank evaluates the full matrix from the gathered batch.
+    Both returned sums are differentiable: the backward combines the two gradient pieces (the diagonal one
+    is elementwise given diagonal(c)) with whatever upstream weights arrive, without a second pass or a sync.
+    ``k`` gets no gradient (``no_grad`` at objectives.py:461)."""
+
+    @staticmethod
+    def forward(ctx, q, k, inv_bs, lam, gather=None):
+        ql, kl = q.detach().contiguous(), k.detach().contiguous()
+        Bl = ql.shape[0]
+        b0 = 0
+        if gather is not None:
+            qa, ka, b0 = gather(ql), gather(kl), gather.rank * Bl
+        else:
+            qa, ka = ql, kl
+        res = barlow_fwd_bwd(qa, ka, inv_bs, lam, b0=b0, Bl=Bl, w_on=0.0, w_off=1.0, want=("on_diag", "off_diag", "dq", "cdiag"))
+        ctx.save_for_backward(res["dq"], res["cdiag"], kl)
+        ctx.inv_bs, ctx.lam, ctx.q_dtype = float(inv_bs), float(lam), q.dtype
+        return res["on_diag"], res["off_diag"] * lam
+
+    @staticmethod
+    def backward(ctx, g_on, g_offs):
+        dq_off, cdiag, kl = ctx.saved_tensors
+        dq_on = (2.0 * ctx.inv_bs) * (cdiag - 1.0)[None, :] * kl.float()
+        return (g_on * dq_on + (g_offs * ctx.lam) * dq_off).to(ctx.q_dtype), None, None, None, None
+
+
+def barlow_twins_loss(q, k, inv_bs, lam, gather=None):
+    """(on_diag, lam*off_diag) with autograd support for ``q``; ``gather`` = rmcl_b200.dist.Gather() under DDP."""
+    return BarlowTwins.apply(q, k, inv_bs, lam, gather)
+
+
 # -------------------------------------------------------------------------------- enqueue
 class QueueShadow:
     """bf16 copy of an fp32 queue buffer, kept current by ``enqueue_(..., shadow=...)``.

@@ -624,6 +624,74 @@ def test_infonce_tcgen05_strided_queue_and_auto_dispatch(ops):
         ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.float().to(DEV), 0.07, path="tcgen05")
 
 
+# ================================================================= Barlow Twins (fused cross-correlation loss)
+def _bt_oracle(q, k, bs, lam, **kw):
+    """float64 oracle fed the bf16-rounded operands the tensor cores see."""
+    return O.barlow_twins([q.bfloat16().double()], [k.bfloat16().double()], bs, lam, **kw)
+
+
+BT_SHAPES = [(128, 8192), (64, 2048), (256, 4096), (8, 128), (33, 200), (100, 1000), (16, 1001), (128, 520), (200, 384)]
+
+
+@pytest.mark.parametrize("B,D", BT_SHAPES)
+def test_barlow_fused_vs_oracle(ops, B, D):
+    g = torch.Generator().manual_seed(B + D)
+    k = torch.randn(B, D, generator=g)
+    q = 0.7 * k + 0.7 * torch.randn(B, D, generator=g)          # correlated views: diagonal ~0.7, off-diagonal ~1/sqrt(B)
+    lam = 0.0051
+    ref = _bt_oracle(q, k, B, lam)
+    res = ops.barlow_fwd_bwd(q.to(DEV), k.to(DEV), 1.0 / B, lam)
+    torch.cuda.synchronize()
+    assert rel_err(res["on_diag"], ref["on_diag"]) < 1e-4
+    assert rel_err(res["off_diag"], ref["off_diag"]) < 1e-4
+    assert rel_err(res["loss"], ref["loss"]) < 1e-4
+    assert rel_err(res["cdiag"], torch.diagonal(ref["c"])) < 1e-5
+    assert rel_err(res["dq"], ref["dq"][0]) < 1e-2              # P = w (c - I) is rounded to bf16 for the second GEMM
+    # ... and against the reference's own fp32 arithmetic (no operand rounding): the north-star bf16 bar
+    ref32 = O.barlow_twins([q.double()], [k.double()], B, lam)
+    assert rel_err(res["loss"], ref32["loss"]) < BF16_RTOL and rel_err(res["dq"], ref32["dq"][0]) < BF16_RTOL
+
+
+def test_barlow_gathered_batch_and_weights(ops):
+    """Two ranks of 128: every rank evaluates the full matrix from the gathered batch and keeps dq of its own rows
+    (the reference all-reduces c instead, objectives.py:482).  Also bf16 inputs and unequal gradient weights."""
+    B, D, lam = 128, 2048, 0.0051
+    g = torch.Generator().manual_seed(3)
+    ks = [torch.randn(B, D, generator=g) for _ in range(2)]
+    qs = [0.7 * k + 0.7 * torch.randn(B, D, generator=g) for k in ks]
+    ref = _bt_oracle(torch.cat(qs), torch.cat(ks), 2 * B, lam)          # sum over ranks of q_r.T k_r == gathered product
+    ref_split = O.barlow_twins([x.bfloat16().double() for x in qs], [x.bfloat16().double() for x in ks], 2 * B, lam)
+    assert rel_err(ref_split["loss"], ref["loss"]) < 1e-12
+    qa, ka = torch.cat(qs).to(DEV), torch.cat(ks).to(DEV)
+    for r in range(2):
+        res = ops.barlow_fwd_bwd(qa, ka, 1.0 / (2 * B), lam, b0=r * B, Bl=B)
+        assert rel_err(res["loss"], ref["loss"]) < 1e-4
+        assert rel_err(res["dq"], ref_split["dq"][r]) < 1e-2
+    res16 = ops.barlow_fwd_bwd(qa.bfloat16(), ka.bfloat16(), 1.0 / (2 * B), lam, b0=0, Bl=2 * B)
+    assert rel_err(res16["dq"], ref["dq"][0]) < 1e-2
+    w = _bt_oracle(torch.cat(qs), torch.cat(ks), 2 * B, lam, grad_on=0.25, grad_offs=3.0)
+    resw = ops.barlow_fwd_bwd(qa, ka, 1.0 / (2 * B), lam, w_on=0.25, w_off=3.0 * lam)
+    assert rel_err(resw["dq"], w["dq"][0]) < 1e-2
+    from rmcl_b200._lib import RmclError
+    with pytest.raises(RmclError):                                      # gathered batch > 256: explicit, no fallback
+        ops.barlow_fwd_bwd(torch.zeros(264, 64, device=DEV), torch.zeros(264, 64, device=DEV), 1.0, lam)
+
+
+def test_barlow_autograd_function(ops):
+    """Both returned sums are differentiable with independent upstream gradients (the reference sums
+    barlowtwins_loss, *_invariance_* and *_redundancy_* into the training loss, vilt_module.py:475)."""
+    B, D, lam = 64, 512, 0.0051
+    g = torch.Generator().manual_seed(9)
+    k = torch.randn(B, D, generator=g)
+    q0 = 0.5 * k + torch.randn(B, D, generator=g)
+    q = q0.clone().to(DEV).requires_grad_(True)
+    on, offs = ops.barlow_twins_loss(q, k.to(DEV), 1.0 / B, lam)
+    (1.5 * on + 0.5 * offs + (on + offs) / 3).backward()
+    ref = _bt_oracle(q0, k, B, lam, grad_on=1.5 + 1 / 3, grad_offs=0.5 + 1 / 3)
+    assert rel_err(on, ref["on_diag"]) < 1e-4 and rel_err(offs, lam * ref["off_diag"]) < 1e-4
+    assert rel_err(q.grad, ref["dq"][0]) < 1e-2
+
+
 # ======================================================== host-buffer step (C-ABI rmcl_step_host)
 @pytest.mark.parametrize("qdt", [torch.float32, torch.bfloat16])
 def test_step_host_matches_separate_ops_and_oracle(ops, qdt):
