@@ -447,6 +447,22 @@ def run_cuda(args):
                                             "launches": ["infonce_prep_kernel", "infonce_s_kernel", "infonce_pv_kernel",
                                                          "infonce_finalize_kernel"]}
         del q5, k5, queue5
+    # ---- Barlow-Twins objective at the reference's size (batch 128, projector 8192): fused cross-correlation loss
+    #      fwd+bwd (prep + barlow_tc_kernel + finalize as one call); 4*B*D^2 flop, the D x D matrix is never stored
+    if world == 1 and not args.no_pgd:
+        Bb, Db = 128, 8192
+        gb = torch.Generator(device=dev).manual_seed(6)
+        kb_ = torch.randn(Bb, Db, device=dev, generator=gb)
+        qb_ = 0.7 * kb_ + 0.7 * torch.randn(Bb, Db, device=dev, generator=gb)
+        for _ in range(3):
+            ops.barlow_fwd_bwd(qb_, kb_, 1.0 / Bb, 0.0051)
+        msb = timed(lambda: ops.barlow_fwd_bwd(qb_, kb_, 1.0 / Bb, 0.0051), 20) / 20
+        fb = 4.0 * Bb * Db * Db
+        kernels["barlow_fused_b128_d8192"] = {"bound": "tensor", "achieved": fb / (msb * 1e-3) / 1e12, "peak": pk_peak["tf_sust"],
+                                              "unit": "TFLOP/s", "frac": fb / (msb * 1e-3) / 1e12 / pk_peak["tf_sust"], "ms": msb,
+                                              "traffic": traffic.get("barlow_fused_b128_d8192"), "shape": [Bb, Db],
+                                              "launches": ["barlow_prep_kernel", "barlow_tc_kernel", "barlow_finalize_kernel"]}
+        del qb_, kb_
     for name in ("infonce_prep", "infonce_finalize"):
         kernels[name] = {"ms": kern_ms[name]}
     dominant = max(alg, key=lambda n: kern_ms[n])

@@ -483,12 +483,82 @@ def make_facade(ref):
               f"{out['step0/ret/moco_loss']}, {out['step1/ret/moco_loss']}")
 
 
+def make_barlow(ref):
+    """Whole-step golden of the Barlow-Twins objective (objectives.py:449-602, image view, PGD attacker
+    PGDAttack_bartlowtwins): the tiny module with a stand-in projection head, two consecutive steps with
+    backward, everything the reference returned and logged, plus the gradients of every parameter of
+    sum(v for k, v in ret.items() if "loss" in k) — the training loss of vilt_module.py:475."""
+    B, hidden, D, n_pgd, lr, eps = 16, 32, 96, 2, 0.05, 8.0 / 255.0
+    mod = build_tiny_module(ref, B, 16, 64, hidden=hidden, n_pgd=n_pgd, lr=lr, eps=eps, T=0.07, m=0.999, seed=12)
+    torch.manual_seed(121)
+    mod.barlowtwins_head = nn.Sequential(nn.Linear(hidden, D), nn.ReLU(), nn.Linear(D, D))
+    with torch.no_grad():                       # projections of O(1) spread so that diagonal(c) is O(1) as in training
+        mod.barlowtwins_head[2].weight.mul_(6.0)
+    mod.adv_lr = 0.0051
+    cfg = dict(adv_steps_img=n_pgd, adv_lr_img=lr, adv_max_norm_img=eps, max_image_len=200)
+    mod.pgd_attacker = ref.pgd.PGDAttack_bartlowtwins(cfg)
+    for phase in ("train", "val"):
+        for name in ("barlowtwins_loss", "barlowtwins_loss_invariance_img", "barlowtwins_loss_redundancy_img"):
+            setattr(mod, f"{phase}_{name}", lambda x: x)
+    out = {"meta/B": np.int64(B), "meta/hidden": np.int64(hidden), "meta/D": np.int64(D), "meta/n_pgd": np.int64(n_pgd),
+           "meta/lr": np.float64(lr), "meta/eps": np.float64(eps), "meta/adv_lr": np.float64(mod.adv_lr),
+           "meta/steps": np.int64(2)}
+    for k, v in mod.state_dict().items():
+        out[f"state/{k}"] = _np(v)
+    for s in range(2):
+        mod.zero_grad()
+        batch = tiny_batch(B, 16, 6, 1200 + s)
+        out[f"step{s}/batch/image"] = _np(batch["image"][0])
+        out[f"step{s}/batch/text_ids"] = _np(batch["text_ids"])
+        ret = ref.objectives.compute_barlowtwins_contrastive(mod, deepcopy(batch))
+        total = sum(v for k, v in ret.items() if "loss" in k)
+        total.backward()
+        out[f"step{s}/total_loss"] = _np(total)
+        for k, v in ret.items():
+            out[f"step{s}/ret/{k}"] = _np(v)
+        for k, v in mod.__dict__.get("_logged", {}).items():
+            out[f"step{s}/log/{k}"] = _np(torch.as_tensor(v))
+        for k, v in mod.named_parameters():
+            if v.grad is not None:
+                out[f"step{s}/grad/{k}"] = _np(v.grad)
+        with torch.no_grad():
+            for k, v in mod.named_parameters():
+                if v.grad is not None:
+                    v.add_(-0.02 * v.grad)
+    path = os.path.join(GOLDEN_DIR, "ref_barlow_facade.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {os.path.getsize(path) / 1e3:.1f} kB, losses {out['step0/ret/barlowtwins_loss']}, "
+          f"{out['step1/ret/barlowtwins_loss']} (invariance {out['step0/ret/barlowtwins_loss_invariance_img']}, "
+          f"redundancy {out['step0/ret/barlowtwins_loss_redundancy_img']})")
+
+    # kernel-level vectors: the reference expression chain itself (objectives.py:480-486) on random projections
+    g = torch.Generator().manual_seed(122)
+    vec = {}
+    for name, Bv, Dv in (("a", 8, 64), ("b", 32, 200)):
+        k = torch.randn(Bv, Dv, generator=g)
+        q = (0.7 * k + 0.7 * torch.randn(Bv, Dv, generator=g)).requires_grad_(True)
+        c = q.T @ k
+        c.div_(Bv)
+        torch.distributed.all_reduce(c)
+        on_diag = torch.diagonal(c).add_(-1).pow_(2).sum()
+        n = c.shape[0]
+        off_diag = c.flatten()[:-1].view(n - 1, n + 1)[:, 1:].flatten().pow_(2).sum()
+        loss = on_diag + 0.0051 * off_diag
+        loss.backward()
+        for kk, vv in (("q", q), ("k", k), ("on_diag", on_diag), ("off_diag", off_diag), ("loss", loss), ("dq", q.grad)):
+            vec[f"{name}/{kk}"] = _np(vv)
+    path = os.path.join(GOLDEN_DIR, "ref_barlow_vectors.npz")
+    np.savez_compressed(path, **vec)
+    print(f"wrote {path}")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg1", action="store_true")
     ap.add_argument("--only-cfg1", action="store_true")
     ap.add_argument("--only-facade", action="store_true")
     ap.add_argument("--only-pgd-others", action="store_true")
+    ap.add_argument("--only-barlow", action="store_true")
     args = ap.parse_args()
     ref = ref_harness.load_reference()
     ref_harness.ensure_process_group()
@@ -499,12 +569,16 @@ def main():
     if args.only_pgd_others:
         make_pgd_others(ref)
         return
+    if args.only_barlow:
+        make_barlow(ref)
+        return
     if not args.only_cfg1:
         make_facade(ref)
         make_tiny(ref, "ref_tiny_c16", B=4, C=16, K=64, n_pgd=1, lr=0.05, eps=8.0 / 255.0, steps=3)
         make_tiny(ref, "ref_tiny_c128", B=8, C=128, K=256, n_pgd=3, lr=0.05, eps=0.005, steps=2, seed=1)
         make_pgd_direct(ref)
         make_pgd_others(ref)
+        make_barlow(ref)
     if args.cfg1 or args.only_cfg1:
         make_cfg1(ref)
 

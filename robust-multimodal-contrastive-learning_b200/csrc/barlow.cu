@@ -110,12 +110,21 @@ __global__ void __launch_bounds__(256) barlow_prep_kernel(const TQ* __restrict__
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int i0 = blockIdx.x * 32;
   const int i = i0 + tx;
-  for (int b = ty; b < BG; b += 8) {
-    const bool ok = (b < Bg) && (i < D);
-    const float qv = ok ? to_f32(q[(size_t)b * D + i]) : 0.f;
-    const float kv = ok ? to_f32(k[(size_t)b * D + i]) : 0.f;
-    tile[b * 33 + tx] = __float2bfloat16_rn(qv);
-    if (i < d_ld) kb[(size_t)b * d_ld + i] = __float2bfloat16_rn(kv);
+  for (int bb = 0; bb < BG; bb += 64) {                 // 8 + 8 independent loads per thread in flight
+    float qv[8], kv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int b = bb + ty + 8 * u;
+      const bool ok = (b < Bg) && (i < D);
+      qv[u] = ok ? to_f32(q[(size_t)b * D + i]) : 0.f;
+      kv[u] = ok ? to_f32(k[(size_t)b * D + i]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int b = bb + ty + 8 * u;
+      tile[b * 33 + tx] = __float2bfloat16_rn(qv[u]);
+      if (i < d_ld) kb[(size_t)b * d_ld + i] = __float2bfloat16_rn(kv[u]);
+    }
   }
   __syncthreads();
   for (int r = ty; r < 32; r += 8)                      // q^T row i0 + r (rows up to d_pad exist: zero padding)
@@ -412,14 +421,25 @@ __global__ void __launch_bounds__(256) barlow_finalize_kernel(int D, int BG, int
   const int nb = gridDim.x;
   pdl_wait();
   if (dq != nullptr) {
-    for (int r = ty; r < 32; r += 8) {
+    const int vec_per_row = BG / 8;                     // 16-byte loads: 8 bf16 partials of one row
+    for (int idx = tid; idx < 32 * vec_per_row; idx += 256) {
+      const int r = idx / vec_per_row, c8 = idx - r * vec_per_row;
       const int i = i0 + r;
-      for (int b = tx; b < BG; b += 32) {
-        float a = 0.f;
-        if (i < D)
-          for (int s = 0; s < splits; ++s) a += __bfloat162float(po[((size_t)s * D + i) * BG + b]);
-        ftile[r * (BG + 1) + b] = a;
+      float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (i < D) {
+        for (int s = 0; s < splits; ++s) {
+          const uint4 u = __ldcs(reinterpret_cast<const uint4*>(po + ((size_t)s * D + i) * BG) + c8);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(h[j]);
+            a[2 * j] += f.x;
+            a[2 * j + 1] += f.y;
+          }
+        }
       }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ftile[r * (BG + 1) + c8 * 8 + j] = a[j];
     }
     __syncthreads();
     if (i0 + tx < D)

@@ -292,3 +292,81 @@ def test_other_pgd_attackers_match_reference(golden):
     a = P.PGDAttack_vqa(cfg, copy_modules=True).pgd_attack(mod, deepcopy(one))
     b = P.PGDAttack_vqa(cfg).pgd_attack(mod, deepcopy(one))
     assert torch.equal(a, b)
+
+
+# ------------------------------------------------- Barlow-Twins objective (objectives.py:449-602)
+class BarlowModule(nn.Module):
+    """Stand-in of oracle/make_golden.py:make_barlow: toy encoder + stand-in projection head."""
+
+    def __init__(self, g):
+        super().__init__()
+        import rmcl_b200
+        h, D = g.i("meta/hidden"), g.i("meta/D")
+        self.text_embeddings = nn.Embedding(50, h)
+        self.token_type_embeddings = nn.Embedding(2, h)
+        self.transformer = ToyTransformer(h, 8)
+        self.pooler = ToyPooler(h)
+        self.barlowtwins_head = nn.Sequential(nn.Linear(h, D), nn.ReLU(), nn.Linear(D, D))
+        self.adv_lr, self.per_step_bs = g.f("meta/adv_lr"), g.i("meta/B")
+        self.text_view, self.image_view, self.augmentation = False, True, False
+        self.cosine = nn.CosineSimilarity(dim=1, eps=1e-6)
+        self.max_image_len = 200
+        cfg = dict(adv_steps_img=g.i("meta/n_pgd"), adv_lr_img=g.f("meta/lr"), adv_max_norm_img=g.f("meta/eps"),
+                   max_image_len=200)
+        self.pgd_attacker = rmcl_b200.PGDAttack_bartlowtwins(cfg)
+        for phase in ("train", "val"):
+            for name in ("barlowtwins_loss", "barlowtwins_loss_invariance_img", "barlowtwins_loss_redundancy_img"):
+                setattr(self, f"{phase}_{name}", lambda x: x)
+        self.logged = {}
+        own = self.state_dict()
+        self.load_state_dict({k[len("state/"):]: g.t(k) for k in g.z.files
+                              if k.startswith("state/") and k[len("state/"):] in own})
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def log(self, name, value, **kw):
+        self.logged[name] = value
+
+    def infer(self, batch, mask_text=False, mask_image=False, **kw):
+        import rmcl_b200
+        return rmcl_b200.PGDAttack.infer(self, batch, mask_text, mask_image, **kw)
+
+
+def test_compute_barlowtwins_contrastive_matches_reference(golden):
+    """The drop-in Barlow-Twins objective on the fused tcgen05 loss against the unmodified reference (CPU, fp32,
+    materialised 96 x 96 matrix): two steps with backward through sum of the "*loss*" keys (vilt_module.py:475).
+    The kernel rounds q, k and w(c - I) to bf16 (fp32 accumulation): north-star bf16 bar 2e-2."""
+    import rmcl_b200
+    g = golden("ref_barlow_facade")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    mod = BarlowModule(g).to(DEV).train()
+    for s in range(g.i("meta/steps")):
+        mod.zero_grad()
+        mod.logged.clear()
+        ret = rmcl_b200.compute_barlowtwins_contrastive(mod, _batch(g, s))
+        want_keys = sorted(k.split("/")[-1] for k in g.z.files if k.startswith(f"step{s}/ret/"))
+        assert sorted(ret) == want_keys
+        total = sum(v for k, v in ret.items() if "loss" in k)
+        total.backward()
+        torch.cuda.synchronize()
+        _close(total, g.np(f"step{s}/total_loss"), 2e-2, f"step {s} total loss")
+        for k in want_keys:
+            # step 1 runs on parameters nudged by step 0's (bf16-path) gradients: the diagnostics inherit that drift
+            _close(ret[k], g.np(f"step{s}/ret/{k}"), 2e-2 if "loss" in k else (1e-3 if s == 0 else 5e-3), f"step {s} {k}")
+        for k in g.z.files:
+            if k.startswith(f"step{s}/log/"):
+                name = k[len(f"step{s}/log/"):]
+                _close(torch.as_tensor(mod.logged[name]), g.np(k), 2e-2, f"step {s} log {name}")
+        n_grads = 0
+        for k, v in mod.named_parameters():
+            if f"step{s}/grad/{k}" in g:
+                _close(v.grad, g.np(f"step{s}/grad/{k}"), 3e-2, f"step {s} grad {k}")
+                n_grads += 1
+        assert n_grads >= 10
+        with torch.no_grad():
+            for k, v in mod.named_parameters():
+                if v.grad is not None:
+                    v.add_(-0.02 * v.grad)

@@ -141,3 +141,39 @@ def test_diagnostics_restatement_matches_reference_values(golden):
                          ("pos_cosine", "pos_cosine_attacked_img"), ("neg_cosine", "neg_cosine_attacked_img"),
                          ("pos_dot", "pos_dot_attacked_img"), ("neg_dot", "neg_dot_attacked_img")):
         torch.testing.assert_close(d[ours], g.t(f"step0/diag/{theirs}"), rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------ Barlow Twins
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_barlow_twins_matches_reference_expression_chain(golden, name):
+    """oracle.barlow_twins against the reference's own lines (objectives.py:480-486 run verbatim, with the
+    in-place div_/all_reduce/add_/pow_ and autograd backward, by oracle/make_golden.py:make_barlow)."""
+    g = golden("ref_barlow_vectors")
+    q, k = g.t(f"{name}/q"), g.t(f"{name}/k")
+    r = O.barlow_twins([q], [k], q.shape[0], 0.0051)
+    for key in ("on_diag", "off_diag", "loss"):
+        assert abs(float(r[key]) - g.f(f"{name}/{key}")) <= 2e-6 * abs(g.f(f"{name}/{key}")), key
+    want = g.t(f"{name}/dq")
+    assert (r["dq"][0] - want).abs().max().item() <= 2e-6 * want.abs().max().item()
+
+
+def test_barlow_twins_facade_golden_is_consistent(golden):
+    """The whole-step golden's returned sums obey the reference's own bookkeeping (objectives.py:486,555):
+    barlowtwins_loss = (invariance + redundancy) / 1 view, total = sum of the three "*loss*" keys."""
+    g = golden("ref_barlow_facade")
+    for s in range(g.i("meta/steps")):
+        inv, red = g.f(f"step{s}/ret/barlowtwins_loss_invariance_img"), g.f(f"step{s}/ret/barlowtwins_loss_redundancy_img")
+        assert g.f(f"step{s}/ret/barlowtwins_loss") == pytest.approx(inv + red, rel=1e-6)
+        assert g.f(f"step{s}/total_loss") == pytest.approx(2 * (inv + red), rel=1e-6)
+
+
+def test_barlow_twins_rank_split_equals_gathered_batch():
+    """sum_r q_r.T k_r (the reference's all-reduce of c) == (gathered q).T (gathered k): the identity the CUDA
+    path relies on to replace the 268 MB all-reduce by an all-gather of the projections."""
+    g = torch.Generator().manual_seed(0)
+    qs = [torch.randn(6, 40, generator=g, dtype=torch.float64) for _ in range(3)]
+    ks = [torch.randn(6, 40, generator=g, dtype=torch.float64) for _ in range(3)]
+    a = O.barlow_twins(qs, ks, 18, 0.0051)
+    b = O.barlow_twins([torch.cat(qs)], [torch.cat(ks)], 18, 0.0051)
+    assert torch.allclose(a["c"], b["c"], rtol=1e-12, atol=1e-14)
+    assert torch.allclose(torch.cat(a["dq"]), b["dq"][0], rtol=1e-12, atol=1e-14)
