@@ -57,3 +57,42 @@ def test_single_process_gather_is_identity():
     from rmcl_b200.dist import concat_all_gather
     t = torch.randn(3, 5)
     assert concat_all_gather(t) is t
+
+
+def _barlow_worker(rank, world, init_file, out_dir):
+    """The Barlow-Twins exchange on the host side: the reference all-reduces c = q.T k / bs (objectives.py:482);
+    the CUDA path all-gathers q and k and evaluates the matrix from the gathered batch.  Here both are done with
+    gloo and the oracle stands in for the kernel: same c, same loss, and the per-rank gradient rows line up."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
+    import rmcl_oracle as O
+    from rmcl_b200.dist import Gather
+    B, D, lam = 6, 24, 0.0051
+    g = torch.Generator().manual_seed(200 + rank)
+    k = torch.randn(B, D, generator=g, dtype=torch.float64)
+    q = 0.7 * k + 0.7 * torch.randn(B, D, generator=g, dtype=torch.float64)
+    gather = Gather()
+    assert gather.rank == rank and gather.world == world
+    qa, ka = gather(q), gather(k)
+    assert torch.equal(qa[rank * B:(rank + 1) * B], q)
+    mine = O.barlow_twins([qa], [ka], world * B, lam)                    # what the kernel computes (b0 = rank * B)
+    c = q.T @ k / (world * B)                                            # what the reference computes
+    dist.all_reduce(c)
+    assert torch.allclose(mine["c"], c, rtol=1e-12, atol=1e-14)
+    torch.save({"loss": mine["loss"], "dq_local": mine["dq"][0][rank * B:(rank + 1) * B], "q": q, "k": k},
+               os.path.join(out_dir, f"b{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_barlow_gather_replaces_allreduce_world2():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import rmcl_oracle as O
+    world = 2
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_barlow_worker, args=(world, os.path.join(d, "pg"), d), nprocs=world, join=True)
+        r = [torch.load(os.path.join(d, f"b{i}.pt")) for i in range(world)]
+    assert torch.equal(r[0]["loss"], r[1]["loss"])
+    ref = O.barlow_twins([x["q"] for x in r], [x["k"] for x in r], 12, 0.0051)   # the reference's per-rank backward
+    for i in range(world):
+        assert torch.allclose(r[i]["dq_local"], ref["dq"][i], rtol=1e-12, atol=1e-14)
