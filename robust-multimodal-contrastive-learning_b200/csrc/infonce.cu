@@ -470,14 +470,8 @@ static int infonce_impl(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_d
   RMCL_CHECK_ARG(dtype_ok(q_dtype) && dtype_ok(k_dtype) && dtype_ok(queue_dtype), "rmcl_infonce_fwd_bwd: bad dtype");
   RMCL_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "rmcl_infonce_fwd_bwd: workspace must be 256B aligned");
   InfoNcePlan p;
-  // the per-view diagnostics are fused into the single-pass kernels only
-  if (diag.out && path == RMCL_INFONCE_AUTO && infonce_tc2_supports(C)) path = RMCL_INFONCE_SIMT;
   int rc = infonce_make_plan(B, C, K, queue_dtype, path, tc_alignment_ok(queue, ldq), &p);
   if (rc != RMCL_OK) return rc;
-  if (diag.out && p.two_pass) {
-    set_error("rmcl_infonce_fwd_bwd_diag: the two-pass tcgen05 path (C=%d) has no fused diagnostics; use AUTO or SIMT", C);
-    return RMCL_E_UNSUPPORTED_DIM;
-  }
   if (workspace_bytes < p.total) {
     set_error("rmcl_infonce_fwd_bwd: workspace %zu < required %zu", workspace_bytes, p.total);
     return RMCL_E_WORKSPACE;

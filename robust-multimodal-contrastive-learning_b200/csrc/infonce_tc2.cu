@@ -48,15 +48,17 @@ struct SShared {
   float xl[kRows];
   float xav[kRows];
   int xai[kRows];
+  float xd[kRows];     // diagnostics: the odd-tile warp's distance sum
 };
 
 // =========================================================================================== S pass
-template <int C>
+template <int C, bool DIAG>
 __global__ void __launch_bounds__(kThreads, 1)
     infonce_s_kernel(const __grid_constant__ CUtensorMap tmap_queue, const __nv_bfloat16* __restrict__ q_hat, int B,
                      long long K, long long k_pad, float scale2, long long cols_per_split, int want_argmax,
                      float* __restrict__ pm, float* __restrict__ pl, float* __restrict__ pav, int* __restrict__ pai,
-                     __nv_bfloat16* __restrict__ ptilde, unsigned int* __restrict__ overflow_flag) {
+                     __nv_bfloat16* __restrict__ ptilde, unsigned int* __restrict__ overflow_flag,
+                     const float* __restrict__ n2, const float* __restrict__ qn2, float* __restrict__ pdist) {
   constexpr int kChunks = C / kChunkRows;              // ring stages consumed per tile
   constexpr int kStages = 5;
   constexpr uint32_t kTmQ = 0, kTmS = C / 2;
@@ -140,6 +142,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     float m_ref = 0.f, l_run = 0.f, av_raw = -INFINITY;
     int ai = 0;
     bool overflow = false;
+    float dsum = 0.f;                                     // diagnostics: sum_j |q^_r - queue_j| (infonce_tc.cu)
+    const float qn2_r = (DIAG && row0 + r < B) ? qn2[row0 + r] : 0.f;
     for (int i = par; i < n_tiles; i += 2) {
       const int b = par;
       const uint32_t ts = tlane + kTmS + b * kTN;
@@ -152,6 +156,21 @@ __global__ void __launch_bounds__(kThreads, 1)
       tc_fence_before();
       mbar_arrive(&sh.s_free[b]);
       const long long col0 = k_begin + (long long)i * kTN;
+      if (DIAG) {
+        // mean L2 distance to the negatives (objectives.py:343): |q^ - queue_j|^2 = |q^|^2 - 2 S_j + |queue_j|^2
+        const float4* nv = reinterpret_cast<const float4*>(n2 + col0);
+#pragma unroll
+        for (int c4 = 0; c4 < kTN / 4; ++c4) {
+          if (col0 + 4 * c4 < k_end) {                    // k_end is a multiple of 8 on this path
+            const float4 nn = __ldg(nv + c4);
+            const float d0 = fmaf(-2.f, __uint_as_float(sv[4 * c4 + 0]), qn2_r + nn.x);
+            const float d1 = fmaf(-2.f, __uint_as_float(sv[4 * c4 + 1]), qn2_r + nn.y);
+            const float d2 = fmaf(-2.f, __uint_as_float(sv[4 * c4 + 2]), qn2_r + nn.z);
+            const float d3 = fmaf(-2.f, __uint_as_float(sv[4 * c4 + 3]), qn2_r + nn.w);
+            dsum += (sqrtf(fmaxf(d0, 0.f)) + sqrtf(fmaxf(d1, 0.f))) + (sqrtf(fmaxf(d2, 0.f)) + sqrtf(fmaxf(d3, 0.f)));
+          }
+        }
+      }
       if (col0 + kTN > k_end) {
         const int valid = (int)(k_end - col0);
 #pragma unroll
@@ -216,6 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       sh.xl[r] = l_run;
       sh.xav[r] = av_raw;
       sh.xai[r] = ai;
+      if (DIAG) sh.xd[r] = dsum;
     }
     named_bar_sync(9 + quad, 64);
     if (par == 0 && row0 + r < B) {
@@ -228,6 +248,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       pl[o] = l_tot;
       pav[o] = av_raw * scale2;
       pai[o] = ai;
+      if (DIAG) pdist[o] = dsum + sh.xd[r];
     }
     tc_fence_before();
   } else if (warp == 8) {
@@ -406,15 +427,15 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 }
 
-template <int C>
+template <int C, bool DIAG>
 int launch_s(const CUtensorMap& tq, const __nv_bfloat16* q_hat, int B, long long K, long long k_pad, float scale2,
              const InfoNcePlan& p, InfoNcePartials out, __nv_bfloat16* ptilde, unsigned int* flag, int want_argmax,
              cudaStream_t s) {
   const size_t smem = 8 * 4096 + 5 * (size_t)kChunkBytes + 1024;
-  auto kern = infonce_s_kernel<C>;
+  auto kern = infonce_s_kernel<C, DIAG>;
   RMCL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   RMCL_CUDA_OK(launch_pdl(kern, dim3(p.splits, p.row_blocks), dim3(kThreads), smem, s, tq, q_hat, B, K, k_pad, scale2,
-                          p.cols_per_split, want_argmax, out.m, out.l, out.av, out.ai, ptilde, flag));
+                          p.cols_per_split, want_argmax, out.m, out.l, out.av, out.ai, ptilde, flag, out.n2, out.qn2, out.dist));
   return RMCL_OK;
 }
 
@@ -434,10 +455,13 @@ int infonce_tc2_launch(const __nv_bfloat16* q_hat, const void* queue, int B, int
   if (rc != RMCL_OK) return rc;
   rc = make_tmap_bf16(&tp, ptilde, (uint64_t)p.b_pad, (uint64_t)k_pad, (uint64_t)k_pad, kRows);
   if (rc != RMCL_OK) return rc;
+  const bool dg = out.n2 != nullptr;
   if (C == 768)
-    rc = launch_s<768>(tq, q_hat, B, K, k_pad, scale2, p, out, ptilde, overflow_flag, want_argmax, s);
+    rc = dg ? launch_s<768, true>(tq, q_hat, B, K, k_pad, scale2, p, out, ptilde, overflow_flag, want_argmax, s)
+            : launch_s<768, false>(tq, q_hat, B, K, k_pad, scale2, p, out, ptilde, overflow_flag, want_argmax, s);
   else if (C == 512)
-    rc = launch_s<512>(tq, q_hat, B, K, k_pad, scale2, p, out, ptilde, overflow_flag, want_argmax, s);
+    rc = dg ? launch_s<512, true>(tq, q_hat, B, K, k_pad, scale2, p, out, ptilde, overflow_flag, want_argmax, s)
+            : launch_s<512, false>(tq, q_hat, B, K, k_pad, scale2, p, out, ptilde, overflow_flag, want_argmax, s);
   else {
     set_error("two-pass tcgen05 InfoNCE supports C in {512, 768} (got %d)", C);
     return RMCL_E_UNSUPPORTED_DIM;

@@ -417,7 +417,8 @@ def test_greedy_split_forward_losses(ops, B, C, K, all_num):
 @pytest.mark.parametrize("B,C,K,qdt,path", [
     (8, 128, 4096, torch.float32, "simt"), (37, 70, 1000, torch.float32, "simt"), (16, 768, 520, torch.float32, "simt"),
     (24, 128, 4096, torch.bfloat16, "simt"), (128, 128, 4096, torch.bfloat16, "tcgen05"),
-    (200, 256, 8192, torch.bfloat16, "tcgen05"), (64, 64, 1000, torch.bfloat16, "tcgen05")])
+    (200, 256, 8192, torch.bfloat16, "tcgen05"), (64, 64, 1000, torch.bfloat16, "tcgen05"),
+    (130, 768, 4096, torch.bfloat16, "tcgen05"), (64, 512, 1000, torch.bfloat16, "auto")])     # two-pass variant
 def test_infonce_diagnostics_vs_oracle(ops, B, C, K, qdt, path):
     """pos/neg L2, cosine and dot means of objectives.py:337-349 out of the fused pass, against the
     oracle's restatement of the reference's per-sample loop (un-normalised randn queue, as initialised)."""
