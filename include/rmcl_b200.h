@@ -160,13 +160,16 @@ int rmcl_infonce_fwd_bwd_diag(const void* q, rmcl_dtype q_dtype, const void* k, 
  *           loss_scale * (on_diag + lambda * off_diag), dq f32[Bl, D], cdiag f32[D] = diagonal(c);
  *           any may be NULL.  (cdiag lets a caller whose upstream gradients of the two sums differ
  *           combine dq = g_on * 2/bs (cdiag-1) k + g_off * dq(w_on=0, w_off=1) without a second pass.)
- * Gathered batches > 256 return RMCL_E_UNSUPPORTED_DIM.
+ * path      RMCL_BARLOW_GRAM (= AUTO): through the Gram matrices q q^T, k k^T — sum_ij c_ij^2 = <q q^T, k k^T>/bs^2,
+ *           gradient 2/bs^2 (k k^T) q — three tcgen05 GEMMs with D as the long dimension, any Bg <= 4096,
+ *           ~D/(1.5 Bg) times fewer flops.  RMCL_BARLOW_DIRECT: c evaluated tile by tile (Bg <= 256).
  */
+enum { RMCL_BARLOW_AUTO = 0, RMCL_BARLOW_DIRECT = 1, RMCL_BARLOW_GRAM = 2 };
 size_t rmcl_barlow_workspace_bytes(int Bg, int D);
 int rmcl_barlow_fwd_bwd(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_dtype k_dtype, int Bg, int D,
                         int b0, int Bl, float inv_bs, float lambda, float w_on, float w_off,
-                        float loss_scale, float* on_diag, float* off_diag, float* loss, float* dq,
-                        float* cdiag, void* workspace, size_t workspace_bytes, void* stream);
+                        float loss_scale, int path, float* on_diag, float* off_diag, float* loss,
+                        float* dq, float* cdiag, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Measurement aid (off by default): when enabled on the calling thread, rmcl_infonce_fwd_bwd
  * records CUDA events on its stream around its three launches (prep, split-K partial, finalize);

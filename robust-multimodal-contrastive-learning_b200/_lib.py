@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, os.environ.get("RMCL_B200_LIB", "librmcl_b200.so"
 RMCL_F32, RMCL_BF16 = 0, 1
 PGD_MODES = {"ref_linf": 0, "sign_linf": 1, "l2": 2}
 INFONCE_PATHS = {"auto": 0, "simt": 1, "tcgen05": 2}
+BARLOW_PATHS = {"auto": 0, "direct": 1, "gram": 2}
 FLAG_NORMALIZE_K, FLAG_NO_GRAD, FLAG_DEBUG_PARTIAL_ONLY = 1, 2, 4
 
 EXPORTS = (
@@ -79,7 +80,7 @@ def lib():
     L.rmcl_barlow_workspace_bytes.restype = sz
     L.rmcl_barlow_workspace_bytes.argtypes = [i32, i32]
     L.rmcl_barlow_fwd_bwd.restype = i32
-    L.rmcl_barlow_fwd_bwd.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, f32, f32, f32, f32, f32, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.rmcl_barlow_fwd_bwd.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, f32, f32, f32, f32, f32, i32, vp, vp, vp, vp, vp, vp, sz, vp]
     L.rmcl_pgd_step.restype = i32
     L.rmcl_pgd_step.argtypes = [vp, i32, vp, i32, i32, i64, f32, f32, i32, vp, sz, vp]
     L.rmcl_pgd_workspace_bytes.restype = sz

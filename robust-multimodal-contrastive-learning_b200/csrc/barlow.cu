@@ -69,7 +69,7 @@ int barlow_make_plan(int Bg, int D, BtPlan* p) {
   const int sms = sm_count();
   if (sms <= 0) return RMCL_E_CUDA;
   if (Bg > 256) {
-    set_error("rmcl_barlow_fwd_bwd: gathered batch %d > 256 is not supported by the fused tcgen05 kernel yet", Bg);
+    set_error("rmcl_barlow_fwd_bwd: gathered batch %d > 256 is not supported by the direct (D x D) kernel; use the Gram path", Bg);
     return RMCL_E_UNSUPPORTED_DIM;
   }
   p->BG = Bg <= 64 ? 64 : (Bg <= 128 ? 128 : 256);
@@ -518,24 +518,40 @@ int launch_prep(const void* q, const void* k, int Bg, int D, const BtPlan& p, ch
 
 }  // namespace rmcl
 
+namespace rmcl {
+// barlow_gram.cu
+size_t barlow_gram_workspace_bytes(int Bg, int D);
+int barlow_gram_run(const void* q, int q_dtype, const void* k, int k_dtype, int Bg, int D, int b0, int Bl, float inv_bs,
+                    float lambda, float w_on, float w_off, float loss_scale, float* on_diag, float* off_diag, float* loss,
+                    float* dq, float* cdiag_out, void* workspace, size_t workspace_bytes, cudaStream_t s);
+}  // namespace rmcl
+
 using namespace rmcl;
 
 extern "C" size_t rmcl_barlow_workspace_bytes(int Bg, int D) {
   if (Bg <= 0 || D <= 0) return 0;
-  BtPlan p;
-  if (barlow_make_plan(Bg, D, &p) != RMCL_OK) return 0;
-  return p.total;
+  size_t best = barlow_gram_workspace_bytes(Bg, D);      // sized for whichever formulation needs more
+  if (Bg <= 256) {
+    BtPlan p;
+    if (barlow_make_plan(Bg, D, &p) == RMCL_OK && p.total > best) best = p.total;
+  }
+  return best;
 }
 
 extern "C" int rmcl_barlow_fwd_bwd(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_dtype k_dtype, int Bg, int D, int b0,
                                    int Bl, float inv_bs, float lambda, float w_on, float w_off, float loss_scale,
-                                   float* on_diag, float* off_diag, float* loss, float* dq, float* cdiag, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
+                                   int path, float* on_diag, float* off_diag, float* loss, float* dq, float* cdiag,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
   RMCL_CHECK_ARG(q && k && workspace, "rmcl_barlow_fwd_bwd: null pointer");
+  RMCL_CHECK_ARG(path >= RMCL_BARLOW_AUTO && path <= RMCL_BARLOW_GRAM, "rmcl_barlow_fwd_bwd: bad path %d", path);
   RMCL_CHECK_ARG(Bg > 0 && D > 0 && b0 >= 0 && Bl > 0 && b0 + Bl <= Bg, "rmcl_barlow_fwd_bwd: bad sizes Bg=%d D=%d b0=%d Bl=%d", Bg,
                  D, b0, Bl);
   RMCL_CHECK_ARG(dtype_ok(q_dtype) && dtype_ok(k_dtype), "rmcl_barlow_fwd_bwd: bad dtype");
   RMCL_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "rmcl_barlow_fwd_bwd: workspace must be 256B aligned");
+  if (path == RMCL_BARLOW_AUTO) path = RMCL_BARLOW_GRAM;
+  if (path == RMCL_BARLOW_GRAM)
+    return barlow_gram_run(q, q_dtype, k, k_dtype, Bg, D, b0, Bl, inv_bs, lambda, w_on, w_off, loss_scale, on_diag, off_diag, loss,
+                           dq, cdiag, workspace, workspace_bytes, (cudaStream_t)stream);
   BtPlan p;
   int rc = barlow_make_plan(Bg, D, &p);
   if (rc != RMCL_OK) return rc;

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(os.path.dirname(HERE), "librmcl_b200.so")
 SOURCES = ["capi.cu", "ema.cu", "enqueue.cu", "pgd.cu", "infonce.cu", "infonce_simt.cu", "infonce_tc.cu", "infonce_tc2.cu",
-           "queue_stats.cu", "barlow.cu"]
+           "queue_stats.cu", "barlow.cu", "barlow_gram.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "-shared", "-cudart", "static"]
 

@@ -228,14 +228,15 @@ def infonce_loss(q, k, queue, temperature, path="auto", normalize_k=False, diag=
 _bt_ws_cache = {}
 
 
-def barlow_fwd_bwd(q, k, inv_bs, lam, *, b0=0, Bl=None, w_on=1.0, w_off=None, loss_scale=1.0,
+def barlow_fwd_bwd(q, k, inv_bs, lam, *, b0=0, Bl=None, w_on=1.0, w_off=None, loss_scale=1.0, path="auto",
                    want=("on_diag", "off_diag", "loss", "dq", "cdiag")):
     """Fused Barlow-Twins loss of ``q``, ``k`` [Bg, D] (the batch gathered over all ranks): the D x D
     cross-correlation ``c = q.T @ k * inv_bs`` is evaluated tile by tile on the tensor cores and never stored.
 
     Returns ``on_diag = sum_i (c_ii-1)^2``, ``off_diag = sum_{i!=j} c_ij^2`` (objectives.py:483-484),
     ``loss = loss_scale*(on_diag + lam*off_diag)``, ``dq`` [Bl, D] = d(w_on*on_diag + w_off*off_diag)/dq[b0:b0+Bl]
-    * loss_scale (``w_off`` defaults to ``lam``) and ``cdiag`` = diagonal(c)."""
+    * loss_scale (``w_off`` defaults to ``lam``) and ``cdiag`` = diagonal(c).  ``path``: "gram" (= "auto": through the
+    Gram matrices q q^T and k k^T, any batch) or "direct" (c tile by tile, gathered batch <= 256)."""
     _need_cuda(q, k)
     if q.dim() != 2 or q.shape != k.shape or not q.is_contiguous() or not k.is_contiguous():
         raise ValueError("q and k must be contiguous [Bg, D] tensors of the same shape")
@@ -260,7 +261,8 @@ def barlow_fwd_bwd(q, k, inv_bs, lam, *, b0=0, Bl=None, w_on=1.0, w_off=None, lo
            "cdiag": torch.empty(D, **f32) if "cdiag" in want else None}
     ptr = lambda t: None if t is None else _p(t)
     rc = L.rmcl_barlow_fwd_bwd(_p(q), _dt(q), _p(k), _dt(k), Bg, D, int(b0), int(Bl), float(inv_bs), float(lam), float(w_on),
-                               float(w_off), float(loss_scale), ptr(out["on_diag"]), ptr(out["off_diag"]), ptr(out["loss"]),
+                               float(w_off), float(loss_scale), _lib.BARLOW_PATHS[path], ptr(out["on_diag"]), ptr(out["off_diag"]),
+                               ptr(out["loss"]),
                                ptr(out["dq"]), ptr(out["cdiag"]), ws.data_ptr() + off, ws.numel() - off, _stream())
     check(rc, "rmcl_barlow_fwd_bwd")
     return out

@@ -634,26 +634,31 @@ def _bt_oracle(q, k, bs, lam, **kw):
 BT_SHAPES = [(128, 8192), (64, 2048), (256, 4096), (8, 128), (33, 200), (100, 1000), (16, 1001), (128, 520), (200, 384)]
 
 
-@pytest.mark.parametrize("B,D", BT_SHAPES)
-def test_barlow_fused_vs_oracle(ops, B, D):
+BT_SHAPES_GRAM = BT_SHAPES + [(300, 1000), (512, 2048), (1024, 2048), (1000, 520)]     # any gathered batch
+
+
+@pytest.mark.parametrize("B,D,path", [(b, d, "direct") for b, d in BT_SHAPES] + [(b, d, "gram") for b, d in BT_SHAPES_GRAM])
+def test_barlow_fused_vs_oracle(ops, B, D, path):
     g = torch.Generator().manual_seed(B + D)
     k = torch.randn(B, D, generator=g)
     q = 0.7 * k + 0.7 * torch.randn(B, D, generator=g)          # correlated views: diagonal ~0.7, off-diagonal ~1/sqrt(B)
     lam = 0.0051
     ref = _bt_oracle(q, k, B, lam)
-    res = ops.barlow_fwd_bwd(q.to(DEV), k.to(DEV), 1.0 / B, lam)
+    res = ops.barlow_fwd_bwd(q.to(DEV), k.to(DEV), 1.0 / B, lam, path=path)
     torch.cuda.synchronize()
     assert rel_err(res["on_diag"], ref["on_diag"]) < 1e-4
     assert rel_err(res["off_diag"], ref["off_diag"]) < 1e-4
     assert rel_err(res["loss"], ref["loss"]) < 1e-4
     assert rel_err(res["cdiag"], torch.diagonal(ref["c"])) < 1e-5
-    assert rel_err(res["dq"], ref["dq"][0]) < 1e-2              # P = w (c - I) is rounded to bf16 for the second GEMM
+    # direct: P = w (c - I) is rounded to bf16 for the second GEMM; gram: Gk enters as a bf16 hi/lo pair
+    assert rel_err(res["dq"], ref["dq"][0]) < (1e-2 if path == "direct" else 1e-4)
     # ... and against the reference's own fp32 arithmetic (no operand rounding): the north-star bf16 bar
     ref32 = O.barlow_twins([q.double()], [k.double()], B, lam)
     assert rel_err(res["loss"], ref32["loss"]) < BF16_RTOL and rel_err(res["dq"], ref32["dq"][0]) < BF16_RTOL
 
 
-def test_barlow_gathered_batch_and_weights(ops):
+@pytest.mark.parametrize("path", ["direct", "gram"])
+def test_barlow_gathered_batch_and_weights(ops, path):
     """Two ranks of 128: every rank evaluates the full matrix from the gathered batch and keeps dq of its own rows
     (the reference all-reduces c instead, objectives.py:482).  Also bf16 inputs and unequal gradient weights."""
     B, D, lam = 128, 2048, 0.0051
@@ -665,17 +670,33 @@ def test_barlow_gathered_batch_and_weights(ops):
     assert rel_err(ref_split["loss"], ref["loss"]) < 1e-12
     qa, ka = torch.cat(qs).to(DEV), torch.cat(ks).to(DEV)
     for r in range(2):
-        res = ops.barlow_fwd_bwd(qa, ka, 1.0 / (2 * B), lam, b0=r * B, Bl=B)
+        res = ops.barlow_fwd_bwd(qa, ka, 1.0 / (2 * B), lam, b0=r * B, Bl=B, path=path)
         assert rel_err(res["loss"], ref["loss"]) < 1e-4
         assert rel_err(res["dq"], ref_split["dq"][r]) < 1e-2
-    res16 = ops.barlow_fwd_bwd(qa.bfloat16(), ka.bfloat16(), 1.0 / (2 * B), lam, b0=0, Bl=2 * B)
+    res16 = ops.barlow_fwd_bwd(qa.bfloat16(), ka.bfloat16(), 1.0 / (2 * B), lam, b0=0, Bl=2 * B, path=path)
     assert rel_err(res16["dq"], ref["dq"][0]) < 1e-2
     w = _bt_oracle(torch.cat(qs), torch.cat(ks), 2 * B, lam, grad_on=0.25, grad_offs=3.0)
-    resw = ops.barlow_fwd_bwd(qa, ka, 1.0 / (2 * B), lam, w_on=0.25, w_off=3.0 * lam)
+    resw = ops.barlow_fwd_bwd(qa, ka, 1.0 / (2 * B), lam, w_on=0.25, w_off=3.0 * lam, path=path)
     assert rel_err(resw["dq"], w["dq"][0]) < 1e-2
+    # an unaligned slice of local rows (b0 not a multiple of 128)
+    part = ops.barlow_fwd_bwd(qa, ka, 1.0 / (2 * B), lam, b0=40, Bl=150, path=path)
+    assert rel_err(part["dq"], ref["dq"][0][40:190]) < 1e-2
     from rmcl_b200._lib import RmclError
-    with pytest.raises(RmclError):                                      # gathered batch > 256: explicit, no fallback
-        ops.barlow_fwd_bwd(torch.zeros(264, 64, device=DEV), torch.zeros(264, 64, device=DEV), 1.0, lam)
+    with pytest.raises(RmclError):                                      # direct kernel: gathered batch > 256 is explicit
+        ops.barlow_fwd_bwd(torch.zeros(264, 64, device=DEV), torch.zeros(264, 64, device=DEV), 1.0, lam, path="direct")
+
+
+def test_barlow_gram_matches_direct_at_reference_size(ops):
+    """Batch 128, projector 8192 (vilt_module.py:115): the two formulations agree far inside the bf16 bar."""
+    g = torch.Generator().manual_seed(1)
+    k = torch.randn(128, 8192, generator=g).to(DEV)
+    q = 0.7 * k + 0.7 * torch.randn(128, 8192, generator=g).to(DEV)
+    a = ops.barlow_fwd_bwd(q, k, 1.0 / 128, 0.0051, path="direct")
+    b = ops.barlow_fwd_bwd(q, k, 1.0 / 128, 0.0051, path="gram")
+    assert rel_err(b["on_diag"], a["on_diag"]) < 1e-5 and rel_err(b["off_diag"], a["off_diag"]) < 1e-5
+    assert rel_err(b["cdiag"], a["cdiag"]) < 1e-5 and rel_err(b["dq"], a["dq"]) < 1e-2
+    b2 = ops.barlow_fwd_bwd(q, k, 1.0 / 128, 0.0051, path="gram")
+    assert torch.equal(b["dq"], b2["dq"]) and torch.equal(b["loss"], b2["loss"])          # deterministic
 
 
 def test_barlow_autograd_function(ops):
