@@ -447,22 +447,33 @@ def run_cuda(args):
                                             "launches": ["infonce_prep_kernel", "infonce_s_kernel", "infonce_pv_kernel",
                                                          "infonce_finalize_kernel"]}
         del q5, k5, queue5
-    # ---- Barlow-Twins objective at the reference's size (batch 128, projector 8192): fused cross-correlation loss
-    #      fwd+bwd (prep + barlow_tc_kernel + finalize as one call); 4*B*D^2 flop, the D x D matrix is never stored
+    # ---- Barlow-Twins objective at the reference's size (batch 128, projector 8192) and at an 8-GPU gathered batch (1024):
+    #      Gram formulation (default; 6*Bg^2*D flop, bound by reading q, k once and four short launches) and the direct
+    #      D x D kernel (4*B*D^2 flop, tensor bound); each timed as one call = prep + tcgen05 kernel(s) + finalize
     if world == 1 and not args.no_pgd:
-        Bb, Db = 128, 8192
         gb = torch.Generator(device=dev).manual_seed(6)
-        kb_ = torch.randn(Bb, Db, device=dev, generator=gb)
-        qb_ = 0.7 * kb_ + 0.7 * torch.randn(Bb, Db, device=dev, generator=gb)
-        for _ in range(3):
-            ops.barlow_fwd_bwd(qb_, kb_, 1.0 / Bb, 0.0051)
-        msb = timed(lambda: ops.barlow_fwd_bwd(qb_, kb_, 1.0 / Bb, 0.0051), 20) / 20
-        fb = 4.0 * Bb * Db * Db
-        kernels["barlow_fused_b128_d8192"] = {"bound": "tensor", "achieved": fb / (msb * 1e-3) / 1e12, "peak": pk_peak["tf_sust"],
-                                              "unit": "TFLOP/s", "frac": fb / (msb * 1e-3) / 1e12 / pk_peak["tf_sust"], "ms": msb,
-                                              "traffic": traffic.get("barlow_fused_b128_d8192"), "shape": [Bb, Db],
-                                              "launches": ["barlow_prep_kernel", "barlow_tc_kernel", "barlow_finalize_kernel"]}
-        del qb_, kb_
+        for tag, Bb, Db, bpath, bound in (("barlow_gram_b128_d8192", 128, 8192, "gram", "hbm"),
+                                          ("barlow_direct_b128_d8192", 128, 8192, "direct", "tensor"),
+                                          ("barlow_gram_b1024_d8192", 1024, 8192, "gram", "tensor")):
+            kb_ = torch.randn(Bb, Db, device=dev, generator=gb)
+            qb_ = 0.7 * kb_ + 0.7 * torch.randn(Bb, Db, device=dev, generator=gb)
+            for _ in range(3):
+                ops.barlow_fwd_bwd(qb_, kb_, 1.0 / Bb, 0.0051, path=bpath)
+            graph = torch.cuda.CUDAGraph()      # graph replay: the host cost of 3-4 short launches would dominate a Python loop
+            with torch.cuda.graph(graph):
+                for _ in range(10):
+                    ops.barlow_fwd_bwd(qb_, kb_, 1.0 / Bb, 0.0051, path=bpath)
+            graph.replay()
+            msb = min(timed(graph.replay, 1) for _ in range(5)) / 10
+            if bound == "tensor":
+                work = (6.0 * Bb * Bb * Db) if bpath == "gram" else (4.0 * Bb * Db * Db)
+                ach, peak, unit = work / (msb * 1e-3) / 1e12, pk_peak["tf_sust"], "TFLOP/s"
+            else:
+                work = 3.0 * Bb * Db * 4         # read q, k (fp32), write dq
+                ach, peak, unit = work / (msb * 1e-3) / 1e9, pk_peak["hbm"], "GB/s"
+            kernels[tag] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "ms": msb,
+                            "traffic": traffic.get(tag), "shape": [Bb, Db], "timing": "CUDA graph of 10 calls"}
+            del graph, qb_, kb_
     for name in ("infonce_prep", "infonce_finalize"):
         kernels[name] = {"ms": kern_ms[name]}
     dominant = max(alg, key=lambda n: kern_ms[n])

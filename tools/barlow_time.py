@@ -7,7 +7,7 @@ import rmcl_b200
 from rmcl_b200 import ops
 dev = "cuda"
 lam = 0.0051
-shapes = [(128, 8192), (256, 8192), (64, 8192), (128, 2048)]
+shapes = [(128, 8192), (256, 8192), (1024, 8192), (128, 2048)]
 if len(sys.argv) > 1:
     shapes = [tuple(int(x) for x in a.split(",")) for a in sys.argv[1:]]
 
@@ -40,13 +40,27 @@ for (B, D) in shapes:
     k = torch.randn(B, D, generator=g).to(dev)
     q = (0.7 * k + 0.7 * torch.randn(B, D, generator=g).to(dev))
     for _ in range(3):
-        r = ops.barlow_fwd_bwd(q, k, 1.0 / B, lam)
+        r = ops.barlow_fwd_bwd(q, k, 1.0 / B, lam, path="gram")
         le, ge = eager(q, k, B)
-    us = timed(lambda: ops.barlow_fwd_bwd(q, k, 1.0 / B, lam), 20)
+    us = timed(lambda: ops.barlow_fwd_bwd(q, k, 1.0 / B, lam, path="gram"), 20)
+    us_d = float("nan")
+    if B <= 256:
+        ops.barlow_fwd_bwd(q, k, 1.0 / B, lam, path="direct")
+        us_d = timed(lambda: ops.barlow_fwd_bwd(q, k, 1.0 / B, lam, path="direct"), 20)
+    # the same call replayed as a CUDA graph: without the host-side launch overhead of three/four short kernels
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=st):
+            for _ in range(10):
+                ops.barlow_fwd_bwd(q, k, 1.0 / B, lam, path="gram")
+    gr.replay()
+    us_g = timed(gr.replay, 5) / 10
     us_e = timed(lambda: eager(q, k, B), 5)
     torch.backends.cuda.matmul.allow_tf32 = True
     us_e_tf32 = timed(lambda: eager(q, k, B), 5)
     torch.backends.cuda.matmul.allow_tf32 = False
     rel = lambda x, y: ((x.double() - y.double()).norm() / y.double().norm()).item()
-    print(f"B={B} D={D}: fused {us:.1f} us = {4.0*B*D*D/us/1e6:.0f} TF/s | eager torch fp32 {us_e:.1f} us, tf32 {us_e_tf32:.1f} us "
-          f"| speed-up {us_e/us:.1f}x / {us_e_tf32/us:.1f}x | loss rel {rel(r['loss'], le):.2e} dq rel {rel(r['dq'], ge):.2e}", flush=True)
+    print(f"B={B} D={D}: gram {us:.1f} us (graph replay {us_g:.1f} us) | direct {us_d:.1f} us = {4.0*B*D*D/us_d/1e6:.0f} TF/s | eager torch fp32 "
+          f"{us_e:.1f} us, tf32 {us_e_tf32:.1f} us | speed-up of gram {us_e/us:.1f}x | loss rel {rel(r['loss'], le):.2e} "
+          f"dq rel {rel(r['dq'], ge):.2e}", flush=True)
