@@ -283,6 +283,12 @@ def test_other_pgd_attackers_match_reference(golden):
     d0, d1 = P.PGDAttack_nlvr2(dict(cfg, attack_idx=[False, True])).pgd_attack(mod, deepcopy(two))
     assert d0.abs().max().item() == 0.0
     close(d1, "nlvr2_only1_1")
+    # fused inner loss (bf16 tensor-core Gram path): same perturbation within the bf16 bar, signs agree
+    df = P.PGDAttack_bartlowtwins(cfg, fused_loss=True).pgd_attack(mod, deepcopy(one), k_modality=g.t("k_barlowtwins").to(DEV))
+    want = g.t("delta/barlowtwins")
+    assert (df.cpu() - want).abs().max().item() <= 2e-2 * eps
+    nz = want.abs() > 1e-3 * eps
+    assert (torch.sign(df.cpu())[nz] == torch.sign(want)[nz]).float().mean().item() >= 0.999
     # irtr: the reference body cannot run (undefined name); check the documented intent on its own terms
     k_txt = torch.nn.functional.normalize(torch.randn(ids.shape[0], 16, device=DEV), dim=1)
     mod.moco_head = MOCOHead(g.i("meta/hidden"), g.i("meta/hidden"), 16).to(DEV)
