@@ -142,6 +142,25 @@ int rmcl_infonce_fwd_bwd_diag(const void* q, rmcl_dtype q_dtype, const void* k, 
                               float* diag_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused key exchange + enqueue over NVLink peer memory (one node, one launch per rank).
+ * replaces: _concat_all_gather (objectives.py:226-235) followed by _dequeue_and_enqueue (objectives.py:238-248),
+ *           i.e. the pair ncclAllGather -> rmcl_enqueue.
+ * stage_ptrs_dev  device array [world] of pointers: every rank's staging buffer f32[2][world*B_local][C], peer mapped
+ *                 (e.g. torch.distributed._symmetric_memory: handle.buffer_ptrs_dev)
+ * flag_ptrs_dev   device array [world] of pointers: every rank's flag words u32[>=2], zero before the first call
+ * keys_local      f32[B_local][C], the caller's normalised keys
+ * epoch           1, 2, 3, ... — the number of this call on this exchange (selects the staging slot; the flag counts
+ *                 epoch*world arrivals)
+ * Every rank pushes its keys into every rank's staging slot, signals, waits until all keys of the step have arrived
+ * and then performs the identical enqueue into its own replica (queue / optional bf16 shadow / pointer as rmcl_enqueue).
+ * All ranks must make the same sequence of calls.
+ */
+int rmcl_gather_enqueue_p2p(void* const* stage_ptrs_dev, void* const* flag_ptrs_dev, const void* keys_local,
+                            void* queue, rmcl_dtype queue_dtype, void* shadow_bf16, int64_t lds,
+                            int64_t* ptr_dev, int rank, int world, int B_local, int C, int64_t K,
+                            int64_t ldq, unsigned int epoch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Fused Barlow-Twins cross-correlation loss, forward + backward.
  * replaces: vilt/modules/objectives.py:480-486 (text view), 506-512 (image view), 533-539 (both) and the
  *           attacker's inner loss attack/pgd_attack_vilt.py:219-224:

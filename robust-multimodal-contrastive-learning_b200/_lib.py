@@ -22,7 +22,7 @@ EXPORTS = (
     "rmcl_infonce_workspace_bytes", "rmcl_infonce_fwd_bwd", "rmcl_enqueue", "rmcl_pgd_workspace_bytes", "rmcl_pgd_step", "rmcl_step_host",
     "rmcl_profile_enable", "rmcl_profile_infonce_ms", "rmcl_enqueue_shadow", "rmcl_debug_tc_timeline",
     "rmcl_debug_tc_timeline_words", "rmcl_queue_stats", "rmcl_infonce_fwd_bwd_diag",
-    "rmcl_barlow_workspace_bytes", "rmcl_barlow_fwd_bwd",
+    "rmcl_barlow_workspace_bytes", "rmcl_barlow_fwd_bwd", "rmcl_gather_enqueue_p2p",
 )
 
 
@@ -81,6 +81,8 @@ def lib():
     L.rmcl_barlow_workspace_bytes.argtypes = [i32, i32]
     L.rmcl_barlow_fwd_bwd.restype = i32
     L.rmcl_barlow_fwd_bwd.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, f32, f32, f32, f32, f32, i32, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.rmcl_gather_enqueue_p2p.restype = i32
+    L.rmcl_gather_enqueue_p2p.argtypes = [vp, vp, vp, vp, i32, vp, i64, vp, i32, i32, i32, i32, i64, i64, u32, vp]
     L.rmcl_pgd_step.restype = i32
     L.rmcl_pgd_step.argtypes = [vp, i32, vp, i32, i32, i64, f32, f32, i32, vp, sz, vp]
     L.rmcl_pgd_workspace_bytes.restype = sz

@@ -102,3 +102,147 @@ extern "C" int rmcl_enqueue_shadow(void* queue, rmcl_dtype queue_dtype, void* sh
   RMCL_CHECK_ARG(shadow_bf16 != nullptr, "rmcl_enqueue_shadow: null shadow");
   return enqueue_impl(queue, queue_dtype, keys, keys_dtype, ptr_dev, B, C, K, ldq, shadow_bf16, lds, stream);
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Fused key exchange + enqueue over NVLink peer memory (single node): replaces the pair
+//   ncclAllGather(keys) -> enqueue_kernel
+// (objectives.py:226-235 + 244-248) by ONE launch per rank.  Every rank owns a two-slot staging buffer
+// [2][world*B][C] in peer-mapped (symmetric) memory and a flag word:
+//   1. push    my keys -> slot (epoch & 1), rows [rank*B, (rank+1)*B) of EVERY rank's staging buffer
+//              (16-byte stores straight into the peers' HBM over NVLink / NVSwitch);
+//   2. signal  when all my CTAs have pushed (local arrival counter), one system-scope release add on every
+//              rank's flag;
+//   3. wait    until my own flag shows epoch*world arrivals (acquire, system scope): all keys of this step are here;
+//   4. enqueue the world*B staged keys into my replica of the queue (+ bf16 shadow) — the transposing scatter of
+//              enqueue_kernel — and advance my pointer.
+// Two slots suffice: a peer can push step n+2 into slot n&1 only after it has seen my signal of step n+1, which I
+// send after my step-n enqueue has finished reading that slot.  All CTAs are co-resident (grid <= 2 per SM), so the
+// spin in step 3 cannot starve the pushes it waits for.
+namespace rmcl {
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_sys_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <typename TQ>
+__global__ void __launch_bounds__(256) gather_enqueue_p2p_kernel(float* const* __restrict__ stage_ptrs,
+                                                                 unsigned int* const* __restrict__ flag_ptrs,
+                                                                 const float* __restrict__ keys_local, TQ* __restrict__ queue,
+                                                                 long long* ptr_dev, int rank, int world, int B, int C,
+                                                                 long long K, long long ldq, __nv_bfloat16* __restrict__ shadow,
+                                                                 long long lds, unsigned int epoch) {
+  __shared__ float tile[32][33];
+  __shared__ long long s_ptr;
+  unsigned int* ptr_words = reinterpret_cast<unsigned int*>(ptr_dev);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int Bt = world * B;
+  const size_t slot = (size_t)(epoch & 1u) * Bt * C;
+  unsigned int* my_flags = flag_ptrs[rank];      // [0] arrivals from all ranks, [1] local CTA counter
+  if (threadIdx.x == 0) s_ptr = (long long)(*reinterpret_cast<volatile unsigned int*>(ptr_words));
+
+  // 1. push
+  const size_t n_local = (size_t)B * C;
+  const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gthreads = (size_t)gridDim.x * blockDim.x;
+  if ((n_local & 3) == 0) {
+    const size_t nv = n_local / 4;
+    const float4* src = reinterpret_cast<const float4*>(keys_local);
+    for (size_t v = gtid; v < nv * world; v += gthreads) {
+      const int peer = (int)(v / nv);
+      const size_t e = v - (size_t)peer * nv;
+      float4* dst = reinterpret_cast<float4*>(stage_ptrs[peer] + slot + (size_t)rank * n_local) + e;
+      *dst = __ldg(src + e);
+    }
+  } else {
+    for (size_t v = gtid; v < n_local * world; v += gthreads) {
+      const int peer = (int)(v / n_local);
+      const size_t e = v - (size_t)peer * n_local;
+      stage_ptrs[peer][slot + (size_t)rank * n_local + e] = keys_local[e];
+    }
+  }
+  // 2. signal (the last CTA of this rank to finish pushing tells everyone)
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(my_flags + 1, 1u) == gridDim.x - 1u) {
+      my_flags[1] = 0u;
+      __threadfence_system();
+      for (int peer = 0; peer < world; ++peer) red_release_sys_add(flag_ptrs[peer], 1u);
+    }
+    // 3. wait for every rank's keys of this step
+    const unsigned int target = epoch * (unsigned int)world;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(my_flags) < target) {
+      if (clock64() - t0 > 20000000000ll) __trap();     // ~10 s: a missing peer becomes an error, not a hang
+    }
+  }
+  __syncthreads();
+
+  // 4. enqueue the staged keys (tiles of 32 keys x 32 channels, persistent loop)
+  const float* staged = stage_ptrs[rank] + slot;
+  const long long ptr = s_ptr;
+  const int tiles_b = (Bt + 31) / 32, tiles_c = (C + 31) / 32;
+  for (int t = blockIdx.x; t < tiles_b * tiles_c; t += gridDim.x) {
+    const int b0 = (t % tiles_b) * 32, c0 = (t / tiles_b) * 32;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int b = b0 + ty + 8 * i, c = c0 + tx;
+      if (b < Bt && c < C) tile[ty + 8 * i][tx] = __ldcg(staged + (size_t)b * C + c);   // written by peers: bypass L1
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + ty + 8 * i, b = b0 + tx;
+      if (b < Bt && c < C) {
+        long long col = ptr + b;
+        if (col >= K) col -= K;
+        const float v = tile[tx][ty + 8 * i];
+        queue[(long long)c * ldq + col] = from_f32<TQ>(v);
+        if (shadow) shadow[(long long)c * lds + col] = __float2bfloat16_rn(to_f32(from_f32<TQ>(v)));
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(ptr_words + 1, 1u);
+    if (ticket == gridDim.x - 1u) *reinterpret_cast<volatile long long*>(ptr_dev) = (ptr + Bt) % K;
+  }
+}
+
+}  // namespace rmcl
+
+extern "C" int rmcl_gather_enqueue_p2p(void* const* stage_ptrs_dev, void* const* flag_ptrs_dev, const void* keys_local,
+                                       void* queue, rmcl_dtype queue_dtype, void* shadow_bf16, int64_t lds, int64_t* ptr_dev,
+                                       int rank, int world, int B_local, int C, int64_t K, int64_t ldq, unsigned int epoch,
+                                       void* stream) {
+  RMCL_CHECK_ARG(stage_ptrs_dev && flag_ptrs_dev && keys_local && queue && ptr_dev, "rmcl_gather_enqueue_p2p: null pointer");
+  RMCL_CHECK_ARG(world > 0 && rank >= 0 && rank < world && B_local > 0 && C > 0 && K > 0 && K < (1ll << 31) && ldq >= K,
+                 "rmcl_gather_enqueue_p2p: bad sizes rank=%d world=%d B=%d C=%d K=%lld", rank, world, B_local, C, (long long)K);
+  RMCL_CHECK_ARG(epoch > 0, "rmcl_gather_enqueue_p2p: epoch counts calls from 1");
+  RMCL_CHECK_ARG(rmcl::dtype_ok(queue_dtype), "rmcl_gather_enqueue_p2p: bad dtype");
+  const long long Bt = (long long)world * B_local;
+  RMCL_CHECK_ARG(Bt <= K && K % Bt == 0, "rmcl_gather_enqueue_p2p: queue length %lld is not a multiple of the gathered batch %lld",
+                 (long long)K, Bt);
+  RMCL_CHECK_ARG(!shadow_bf16 || lds >= K, "rmcl_gather_enqueue_p2p: lds < K");
+  const int sms = rmcl::sm_count();
+  if (sms <= 0) return RMCL_E_CUDA;
+  const long long tiles = ((Bt + 31) / 32) * ((C + 31) / 32);
+  long long grid = 2ll * sms;          // all CTAs must be resident at once (they spin on the flag): 2 x 256 threads per SM
+  if (grid > tiles) grid = tiles;
+  cudaStream_t s = (cudaStream_t)stream;
+  using bf16 = __nv_bfloat16;
+  if (queue_dtype == RMCL_F32)
+    rmcl::gather_enqueue_p2p_kernel<float><<<(unsigned)grid, 256, 0, s>>>(
+        (float* const*)stage_ptrs_dev, (unsigned int* const*)flag_ptrs_dev, (const float*)keys_local, (float*)queue,
+        reinterpret_cast<long long*>(ptr_dev), rank, world, B_local, C, K, ldq, (bf16*)shadow_bf16, lds, epoch);
+  else
+    rmcl::gather_enqueue_p2p_kernel<bf16><<<(unsigned)grid, 256, 0, s>>>(
+        (float* const*)stage_ptrs_dev, (unsigned int* const*)flag_ptrs_dev, (const float*)keys_local, (bf16*)queue,
+        reinterpret_cast<long long*>(ptr_dev), rank, world, B_local, C, K, ldq, (bf16*)shadow_bf16, lds, epoch);
+  RMCL_LAUNCH_OK("gather_enqueue_p2p_kernel");
+  return RMCL_OK;
+}

@@ -45,3 +45,40 @@ class Gather:
 
     def __call__(self, tensor):
         return concat_all_gather(tensor, self.group)
+
+
+class P2PKeyExchange:
+    """Key all-gather + enqueue as ONE kernel per rank over NVLink peer memory (include/rmcl_b200.h,
+    rmcl_gather_enqueue_p2p) instead of ncclAllGather followed by the enqueue kernel.
+
+    The staging buffers and flag words live in torch's symmetric memory (plumbing only: allocation, the IPC handle
+    exchange and the one-time barrier); the data path — pushes into the peers' HBM, the system-scope signal/wait,
+    the transposing scatter into the local queue replica — is the CUDA kernel.  Single node only."""
+
+    def __init__(self, B_local, C, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = dist.group.WORLD if group is None else group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.B, self.C = int(B_local), int(C)
+        self.stage = symm_mem.empty((2, self.world * self.B, self.C), dtype=torch.float32, device=device)
+        self.flags = symm_mem.empty((64,), dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self.stage_hdl = symm_mem.rendezvous(self.stage, group)
+        self.flags_hdl = symm_mem.rendezvous(self.flags, group)
+        torch.cuda.synchronize(device)
+        self.flags_hdl.barrier()              # every rank's flags are zero before anyone signals
+        self.epoch = 0
+
+    def enqueue_(self, queue, keys_local, ptr, shadow=None):
+        """In place: gathers every rank's ``keys_local`` [B_local, C] (fp32) and enqueues the world*B_local keys into
+        this rank's ``queue`` replica, advancing ``ptr`` — the reference's _dequeue_and_enqueue(keys) under DDP."""
+        from . import _lib, ops
+        if keys_local.dtype != torch.float32 or not keys_local.is_contiguous() or tuple(keys_local.shape) != (self.B, self.C):
+            raise ValueError("keys_local must be a contiguous fp32 [B_local, C] tensor")
+        self.epoch += 1
+        sh = None if shadow is None else (shadow.get(queue) if isinstance(shadow, ops.QueueShadow) else shadow)
+        rc = _lib.lib().rmcl_gather_enqueue_p2p(
+            self.stage_hdl.buffer_ptrs_dev, self.flags_hdl.buffer_ptrs_dev, keys_local.data_ptr(), queue.data_ptr(), ops._dt(queue),
+            None if sh is None else sh.data_ptr(), 0 if sh is None else sh.stride(0), ptr.data_ptr(), self.rank, self.world,
+            self.B, self.C, queue.shape[1], queue.stride(0), self.epoch, ops._stream())
+        _lib.check(rc, "rmcl_gather_enqueue_p2p")

@@ -99,3 +99,49 @@ def test_nccl_barlow_twins_gathered_world2():
         assert rel(r[i]["on"], ref["on_diag"]) < 1e-4 and rel(r[i]["offs"], 0.0051 * ref["off_diag"]) < 1e-4
         assert rel(r[i]["dq"], ref["dq"][i]) < 1e-2
     assert torch.equal(r[0]["on"], r[1]["on"])          # every rank evaluates the identical gathered problem
+
+
+def _p2p_worker(rank, world, init_file, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", init_method=f"file://{init_file}", rank=rank, world_size=world, device_id=dev)
+    import rmcl_b200
+    from rmcl_b200 import ops
+    from rmcl_b200.dist import P2PKeyExchange
+    B, C, K, steps = 32, 96, 512, 10                     # 10 steps of 64 keys: the ring wraps, both staging slots are reused
+    ex = P2PKeyExchange(B, C, dev)
+    queue = torch.randn(C, K, generator=torch.Generator().manual_seed(0)).to(dev)
+    ref_queue = queue.clone()
+    ptr = torch.tensor([K - 2 * world * B], dtype=torch.int64, device=dev)
+    ref_ptr = ptr.clone()
+    shadow = ops.QueueShadow()
+    shadow.get(queue)
+    g = torch.Generator().manual_seed(500 + rank)
+    for s in range(steps):
+        keys = torch.nn.functional.normalize(torch.randn(B, C, generator=g), dim=1).to(dev)
+        ex.enqueue_(queue, keys, ptr, shadow=shadow)                               # ONE kernel: push, signal, wait, enqueue
+        ops.enqueue_(ref_queue, rmcl_b200.concat_all_gather(keys), ref_ptr)        # NCCL all-gather + enqueue kernel
+        if rank == 0 and s % 3 == 0:
+            torch.cuda._sleep(20_000_000)                                          # skew the ranks: the flags must hold them together
+    torch.cuda.synchronize()
+    ok = torch.equal(queue, ref_queue) and int(ptr.item()) == int(ref_ptr.item())
+    ok_shadow = torch.equal(shadow.get(queue), queue.bfloat16())
+    torch.save({"queue": queue.cpu(), "ptr": int(ptr.item()), "ok": ok, "ok_shadow": ok_shadow}, os.path.join(out_dir, f"p{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_p2p_gather_enqueue_matches_nccl_path_world2():
+    """rmcl_gather_enqueue_p2p (one kernel per rank over NVLink peer memory) against the NCCL all-gather + enqueue pair:
+    queue, bf16 shadow and pointer bit-identical on every rank, over 10 skewed steps with ring wrap-around."""
+    import torch.multiprocessing as mp
+    world = 2
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_p2p_worker, args=(world, os.path.join(d, "pg"), d), nprocs=world, join=True)
+        r = [torch.load(os.path.join(d, f"p{i}.pt")) for i in range(world)]
+    for x in r:
+        assert x["ok"] and x["ok_shadow"]
+    assert torch.equal(r[0]["queue"], r[1]["queue"]) and r[0]["ptr"] == r[1]["ptr"]
