@@ -243,7 +243,22 @@ def run_cuda(args):
     side_stream = torch.cuda.Stream() if world > 1 else None
     ev_fwd, ev_side = torch.cuda.Event(), torch.cuda.Event()
 
-    def exchange_and_enqueue(keys):
+    # N>1 exchange: the fused peer-memory kernel (rmcl_gather_enqueue_p2p: push over NVLink, signal, wait, enqueue — one
+    # launch) or, if symmetric memory cannot be set up on this box / --exchange nccl, ncclAllGather + the enqueue kernel
+    p2p = None
+    if world > 1 and args.exchange in ("auto", "p2p"):
+        try:
+            from rmcl_b200.dist import P2PKeyExchange
+            p2p = P2PKeyExchange(B, C, dev)
+        except Exception as e:      # noqa: BLE001
+            if args.exchange == "p2p":
+                raise
+            sys.stderr.write(f"[bench] peer-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL all-gather\n")
+
+    def exchange_and_enqueue(keys, impl=None):
+        if world > 1 and p2p is not None and impl != "nccl":
+            p2p.enqueue_(queue, keys, ptr)
+            return
         if world > 1:
             dist.all_gather_into_tensor(gathered, keys)
             keys = gathered
@@ -325,6 +340,16 @@ def run_cuda(args):
         e2e_step()
     e2e_ms = timed(e2e_step, args.steps)
     e2e_value = world * args.steps / (e2e_ms * 1e-3)
+
+    # ---- N>1: the exchange step alone, both implementations, back to back on every rank
+    exchange_info = None
+    if world > 1:
+        keys_x = torch.nn.functional.normalize(torch.randn(B, C, device=dev, generator=g), dim=1)
+        exchange_info = {"impl": "p2p" if p2p is not None else "nccl"}
+        for impl in (("p2p", "nccl") if p2p is not None else ("nccl",)):
+            for _ in range(5):
+                exchange_and_enqueue(keys_x, impl)
+            exchange_info[f"us_{impl}"] = timed(lambda: exchange_and_enqueue(keys_x, impl), 50) / 50 * 1000
 
     # ---- per-kernel durations inside the step (events on the launching stream, same order, so
     #      each kernel sees the cache state it sees in the real step: the EMA's 1.34 GB of traffic
@@ -486,13 +511,15 @@ def run_cuda(args):
         "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, **CFG, "arithmetic": "InfoNCE: bf16 queue/q/k operands, fp32 accumulation and statistics; EMA: fp32 (bit-exact with ATen); enqueue: fp32 keys -> bf16 queue", "per_gpu_batch": B, "global_batch": world * B, "infonce_path": path,
-                   "parallelism": f"dp{world}", "streams": "single stream" if world == 1 else "key all-gather + enqueue on a side stream under the EMA, joined every step", "unit_of_value": "256-sample rank-steps per second, summed over ranks",
+                   "parallelism": f"dp{world}", "exchange": exchange_info,
+                   "streams": "single stream" if world == 1 else "key exchange + enqueue on a side stream under the EMA, joined every step", "unit_of_value": "256-sample rank-steps per second, summed over ranks",
                    "l2": "inputs larger than L2: each step streams 1.34 GB of parameters (EMA) between InfoNCE passes; L2 is 126 MB"},
         "roofline": roofline, "kernels": kernels,
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps, "api": "rmcl_step_host (C-ABI)" if world == 1 else "rmcl_b200.ops + NCCL all-gather"},
         "gpu_launches": 5 * args.steps, "launches_per_step": ["ema_multi_kernel", "infonce_prep_kernel",
-                                                             "infonce_simt_kernel|infonce_tc_kernel", "infonce_finalize_kernel", "enqueue_kernel"],
+                                                             "infonce_simt_kernel|infonce_tc_kernel", "infonce_finalize_kernel",
+                                                             "gather_enqueue_p2p_kernel" if p2p is not None else "enqueue_kernel"],
         "clocks": clocks, "loss": loss_val,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -511,6 +538,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--path", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N>1 key exchange: fused peer-memory kernel (p2p) or ncclAllGather + enqueue (nccl); auto = p2p if available")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pgd", action="store_true", help="skip the cfg3 PGD-kernel and cfg5 InfoNCE roofline lines")
     args = ap.parse_args()

@@ -70,7 +70,22 @@ def infonce_queue(pl_module):
 
 
 def dequeue_and_enqueue(pl_module, keys):
-    """objectives.py:238-248 — gather, skip on a short batch, ring-buffer write, pointer advance."""
+    """objectives.py:238-248 — gather, skip on a short batch, ring-buffer write, pointer advance.
+
+    ``pl_module.rmcl_p2p_exchange = True`` (single node, world > 1) replaces ncclAllGather + enqueue by the fused
+    peer-memory kernel (dist.P2PKeyExchange): every rank pushes its keys straight into the peers' staging slots over
+    NVLink, signals, waits and enqueues in one launch.  The short-batch skip is decided from the local batch size
+    (every rank sees the same ``per_step_bs`` and the same local batch under DistributedSampler with drop_last)."""
+    world = rdist.dist.get_world_size() if (rdist.dist.is_available() and rdist.dist.is_initialized()) else 1
+    if world > 1 and getattr(pl_module, "rmcl_p2p_exchange", False):
+        if not rdist.gathered_batch_matches(pl_module.per_step_bs, world * keys.shape[0]):
+            return
+        ex = pl_module.__dict__.get("_rmcl_p2p")
+        if ex is None or (ex.B, ex.C) != tuple(keys.shape):
+            ex = pl_module.__dict__["_rmcl_p2p"] = rdist.P2PKeyExchange(keys.shape[0], keys.shape[1], keys.device)
+        ex.enqueue_(pl_module.proj_queue, keys.detach().float().contiguous(), pl_module.proj_queue_ptr,
+                    shadow=_queue_shadow(pl_module))
+        return
     keys = rdist.concat_all_gather(keys)
     if not rdist.gathered_batch_matches(pl_module.per_step_bs, keys.shape[0]):
         return

@@ -27,11 +27,21 @@ ptr = torch.zeros(1, dtype=torch.int64, device=dev)
 q = torch.randn(B, C, device=dev, generator=g).bfloat16()
 k = torch.randn(B, C, device=dev, generator=g).bfloat16()
 gathered = torch.empty(world * B, C, dtype=torch.float32, device=dev)
+p2p = None
+if world > 1 and "--nccl" not in sys.argv:       # fused peer-memory exchange (rmcl_gather_enqueue_p2p) unless --nccl
+    try:
+        from rmcl_b200.dist import P2PKeyExchange
+        p2p = P2PKeyExchange(B, C, dev)
+    except Exception as e:      # noqa: BLE001
+        sys.stderr.write(f"peer-memory exchange unavailable ({e}); using NCCL all-gather\n")
 
 
 def step():
     r = ops.infonce_fwd_bwd(q, k, queue, tau, normalize_k=True, path="tcgen05", want=("loss", "dq", "k_hat"))
     keys = r["k_hat"]
+    if p2p is not None:
+        p2p.enqueue_(queue, keys, ptr)
+        return r
     if world > 1:
         dist.all_gather_into_tensor(gathered, keys)
         keys = gathered
@@ -67,7 +77,7 @@ else:
 if rank == 0:
     per = ms / steps
     print(json.dumps({"workload": "cfg5: InfoNCE fwd+bwd B512/GPU C768 K262144 bf16 (two-pass tcgen05) + key all-gather + enqueue",
-                      "n_gpus": world, "global_batch": world * B, "steps": steps, "ms_per_step": per,
+                      "n_gpus": world, "exchange": "p2p" if p2p is not None else ("nccl" if world > 1 else None), "global_batch": world * B, "steps": steps, "ms_per_step": per,
                       "value": world * steps / (ms * 1e-3), "unit": "rank-steps/s", "scaling": "weak",
                       "infonce_tflops_per_gpu": 4.0 * B * C * (K + 1) / (per * 1e-3) / 1e12,
                       "queues_identical_across_ranks": same, "ptr": int(ptr.item()), "loss": float(r["loss"])}), flush=True)
