@@ -4,8 +4,9 @@
 One *step* = one pass of the hot path over one 256-sample batch on one GPU:
     momentum EMA of the 161-tensor / 111.7 M-parameter ViLT-B/32 key encoder (fp32 master params)
  -> fused InfoNCE forward+backward of q[256,256] against [k ; queue[256,65536] bf16], tau 0.07
- -> (N>1) NCCL all-gather of the normalised keys
- -> ring-buffer enqueue of the gathered keys.
+ -> (N>1) exchange of the normalised keys + ring-buffer enqueue of the gathered keys: one fused kernel over NVLink peer
+    memory (rmcl_gather_enqueue_p2p), or ncclAllGather + the enqueue kernel (--exchange nccl / no symmetric memory)
+ -> (N=1) ring-buffer enqueue of the keys.
 Data-parallel weak scaling: every rank runs that step on its own batch, the queue is replicated
 and every rank enqueues the identical gathered keys; ``value`` = (rank-steps all ranks completed)
 / (max-over-ranks device time).
@@ -14,7 +15,8 @@ and every rank enqueues the identical gathered keys; ``value`` = (rank-steps all
     python bench.py --impl reference [...]                          # reference arithmetic on host cores
 
 The JSON line carries ``roofline`` (dominant kernel, CUDA-event timed inside this run),
-``kernels`` (every kernel of the step, same arithmetic), ``cpu_baseline`` (oracle port timed on
+``kernels`` (every kernel of the step, same arithmetic; at N=1 also the path's other kernels at their BASELINE shapes:
+cfg3 PGD updates, the cfg4-shaped and cfg5 InfoNCE calls, the Barlow-Twins loss), ``cpu_baseline`` (oracle port timed on
 this box's host cores, rank 0 at N=1), ``e2e`` (host buffers -> C-ABI ``rmcl_step_host`` -> host
 results, copies inside the timed region), ``clocks`` and ``gpu_launches``.
 Only the cpu_baseline / --impl reference legs touch oracle/ (as the thing being timed there is
@@ -472,6 +474,28 @@ def run_cuda(args):
                                             "launches": ["infonce_prep_kernel", "infonce_s_kernel", "infonce_pv_kernel",
                                                          "infonce_finalize_kernel"]}
         del q5, k5, queue5
+    # ---- cfg4 per-GPU InfoNCE shape (B128 C128 K65536 bf16): arithmetic intensity 2*B = 256 flop per queue byte puts it
+    #      at the HBM/tensor ridge; whole call (prep + tcgen05 partial + finalize) by CUDA-graph replay over queue copies
+    #      larger than L2, so every call streams its 16.8 MB queue from HBM
+    if world == 1 and not args.no_pgd and path in ("auto", "tcgen05"):
+        B4, C4, K4 = 128, 128, 65536
+        g4 = torch.Generator(device=dev).manual_seed(4)
+        q4 = torch.randn(B4, C4, device=dev, generator=g4).bfloat16()
+        k4 = torch.randn(B4, C4, device=dev, generator=g4).bfloat16()
+        queues4 = [torch.nn.functional.normalize(torch.randn(C4, K4, device=dev, generator=g4), dim=0).bfloat16() for _ in range(12)]
+        for qq in queues4[:2]:
+            ops.infonce_fwd_bwd(q4, k4, qq, tau, normalize_k=True, path=path, want=("loss", "dq", "k_hat"))
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for j in range(48):
+                ops.infonce_fwd_bwd(q4, k4, queues4[j % 12], tau, normalize_k=True, path=path, want=("loss", "dq", "k_hat"))
+        graph.replay()
+        ms4 = min(timed(graph.replay, 1) for _ in range(5)) / 48
+        kernels["infonce_cfg4_b128_c128_call"] = {"bound": "hbm", "achieved": C4 * K4 * 2 / (ms4 * 1e-3) / 1e9, "peak": pk_peak["hbm"],
+                                                  "unit": "GB/s", "frac": C4 * K4 * 2 / (ms4 * 1e-3) / 1e9 / pk_peak["hbm"], "ms": ms4,
+                                                  "tflops": 4.0 * B4 * C4 * (K4 + 1) / (ms4 * 1e-3) / 1e12, "traffic": None,
+                                                  "shape": [B4, C4, K4], "timing": "CUDA graph of 48 whole calls over 12 queue copies (> L2)"}
+        del graph, queues4
     # ---- Barlow-Twins objective at the reference's size (batch 128, projector 8192) and at an 8-GPU gathered batch (1024):
     #      Gram formulation (default; 6*Bg^2*D flop, bound by reading q, k once and four short launches) and the direct
     #      D x D kernel (4*B*D^2 flop, tensor bound); each timed as one call = prep + tcgen05 kernel(s) + finalize
