@@ -147,10 +147,10 @@ int rmcl_infonce_fwd_bwd_diag(const void* q, rmcl_dtype q_dtype, const void* k, 
  *           i.e. the pair ncclAllGather -> rmcl_enqueue.
  * stage_ptrs_dev  device array [world] of pointers: every rank's staging buffer f32[2][world*B_local][C], peer mapped
  *                 (e.g. torch.distributed._symmetric_memory: handle.buffer_ptrs_dev)
- * flag_ptrs_dev   device array [world] of pointers: every rank's flag words u32[>=2], zero before the first call
+ * flag_ptrs_dev   device array [world] of pointers: every rank's flag words u32[>=3], zero before the first call
+ *                 ([0] arrivals, [1] local CTA counter, [2] completed calls = the epoch that selects the staging slot;
+ *                 all kept on the device, so the launch can be captured in a CUDA graph)
  * keys_local      f32[B_local][C], the caller's normalised keys
- * epoch           1, 2, 3, ... — the number of this call on this exchange (selects the staging slot; the flag counts
- *                 epoch*world arrivals)
  * Every rank pushes its keys into every rank's staging slot, signals, waits until all keys of the step have arrived
  * and then performs the identical enqueue into its own replica (queue / optional bf16 shadow / pointer as rmcl_enqueue).
  * All ranks must make the same sequence of calls.
@@ -158,7 +158,7 @@ int rmcl_infonce_fwd_bwd_diag(const void* q, rmcl_dtype q_dtype, const void* k, 
 int rmcl_gather_enqueue_p2p(void* const* stage_ptrs_dev, void* const* flag_ptrs_dev, const void* keys_local,
                             void* queue, rmcl_dtype queue_dtype, void* shadow_bf16, int64_t lds,
                             int64_t* ptr_dev, int rank, int world, int B_local, int C, int64_t K,
-                            int64_t ldq, unsigned int epoch, void* stream);
+                            int64_t ldq, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused Barlow-Twins cross-correlation loss, forward + backward.

@@ -82,7 +82,7 @@ def lib():
     L.rmcl_barlow_fwd_bwd.restype = i32
     L.rmcl_barlow_fwd_bwd.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, f32, f32, f32, f32, f32, i32, vp, vp, vp, vp, vp, vp, sz, vp]
     L.rmcl_gather_enqueue_p2p.restype = i32
-    L.rmcl_gather_enqueue_p2p.argtypes = [vp, vp, vp, vp, i32, vp, i64, vp, i32, i32, i32, i32, i64, i64, u32, vp]
+    L.rmcl_gather_enqueue_p2p.argtypes = [vp, vp, vp, vp, i32, vp, i64, vp, i32, i32, i32, i32, i64, i64, vp]
     L.rmcl_pgd_step.restype = i32
     L.rmcl_pgd_step.argtypes = [vp, i32, vp, i32, i32, i64, f32, f32, i32, vp, sz, vp]
     L.rmcl_pgd_workspace_bytes.restype = sz

@@ -112,7 +112,8 @@ extern "C" int rmcl_enqueue_shadow(void* queue, rmcl_dtype queue_dtype, void* sh
 //              (16-byte stores straight into the peers' HBM over NVLink / NVSwitch);
 //   2. signal  when all my CTAs have pushed (local arrival counter), one system-scope release add on every
 //              rank's flag;
-//   3. wait    until my own flag shows epoch*world arrivals (acquire, system scope): all keys of this step are here;
+//   3. wait    until my own flag shows epoch*world arrivals (acquire, system scope): all keys of this step are here
+//              (epoch = number of this call, kept in the rank's own flag words);
 //   4. enqueue the world*B staged keys into my replica of the queue (+ bf16 shadow) — the transposing scatter of
 //              enqueue_kernel — and advance my pointer.
 // Two slots suffice: a peer can push step n+2 into slot n&1 only after it has seen my signal of step n+1, which I
@@ -135,15 +136,23 @@ __global__ void __launch_bounds__(256) gather_enqueue_p2p_kernel(float* const* _
                                                                  const float* __restrict__ keys_local, TQ* __restrict__ queue,
                                                                  long long* ptr_dev, int rank, int world, int B, int C,
                                                                  long long K, long long ldq, __nv_bfloat16* __restrict__ shadow,
-                                                                 long long lds, unsigned int epoch) {
+                                                                 long long lds) {
   __shared__ float tile[32][33];
   __shared__ long long s_ptr;
+  __shared__ unsigned int s_epoch;
   unsigned int* ptr_words = reinterpret_cast<unsigned int*>(ptr_dev);
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int Bt = world * B;
+  unsigned int* my_flags = flag_ptrs[rank];      // [0] arrivals from all ranks, [1] local CTA counter, [2] completed calls
+  if (threadIdx.x == 0) {
+    s_ptr = (long long)(*reinterpret_cast<volatile unsigned int*>(ptr_words));
+    // the call number lives on the device (advanced by the last CTA at the very end, after every CTA has read it), so the
+    // launch carries no host-side counter and can be captured in a CUDA graph
+    s_epoch = *reinterpret_cast<volatile unsigned int*>(my_flags + 2) + 1u;
+  }
+  __syncthreads();
+  const unsigned int epoch = s_epoch;
   const size_t slot = (size_t)(epoch & 1u) * Bt * C;
-  unsigned int* my_flags = flag_ptrs[rank];      // [0] arrivals from all ranks, [1] local CTA counter
-  if (threadIdx.x == 0) s_ptr = (long long)(*reinterpret_cast<volatile unsigned int*>(ptr_words));
 
   // 1. push
   const size_t n_local = (size_t)B * C;
@@ -209,7 +218,10 @@ __global__ void __launch_bounds__(256) gather_enqueue_p2p_kernel(float* const* _
   }
   if (threadIdx.x == 0) {
     const unsigned int ticket = atomicAdd(ptr_words + 1, 1u);
-    if (ticket == gridDim.x - 1u) *reinterpret_cast<volatile long long*>(ptr_dev) = (ptr + Bt) % K;
+    if (ticket == gridDim.x - 1u) {
+      *reinterpret_cast<volatile unsigned int*>(my_flags + 2) = epoch;
+      *reinterpret_cast<volatile long long*>(ptr_dev) = (ptr + Bt) % K;
+    }
   }
 }
 
@@ -217,12 +229,10 @@ __global__ void __launch_bounds__(256) gather_enqueue_p2p_kernel(float* const* _
 
 extern "C" int rmcl_gather_enqueue_p2p(void* const* stage_ptrs_dev, void* const* flag_ptrs_dev, const void* keys_local,
                                        void* queue, rmcl_dtype queue_dtype, void* shadow_bf16, int64_t lds, int64_t* ptr_dev,
-                                       int rank, int world, int B_local, int C, int64_t K, int64_t ldq, unsigned int epoch,
-                                       void* stream) {
+                                       int rank, int world, int B_local, int C, int64_t K, int64_t ldq, void* stream) {
   RMCL_CHECK_ARG(stage_ptrs_dev && flag_ptrs_dev && keys_local && queue && ptr_dev, "rmcl_gather_enqueue_p2p: null pointer");
   RMCL_CHECK_ARG(world > 0 && rank >= 0 && rank < world && B_local > 0 && C > 0 && K > 0 && K < (1ll << 31) && ldq >= K,
                  "rmcl_gather_enqueue_p2p: bad sizes rank=%d world=%d B=%d C=%d K=%lld", rank, world, B_local, C, (long long)K);
-  RMCL_CHECK_ARG(epoch > 0, "rmcl_gather_enqueue_p2p: epoch counts calls from 1");
   RMCL_CHECK_ARG(rmcl::dtype_ok(queue_dtype), "rmcl_gather_enqueue_p2p: bad dtype");
   const long long Bt = (long long)world * B_local;
   RMCL_CHECK_ARG(Bt <= K && K % Bt == 0, "rmcl_gather_enqueue_p2p: queue length %lld is not a multiple of the gathered batch %lld",
@@ -238,11 +248,11 @@ extern "C" int rmcl_gather_enqueue_p2p(void* const* stage_ptrs_dev, void* const*
   if (queue_dtype == RMCL_F32)
     rmcl::gather_enqueue_p2p_kernel<float><<<(unsigned)grid, 256, 0, s>>>(
         (float* const*)stage_ptrs_dev, (unsigned int* const*)flag_ptrs_dev, (const float*)keys_local, (float*)queue,
-        reinterpret_cast<long long*>(ptr_dev), rank, world, B_local, C, K, ldq, (bf16*)shadow_bf16, lds, epoch);
+        reinterpret_cast<long long*>(ptr_dev), rank, world, B_local, C, K, ldq, (bf16*)shadow_bf16, lds);
   else
     rmcl::gather_enqueue_p2p_kernel<bf16><<<(unsigned)grid, 256, 0, s>>>(
         (float* const*)stage_ptrs_dev, (unsigned int* const*)flag_ptrs_dev, (const float*)keys_local, (bf16*)queue,
-        reinterpret_cast<long long*>(ptr_dev), rank, world, B_local, C, K, ldq, (bf16*)shadow_bf16, lds, epoch);
+        reinterpret_cast<long long*>(ptr_dev), rank, world, B_local, C, K, ldq, (bf16*)shadow_bf16, lds);
   RMCL_LAUNCH_OK("gather_enqueue_p2p_kernel");
   return RMCL_OK;
 }

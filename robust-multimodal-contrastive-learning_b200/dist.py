@@ -67,7 +67,6 @@ class P2PKeyExchange:
         self.flags_hdl = symm_mem.rendezvous(self.flags, group)
         torch.cuda.synchronize(device)
         self.flags_hdl.barrier()              # every rank's flags are zero before anyone signals
-        self.epoch = 0
 
     def enqueue_(self, queue, keys_local, ptr, shadow=None):
         """In place: gathers every rank's ``keys_local`` [B_local, C] (fp32) and enqueues the world*B_local keys into
@@ -75,10 +74,9 @@ class P2PKeyExchange:
         from . import _lib, ops
         if keys_local.dtype != torch.float32 or not keys_local.is_contiguous() or tuple(keys_local.shape) != (self.B, self.C):
             raise ValueError("keys_local must be a contiguous fp32 [B_local, C] tensor")
-        self.epoch += 1
         sh = None if shadow is None else (shadow.get(queue) if isinstance(shadow, ops.QueueShadow) else shadow)
         rc = _lib.lib().rmcl_gather_enqueue_p2p(
             self.stage_hdl.buffer_ptrs_dev, self.flags_hdl.buffer_ptrs_dev, keys_local.data_ptr(), queue.data_ptr(), ops._dt(queue),
             None if sh is None else sh.data_ptr(), 0 if sh is None else sh.stride(0), ptr.data_ptr(), self.rank, self.world,
-            self.B, self.C, queue.shape[1], queue.stride(0), self.epoch, ops._stream())
+            self.B, self.C, queue.shape[1], queue.stride(0), ops._stream())
         _lib.check(rc, "rmcl_gather_enqueue_p2p")
