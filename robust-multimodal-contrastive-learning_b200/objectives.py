@@ -51,14 +51,28 @@ def momentum_update_key_encoder(pl_module):
 
 
 def _queue_shadow(pl_module):
-    """The module's bf16 queue shadow (ops.QueueShadow) if it opted in with ``rmcl_bf16_queue=True``
-    — the analogue of running the reference under Lightning ``precision=16`` — else None."""
-    if not getattr(pl_module, "rmcl_bf16_queue", False):
+    """The module's bf16 queue shadow (ops.QueueShadow), or None for the fp32 buffer.
+
+    ``pl_module.rmcl_bf16_queue``: True / False decide explicitly; unset (None) follows the precision the step runs in —
+    under autocast (Lightning ``precision=16``, how the reference trains: its einsum then runs in half precision with an
+    fp32 cross-entropy, objectives.py:272-274) the shadow and hence the tcgen05 kernels are used, in full precision the
+    fp32 buffer and the fp32 parity kernel."""
+    opt = getattr(pl_module, "rmcl_bf16_queue", None)
+    if opt is None:
+        opt = torch.is_autocast_enabled()
+    if not opt:
         return None
     sh = pl_module.__dict__.get("_rmcl_queue_shadow")
     if sh is None:
         sh = pl_module.__dict__["_rmcl_queue_shadow"] = ops.QueueShadow()
     return sh
+
+
+def _enqueue_shadow(pl_module):
+    """The shadow the enqueue must keep current: an existing one always (whatever precision this particular call runs
+    in — a stale shadow would go unnoticed, the kernels write through raw pointers), else what _queue_shadow decides."""
+    sh = pl_module.__dict__.get("_rmcl_queue_shadow")
+    return sh if sh is not None else _queue_shadow(pl_module)
 
 
 def infonce_queue(pl_module):
@@ -84,12 +98,12 @@ def dequeue_and_enqueue(pl_module, keys):
         if ex is None or (ex.B, ex.C) != tuple(keys.shape):
             ex = pl_module.__dict__["_rmcl_p2p"] = rdist.P2PKeyExchange(keys.shape[0], keys.shape[1], keys.device)
         ex.enqueue_(pl_module.proj_queue, keys.detach().float().contiguous(), pl_module.proj_queue_ptr,
-                    shadow=_queue_shadow(pl_module))
+                    shadow=_enqueue_shadow(pl_module))
         return
     keys = rdist.concat_all_gather(keys)
     if not rdist.gathered_batch_matches(pl_module.per_step_bs, keys.shape[0]):
         return
-    ops.enqueue_(pl_module.proj_queue, keys, pl_module.proj_queue_ptr, shadow=_queue_shadow(pl_module))
+    ops.enqueue_(pl_module.proj_queue, keys, pl_module.proj_queue_ptr, shadow=_enqueue_shadow(pl_module))
 
 
 def compute_pgd(pl_module, batch, loss_name, k_modality=None):

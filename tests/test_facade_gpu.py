@@ -185,6 +185,26 @@ def test_facade_bf16_queue_takes_tcgen05_path(golden):
     assert mod.moco_head.projector[0].weight.grad is not None
 
 
+def test_facade_autocast_selects_the_bf16_shadow(golden):
+    """Under autocast (Lightning precision=16, the reference's training mode) the fp32 queue buffer stays the checkpointed
+    state but the main-step InfoNCE reads its bf16 shadow (tcgen05 path); every enqueue keeps the shadow current, also
+    when a later call runs in full precision."""
+    import rmcl_b200
+    g = golden("ref_facade_c128")
+    mod = TinyModule(g, "auto").to(DEV).train()
+    assert mod.proj_queue.dtype == torch.float32 and "_rmcl_queue_shadow" not in mod.__dict__
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ret = rmcl_b200.compute_moco_contrastive(mod, _batch(g, 0))
+    ret["moco_loss"].backward()
+    sh = mod.__dict__["_rmcl_queue_shadow"]
+    assert torch.equal(sh.get(mod.proj_queue), mod.proj_queue.bfloat16())            # shadow == bf16(queue) after the enqueue
+    _close(ret["moco_loss"], g.np("step0/ret/moco_loss"), 5e-2, "autocast moco_loss")  # bf16 backbone + bf16 InfoNCE operands
+    assert mod.proj_queue_ptr.item() == g.i("step0/ptr_after")
+    mod.zero_grad()
+    rmcl_b200.compute_moco_contrastive(mod, _batch(g, 1))["moco_loss"].backward()      # full precision: fp32 buffer, fp32 kernel
+    assert torch.equal(sh.get(mod.proj_queue), mod.proj_queue.bfloat16())            # ... and the shadow followed
+
+
 def test_moco_module_api(golden):
     """MoCo sketch API (MoCo/MoCo_RMCL.py): method names, two enqueues per step, pointer advance."""
     import rmcl_b200
