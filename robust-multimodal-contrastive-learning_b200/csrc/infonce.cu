@@ -192,7 +192,25 @@ __global__ void __launch_bounds__(kFinThreads, 2) infonce_finalize_kernel(
   // batch of loads (column ct, splits grp, grp+G, ...) in flight before waiting for the statistics.
   constexpr int kPre = 8;
   float pre[kPre];
-  {
+  // bf16 partials (tcgen05 kernels; C % 8 == 0): 16-byte loads, 8 columns per thread, C/8 threads per pass over a row and
+  // kFinThreads / (C/8) split groups, so that a thread needs only ~splits/groups loads (5 at cfg2) and all of them are in
+  // flight before the statistics barrier.  (The scalar path below issued 37 two-byte loads per thread in 5 dependent rounds.)
+  constexpr bool kVec = (sizeof(TP) == 2);
+  constexpr int kPreV = 6;
+  uint4 prev[kVec ? kPreV : 1];
+  const int vpr = C >> 3;                           // threads per row pass
+  const int vgroups = kVec ? kFinThreads / vpr : 1;  // split groups
+  const int vg = tid / vpr, vc = tid - vg * vpr;
+  const bool vactive = kVec && want_grad && vg < vgroups;
+  if (kVec) {
+    const uint4* prow4 = reinterpret_cast<const uint4*>(po + (size_t)row * C) + vc;
+    const size_t sstride4 = (size_t)B * C / 8;
+#pragma unroll
+    for (int u = 0; u < kPreV; ++u) {
+      const int s = vg + u * vgroups;
+      prev[u] = (vactive && s < splits) ? __ldcs(prow4 + (size_t)s * sstride4) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  } else {
     const TP* pcol = po + (size_t)row * C + ct;
     const size_t sstride = (size_t)B * C;
 #pragma unroll
@@ -271,6 +289,32 @@ __global__ void __launch_bounds__(kFinThreads, 2) infonce_finalize_kernel(
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     const size_t sstride = (size_t)B * C;
     const TP* prow = po + (size_t)row * C;
+    if (kVec) {
+      // 8 columns per thread, weighted sum over this group's splits, then one row of partial sums per group in shared memory
+      float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (vactive) {
+        const uint4* prow4 = reinterpret_cast<const uint4*>(prow) + vc;
+        const size_t sstride4 = sstride / 8;
+        auto fma8 = [&](const uint4& u, float w) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(h[j]);
+            a8[2 * j] = fmaf(f.x, w, a8[2 * j]);
+            a8[2 * j + 1] = fmaf(f.y, w, a8[2 * j + 1]);
+          }
+        };
+#pragma unroll
+        for (int u = 0; u < kPreV; ++u) {
+          const int sp = vg + u * vgroups;
+          if (sp < splits) fma8(prev[u], sw[sp]);
+        }
+        for (int sp = vg + kPreV * vgroups; sp < splits; sp += vgroups) fma8(__ldcs(prow4 + (size_t)sp * sstride4), sw[sp]);
+        float4* dst = reinterpret_cast<float4*>(part + (size_t)vg * C + vc * 8);
+        dst[0] = make_float4(a8[0], a8[1], a8[2], a8[3]);
+        dst[1] = make_float4(a8[4], a8[5], a8[6], a8[7]);
+      }
+    } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int c = ct + 256 * i;
@@ -296,6 +340,7 @@ __global__ void __launch_bounds__(kFinThreads, 2) infonce_finalize_kernel(
         if (grp > 0) part[(size_t)(grp - 1) * C + c] = acc[i];
       }
     }
+    }
     __syncthreads();
     if (grp == 0) {
       const float o_scale = s_stats[0], pm1 = s_stats[1];
@@ -309,8 +354,13 @@ __global__ void __launch_bounds__(kFinThreads, 2) infonce_finalize_kernel(
         qh[i] = 0.f;
         if (c < C) {
           float a = acc[i];
+          if (kVec) {
+            a = 0.f;
+            for (int g = 0; g < vgroups; ++g) a += part[(size_t)g * C + c];     // fixed order: deterministic
+          } else {
 #pragma unroll
-          for (int g = 1; g < kFinGroups; ++g) a += part[(size_t)(g - 1) * C + c];
+            for (int g = 1; g < kFinGroups; ++g) a += part[(size_t)(g - 1) * C + c];
+          }
           const float kh = round_if(i == 0 ? kh_pre : k_hat[(size_t)row * C + c], bf16_mode);
           qh[i] = (i == 0) ? qh_pre : q_hat[(size_t)row * C + c];
           dqh[i] = gs * fmaf(a, o_scale, pm1 * kh);
@@ -514,7 +564,9 @@ static int infonce_impl(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_d
   RMCL_PROF_MARK(2);
   if (partial_only) return RMCL_OK;
 
-  const size_t fin_smem = ((size_t)((p.splits + 3) & ~3) + (size_t)(kFinGroups - 1) * C) * sizeof(float);
+  // merge weights + per-group partial rows: (groups-1) rows of the scalar path, kFinThreads/(C/8) rows of the 16-byte path
+  const size_t fin_rows = tc ? (size_t)(kFinThreads / (C / 8)) : (size_t)(kFinGroups - 1);
+  const size_t fin_smem = ((size_t)((p.splits + 3) & ~3) + fin_rows * C) * sizeof(float);
   if (tc) {
     RMCL_CUDA_OK(launch_pdl(infonce_finalize_kernel<__nv_bfloat16>, dim3(B), dim3(kFinThreads), fin_smem, s,
         B, C, p.splits, 1.f / tau, loss_scale / (float)B, loss_scale, bf16_mode, want_grad, (const float*)(ws + p.off_qhat),
