@@ -128,6 +128,23 @@ def _p2p_worker(rank, world, init_file, out_dir):
     torch.cuda.synchronize()
     ok = torch.equal(queue, ref_queue) and int(ptr.item()) == int(ref_ptr.item())
     ok_shadow = torch.equal(shadow.get(queue), queue.bfloat16())
+    # the facade's opt-in (pl_module.rmcl_p2p_exchange): same result as its NCCL branch, short batches skipped on both
+    from rmcl_b200 import objectives
+
+    class Mod:
+        pass
+    a, b = Mod(), Mod()
+    for m_, p2p in ((a, True), (b, False)):
+        m_.proj_queue, m_.proj_queue_ptr = queue.clone(), ptr.clone()
+        m_.per_step_bs, m_.rmcl_p2p_exchange, m_.rmcl_bf16_queue = world * B, p2p, False
+    for s in range(3):
+        keys = torch.nn.functional.normalize(torch.randn(B, C, generator=g), dim=1).to(dev)
+        for m_ in (a, b):
+            m_.per_step_bs = world * B + (1 if s == 1 else 0)          # step 1: gathered batch != per_step_bs -> skipped
+            objectives.dequeue_and_enqueue(m_, keys)
+    torch.cuda.synchronize()
+    ok = ok and torch.equal(a.proj_queue, b.proj_queue) and int(a.proj_queue_ptr.item()) == int(b.proj_queue_ptr.item())
+    ok = ok and int(a.proj_queue_ptr.item()) == (int(ptr.item()) + 2 * world * B) % K
     torch.save({"queue": queue.cpu(), "ptr": int(ptr.item()), "ok": ok, "ok_shadow": ok_shadow}, os.path.join(out_dir, f"p{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
