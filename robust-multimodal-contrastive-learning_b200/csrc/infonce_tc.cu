@@ -82,11 +82,13 @@ constexpr int kTimelineTiles = 40;
 constexpr int kTimelineHead = 8 + 8 * kTimelineTiles;
 constexpr int kTimelineCtas = 1024;
 constexpr int kTimelineWords = kTimelineHead + 2 * kTimelineCtas;
+#if defined(RMCL_TC_TIMELINE) && RMCL_TC_TIMELINE
 __device__ __forceinline__ long long global_ns() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+#endif
 // Compiled out of the product build (RMCL_TC_TIMELINE=0): even never-taken, the per-lane predicate in
 // front of the elect-guarded issue blocks cost ~2 us per launch.  tools/tc_timeline.py builds its own
 // instrumented copy of the library.
@@ -135,8 +137,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const int n_tiles = (int)((k_end - k_begin + TN - 1) / TN);
   long long* tl = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) ? timeline : nullptr;   // lane 0 of every warp of CTA (0,0)
   if (tid == 0) tl_stamp(tl, 0);
-  const int cta_linear = blockIdx.y * gridDim.x + blockIdx.x;
 #if RMCL_TC_TIMELINE
+  const int cta_linear = blockIdx.y * gridDim.x + blockIdx.x;
   if (timeline != nullptr && tid == 0 && cta_linear < kTimelineCtas) timeline[kTimelineHead + 2 * cta_linear] = global_ns();
 #endif
 

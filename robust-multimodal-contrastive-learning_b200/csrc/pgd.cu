@@ -40,7 +40,10 @@ namespace rmcl {
 #endif
 constexpr int kPgdThreads = 256;
 constexpr int kPgdChunkBytes = RMCL_PGD_CHUNK_KB * 1024;                 // per operand per work item
-constexpr long long kPgdBatchBytes = 24ll * 1024 * 1024;  // gradient bytes per batch kept L2-resident
+#ifndef RMCL_PGD_BATCH_MB
+#define RMCL_PGD_BATCH_MB 24
+#endif
+constexpr long long kPgdBatchBytes = (long long)RMCL_PGD_BATCH_MB * 1024 * 1024;  // gradient bytes per batch kept L2-resident
 
 __device__ __forceinline__ float block_reduce(float v, bool is_max, float* red /*[32]*/) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
