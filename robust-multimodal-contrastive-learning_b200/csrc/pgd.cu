@@ -43,7 +43,15 @@ constexpr int kPgdChunkBytes = RMCL_PGD_CHUNK_KB * 1024;                 // per 
 #ifndef RMCL_PGD_BATCH_MB
 #define RMCL_PGD_BATCH_MB 24
 #endif
-constexpr long long kPgdBatchBytes = (long long)RMCL_PGD_BATCH_MB * 1024 * 1024;  // gradient bytes per batch kept L2-resident
+#ifndef RMCL_PGD_BATCH_MB_L2
+#define RMCL_PGD_BATCH_MB_L2 40
+#endif
+// bytes per batch kept L2-resident between the two phases.  Same-box sweep (tools/pgd_time.py): batches smaller than the
+// ~740 resident CTAs' worth of work leave CTAs spinning on norms (8 MB: 199 us, 12 MB: 152 us, 24 MB: 136 us, 40 MB: 142 us
+// for the pixel ref_linf case); the L2-projection mode keeps g AND delta resident, i.e. half as many samples per byte, and
+// wants the larger batch (24 MB: 176 us, 40 MB: 168 us).
+constexpr long long kPgdBatchBytes = (long long)RMCL_PGD_BATCH_MB * 1024 * 1024;
+constexpr long long kPgdBatchBytesL2 = (long long)RMCL_PGD_BATCH_MB_L2 * 1024 * 1024;
 
 __device__ __forceinline__ float block_reduce(float v, bool is_max, float* red /*[32]*/) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
@@ -407,7 +415,7 @@ static int pgd_make_plan(int B, long long N, float lr, float eps, int mode, size
   p->n_sums = (mode == RMCL_PGD_L2 && eps > 0.f) ? 3 : 1;
   // bytes per sample that must survive in L2 between the two phases
   const long long resident = N * (long long)(gsize + (p->n_sums == 3 ? dsize : 0));
-  long long batch = kPgdBatchBytes / resident;
+  long long batch = (p->n_sums == 3 ? kPgdBatchBytesL2 : kPgdBatchBytes) / resident;
   if (batch < 1) batch = 1;
   if (batch > B) batch = B;
   p->batch = (int)batch;
