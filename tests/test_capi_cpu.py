@@ -103,3 +103,42 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "rmcl_oracle" not in src and "ref_harness" not in src, f
+
+
+def _declared_prototypes():
+    """name -> number of parameters, parsed from the (comment-stripped) header."""
+    text = open(os.path.join(ROOT, "include", "rmcl_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(rmcl_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        params = m.group(2).strip()
+        out[m.group(1)] = 0 if params in ("", "void") else params.count(",") + 1
+    return out
+
+
+def test_ctypes_signatures_match_the_header(L):
+    """ABI drift guard: every binding in rmcl_b200/_lib.py passes exactly as many arguments as include/rmcl_b200.h declares."""
+    protos = _declared_prototypes()
+    checked = 0
+    for name, n_params in protos.items():
+        fn = getattr(L, name)
+        if fn.argtypes is None:
+            continue
+        assert len(fn.argtypes) == n_params, f"{name}: header declares {n_params} parameters, binding passes {len(fn.argtypes)}"
+        checked += 1
+    assert checked >= 12
+
+
+def test_new_entry_points_validate_arguments_without_gpu(L):
+    one = C.c_void_p(0x1000)
+    # Barlow Twins: local rows must lie inside the gathered batch; path must be known
+    assert L.rmcl_barlow_fwd_bwd(one, 0, one, 0, 8, 64, 4, 8, 0.125, 0.0051, 1.0, 0.0051, 1.0, 0, None, None, None, None, None,
+                                 one, 0, None) == -1
+    assert b"bad sizes" in L.rmcl_last_error()
+    assert L.rmcl_barlow_fwd_bwd(one, 0, one, 0, 8, 64, 0, 8, 0.125, 0.0051, 1.0, 0.0051, 1.0, 9, None, None, None, None, None,
+                                 one, 0, None) == -1
+    assert b"bad path" in L.rmcl_last_error()
+    # peer-memory exchange: rank inside the world, queue length a multiple of the gathered batch
+    assert L.rmcl_gather_enqueue_p2p(one, one, one, one, 0, None, 0, one, 2, 2, 8, 16, 64, 64, None) == -1
+    assert L.rmcl_gather_enqueue_p2p(one, one, one, one, 0, None, 0, one, 0, 2, 8, 16, 40, 40, None) == -1
+    assert b"multiple" in L.rmcl_last_error()
