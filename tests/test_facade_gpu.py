@@ -205,6 +205,25 @@ def test_facade_autocast_selects_the_bf16_shadow(golden):
     assert torch.equal(sh.get(mod.proj_queue), mod.proj_queue.bfloat16())            # ... and the shadow followed
 
 
+def test_pgd_inner_loss_on_the_bf16_shadow(golden):
+    """PGDAttack_moco(inner_queue="shadow"): the inner InfoNCE on the tcgen05 path; perturbation within the bf16 bar of
+    the fp32 attack, sign agreement >= 99.9 % (north-star criterion for the PGD-perturbed tensors)."""
+    import rmcl_b200
+    from rmcl_b200 import ops
+    g = golden("ref_facade_c128")
+    mod = TinyModule(g, "auto").to(DEV).train()
+    sh = mod.__dict__["_rmcl_queue_shadow"] = ops.QueueShadow()
+    sh.get(mod.proj_queue)
+    cfg = dict(adv_steps_img=g.i("meta/n_pgd"), adv_lr_img=g.f("meta/lr"), adv_max_norm_img=g.f("meta/eps"), max_image_len=200)
+    k = torch.nn.functional.normalize(torch.randn(g.i("meta/B"), g.i("meta/C"), device=DEV), dim=1)
+    d32 = rmcl_b200.PGDAttack_moco(cfg).pgd_attack(mod, deepcopy(_batch(g, 0)), k_modality=k)
+    d16 = rmcl_b200.PGDAttack_moco(cfg, inner_queue="shadow").pgd_attack(mod, deepcopy(_batch(g, 0)), k_modality=k)
+    eps = g.f("meta/eps")
+    assert (d16 - d32).abs().max().item() <= 5e-2 * eps
+    nz = d32.abs() > 1e-2 * eps
+    assert (torch.sign(d16)[nz] == torch.sign(d32)[nz]).float().mean().item() >= 0.999
+
+
 def test_moco_module_api(golden):
     """MoCo sketch API (MoCo/MoCo_RMCL.py): method names, two enqueues per step, pointer advance."""
     import rmcl_b200
