@@ -559,7 +559,7 @@ static int infonce_impl(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_d
   else if (tc)
     rc = infonce_tc_launch((const bf16*)(ws + p.off_qhat_bf16), queue, B, C, K, ldq, scale2, p, parts, argmax != nullptr, s);
   else
-    rc = infonce_simt_launch((const float*)(ws + p.off_qhat), queue, queue_dtype, B, C, K, ldq, scale2, p, parts, s);
+    rc = infonce_simt_launch((const float*)(ws + p.off_qhat), queue, queue_dtype, B, C, K, ldq, scale2, p, parts, want_grad, s);
   if (rc != RMCL_OK) return rc;
   RMCL_PROF_MARK(2);
   if (partial_only) return RMCL_OK;

@@ -72,7 +72,8 @@ struct InfoNcePartials {
 
 // partial stages
 int infonce_simt_launch(const float* q_hat, const void* queue, int queue_dtype, int B, int C, long long K,
-                        long long ldq, float scale2, const InfoNcePlan& plan, InfoNcePartials out, cudaStream_t s);
+                        long long ldq, float scale2, const InfoNcePlan& plan, InfoNcePartials out, bool want_o,
+                        cudaStream_t s);
 int infonce_tc_launch(const __nv_bfloat16* q_hat_bf16, const void* queue, int B, int C, long long K, long long ldq,
                       float scale2, const InfoNcePlan& plan, InfoNcePartials out, int want_argmax, cudaStream_t s);
 int infonce_tc_tile_cols(int C);

@@ -22,7 +22,9 @@ __global__ void __launch_bounds__(kSimtThreads) infonce_simt_kernel(
     const float* __restrict__ q_hat, const TQ* __restrict__ queue, int B, int C, long long K, long long ldq,
     float scale2, bool bf16_mode, long long cols_per_split, float* __restrict__ pm, float* __restrict__ pl,
     float* __restrict__ pav, int* __restrict__ pai, float* __restrict__ po, const float* __restrict__ n2,
-    const float* __restrict__ qn2, float* __restrict__ pdist) {
+    const float* __restrict__ qn2, float* __restrict__ pdist, bool want_o) {
+  // want_o == false (no gradient requested: the clean-query argmax call objectives.py:267-275, the greedy attack's
+  // candidate losses): the P.queue^T accumulation — half of the arithmetic — and its write-out are skipped.
   extern __shared__ __align__(16) float smem[];
   float* qs = smem;                               // [16][C]
   float* tile = qs + kSimtRows * C;               // [C][TK+1]
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(kSimtThreads) infonce_simt_kernel(
 #pragma unroll
     for (int i = 0; i < kSimtMaxCPerThread; ++i) {
       const int c = tid + kSimtThreads * i;
-      if (c < C) {
+      if (want_o && c < C) {
 #pragma unroll
         for (int r = 0; r < kSimtRows; ++r) acc[i][r] *= s_alpha[r];
         const float* trow = tile + (size_t)c * (TK + 1);
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(kSimtThreads) infonce_simt_kernel(
 #pragma unroll
   for (int i = 0; i < kSimtMaxCPerThread; ++i) {
     const int c = tid + kSimtThreads * i;
-    if (c < C) {
+    if (want_o && c < C) {
 #pragma unroll
       for (int r = 0; r < kSimtRows; ++r)
         if (row0 + r < B) po[((size_t)split * B + row0 + r) * C + c] = acc[i][r];
@@ -207,31 +209,31 @@ __global__ void __launch_bounds__(kSimtThreads) infonce_simt_kernel(
 
 template <typename TQ, int TK>
 static int launch_simt(const float* q_hat, const void* queue, int B, int C, long long K, long long ldq, float scale2,
-                       bool bf16_mode, const InfoNcePlan& p, InfoNcePartials out, cudaStream_t s) {
+                       bool bf16_mode, const InfoNcePlan& p, InfoNcePartials out, bool want_o, cudaStream_t s) {
   const size_t smem =
       ((size_t)kSimtRows * C + (((size_t)C * (TK + 1) + 3) & ~(size_t)3) + (size_t)kSimtRows * TK + 7 * kSimtRows) * 4;
   auto kern = infonce_simt_kernel<TQ, TK>;
   RMCL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(p.splits, p.row_blocks);
   kern<<<grid, kSimtThreads, smem, s>>>(q_hat, (const TQ*)queue, B, C, K, ldq, scale2, bf16_mode, p.cols_per_split,
-                                        out.m, out.l, out.av, out.ai, out.o, out.n2, out.qn2, out.dist);
+                                        out.m, out.l, out.av, out.ai, out.o, out.n2, out.qn2, out.dist, want_o);
   RMCL_LAUNCH_OK("infonce_simt_kernel");
   return RMCL_OK;
 }
 
 int infonce_simt_launch(const float* q_hat, const void* queue, int queue_dtype, int B, int C, long long K,
-                        long long ldq, float scale2, const InfoNcePlan& p, InfoNcePartials out, cudaStream_t s) {
+                        long long ldq, float scale2, const InfoNcePlan& p, InfoNcePartials out, bool want_o, cudaStream_t s) {
   const bool bf = (queue_dtype == RMCL_BF16);
   if (p.row_blocks > 65535) {
     set_error("InfoNCE: too many rows (%d)", B);
     return RMCL_E_UNSUPPORTED_DIM;
   }
   if (p.tile_cols == 64) {
-    return bf ? launch_simt<__nv_bfloat16, 64>(q_hat, queue, B, C, K, ldq, scale2, true, p, out, s)
-              : launch_simt<float, 64>(q_hat, queue, B, C, K, ldq, scale2, false, p, out, s);
+    return bf ? launch_simt<__nv_bfloat16, 64>(q_hat, queue, B, C, K, ldq, scale2, true, p, out, want_o, s)
+              : launch_simt<float, 64>(q_hat, queue, B, C, K, ldq, scale2, false, p, out, want_o, s);
   }
-  return bf ? launch_simt<__nv_bfloat16, 32>(q_hat, queue, B, C, K, ldq, scale2, true, p, out, s)
-            : launch_simt<float, 32>(q_hat, queue, B, C, K, ldq, scale2, false, p, out, s);
+  return bf ? launch_simt<__nv_bfloat16, 32>(q_hat, queue, B, C, K, ldq, scale2, true, p, out, want_o, s)
+            : launch_simt<float, 32>(q_hat, queue, B, C, K, ldq, scale2, false, p, out, want_o, s);
 }
 
 }  // namespace rmcl
