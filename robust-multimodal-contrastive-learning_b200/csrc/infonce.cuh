@@ -75,7 +75,8 @@ int infonce_simt_launch(const float* q_hat, const void* queue, int queue_dtype, 
                         long long ldq, float scale2, const InfoNcePlan& plan, InfoNcePartials out, bool want_o,
                         cudaStream_t s);
 int infonce_tc_launch(const __nv_bfloat16* q_hat_bf16, const void* queue, int B, int C, long long K, long long ldq,
-                      float scale2, const InfoNcePlan& plan, InfoNcePartials out, int want_argmax, cudaStream_t s);
+                      float scale2, const InfoNcePlan& plan, InfoNcePartials out, int want_argmax, int want_o,
+                      cudaStream_t s);
 int infonce_tc_tile_cols(int C);
 bool infonce_tc2_supports(int C);
 int infonce_tc2_launch(const __nv_bfloat16* q_hat_bf16, const void* queue, int B, int C, long long K, long long ldq,

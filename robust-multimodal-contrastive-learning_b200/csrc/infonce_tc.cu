@@ -102,13 +102,16 @@ __device__ __forceinline__ void tl_stamp(long long* tl, int idx) {
 }
 
 // ----------------------------------------------------------------------------------- kernel
-template <int C, int TN, bool DIAG>
+template <int C, int TN, bool DIAG, bool WANT_O>
 __global__ void __launch_bounds__(kTcThreads, 1)
     infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_queue, const __nv_bfloat16* __restrict__ q_hat, int B,
                       long long K, float scale2, long long cols_per_split, int want_argmax, float* __restrict__ pm,
                       float* __restrict__ pl, float* __restrict__ pav, int* __restrict__ pai, __nv_bfloat16* __restrict__ po,
                       long long* __restrict__ timeline, const float* __restrict__ n2, const float* __restrict__ qn2,
                       float* __restrict__ pdist) {
+  constexpr bool want_o = WANT_O;   // compile-time: the with-gradient instantiation is the tuned kernel, untouched
+  // want_o == false (no gradient requested: the clean-query argmax call, the greedy attack's candidate losses): the statistics
+  // pass only — no P tile, no O GEMM, no partial write-out; ring stages are released by the S GEMM's own commit.
   constexpr int kStageBytes = C * TN * 2;
   constexpr int kBoxBytes = C * 128;            // one TMA box: C rows x 64 bf16 columns
   constexpr int kBoxes = TN / 64;
@@ -323,10 +326,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         // the one of tile i cannot start before this warp arrives on p_full below.
         const float alpha = grow ? exp2f(m_now - m_tile) : 1.f;
         if (grow) { m_mine = m_tile; l_run *= alpha; }
-        mbar_wait(&sh.o_done[(i - 1) & 1], ((i - 1) >> 1) & 1);
-        tc_fence_after();
+        if (want_o) {
+          mbar_wait(&sh.o_done[(i - 1) & 1], ((i - 1) >> 1) & 1);
+          tc_fence_after();
+        }
 #pragma unroll 1
-        for (int ch = 0; ch < C / 32; ++ch) {
+        for (int ch = 0; want_o && ch < C / 32; ++ch) {
           uint32_t o[32];
           tc_ld32(tlane + kTmO + ch * 32, o);
           tc_wait_ld();
@@ -360,12 +365,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       // thing that may be trusted here: a commit behind a later MMA group with another accumulator
       // does NOT imply it has finished — such groups overlap and complete out of order (observed
       // on B200: fast warps overwrote P while the O GEMM was still reading it).
-      if (live && i >= 2) mbar_wait(&sh.o_done[b], ((i - 2) >> 1) & 1);
+      if (live && want_o && i >= 2) mbar_wait(&sh.o_done[b], ((i - 2) >> 1) & 1);
       if (live && quad == 0) tl_stamp(tl, 8 + 8 * i + 4);
       // row r of P in the K-major SWIZZLE_128B layout: 16-byte chunk c of a 128-byte row lands at c ^ (r & 7)
       // (dry pass: the P buffers double as other warps' Q^ transpose scratch, so nothing may be stored;
       //  l_run keeps the exponentials alive for the compiler)
-      if (live) {
+      if (live && want_o) {
         uint8_t* prow = pbuf + b * kPBytes + r * 128;
 #pragma unroll
         for (int c = 0; c < TN / 8; ++c) {
@@ -380,9 +385,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
     // ---- epilogue: merge the two warps' statistics (odd-tile warp -> even-tile warp), then O
     if (tid == 0) pdl_trigger();   // the finalize kernel's CTAs may become resident now
-    if (n_tiles >= 2) mbar_wait(&sh.o_done[(n_tiles - 2) & 1], ((n_tiles - 2) >> 1) & 1);
-    mbar_wait(&sh.o_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
-    tc_fence_after();
+    if (want_o) {
+      if (n_tiles >= 2) mbar_wait(&sh.o_done[(n_tiles - 2) & 1], ((n_tiles - 2) >> 1) & 1);
+      mbar_wait(&sh.o_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
+      tc_fence_after();
+    }
     if (tid == 0) tl_stamp(tl, 4);
     const bool row_ok = (row0 + r) < B;
     if (par == 1) {
@@ -416,7 +423,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // was bf16 already, so this adds one more 2^-9 relative rounding per split to dq.
     uint8_t* stage = ring + (size_t)r * (2 * C + 16) + par * HC * 2;   // every TMA write has been consumed
 #pragma unroll 1
-    for (int ch = 0; ch < HC / 32; ++ch) {
+    for (int ch = 0; want_o && ch < HC / 32; ++ch) {
       uint32_t o[32];
       tc_ld32(tlane + kTmO + par * HC + ch * 32, o);
       tc_wait_ld();
@@ -430,7 +437,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       for (int j = 0; j < 4; ++j)
         *reinterpret_cast<uint4*>(stage + ch * 64 + 16 * j) = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
     }
-    if (row_ok) {
+    if (row_ok && want_o) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       bulk_store_row(po + ((size_t)split * B + row0 + r) * C + par * HC, stage, HC * 2);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -500,10 +507,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             tc_mma_ts(dd, tmem + kTmQ + s * 8, bd, kIdescS, s > 0);
           }
           tc_commit(bar_s);
+          if (!want_o && live) tc_commit(&sh.k_empty[st]);   // no O GEMM will read this stage
         }
         __syncwarp();
       }
-      if (!live || j >= 2) {
+      if (want_o && (!live || j >= 2)) {
         // ------------------------------------------------------------------ O GEMM of tile i = j - 2
         const int i = live ? j - 2 : 0;
         const int st = i % kStages;
@@ -546,7 +554,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 // ------------------------------------------------------------------------------ host side
 thread_local long long* g_tc_timeline = nullptr;
 
-template <int C, int TN, bool DIAG>
+template <int C, int TN, bool DIAG, bool WANT_O>
 int launch_tc(const __nv_bfloat16* q_hat, const void* queue, int B, long long K, long long ldq, float scale2,
               const InfoNcePlan& p, InfoNcePartials out, int want_argmax, cudaStream_t s) {
   alignas(64) CUtensorMap tmap;
@@ -556,7 +564,7 @@ int launch_tc(const __nv_bfloat16* q_hat, const void* queue, int B, long long K,
   constexpr int kPBytes = (TN / 64) * 16384;
   constexpr int kStages = ((kSmemBudget - 2 * kPBytes) / kStageBytes) < 8 ? ((kSmemBudget - 2 * kPBytes) / kStageBytes) : 8;
   const size_t smem = (size_t)kStages * kStageBytes + 2 * kPBytes + 1024;
-  auto kern = infonce_tc_kernel<C, TN, DIAG>;
+  auto kern = infonce_tc_kernel<C, TN, DIAG, WANT_O>;
   RMCL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(p.splits, p.row_blocks);
   RMCL_CUDA_OK(launch_pdl(kern, grid, dim3(kTcThreads), smem, s, tmap, q_hat, B, K, scale2, p.cols_per_split, want_argmax,
@@ -589,23 +597,25 @@ extern "C" int rmcl_debug_tc_timeline_words(void) { return rmcl::kTimelineWords;
 namespace rmcl {
 
 int infonce_tc_launch(const __nv_bfloat16* q_hat, const void* queue, int B, int C, long long K, long long ldq,
-                      float scale2, const InfoNcePlan& p, InfoNcePartials out, int want_argmax, cudaStream_t s) {
+                      float scale2, const InfoNcePlan& p, InfoNcePartials out, int want_argmax, int want_o, cudaStream_t s) {
   if (p.row_blocks > 65535) {
     set_error("InfoNCE: too many rows (%d)", B);
     return RMCL_E_UNSUPPORTED_DIM;
   }
   const bool dg = out.n2 != nullptr;
+#define RMCL_TC_CASE(CC, TT)                                                                                              \
+  case CC:                                                                                                                \
+    if (want_o)                                                                                                           \
+      return dg ? launch_tc<CC, TT, true, true>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s)                  \
+                : launch_tc<CC, TT, false, true>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s);                \
+    return dg ? launch_tc<CC, TT, true, false>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s)                   \
+              : launch_tc<CC, TT, false, false>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s);
   switch (C) {
-    case 256:
-      return dg ? launch_tc<256, 64, true>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s)
-                : launch_tc<256, 64, false>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s);
-    case 128:
-      return dg ? launch_tc<128, 128, true>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s)
-                : launch_tc<128, 128, false>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s);
-    case 64:
-      return dg ? launch_tc<64, 128, true>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s)
-                : launch_tc<64, 128, false>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s);
+    RMCL_TC_CASE(256, 64)
+    RMCL_TC_CASE(128, 128)
+    RMCL_TC_CASE(64, 128)
   }
+#undef RMCL_TC_CASE
   set_error("tcgen05 InfoNCE supports C in {64,128,256} (got %d)", C);
   return RMCL_E_UNSUPPORTED_DIM;
 }
