@@ -555,7 +555,8 @@ static int infonce_impl(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_d
                         (float*)(ws + p.off_pdist)};
   if (tc && p.two_pass)
     rc = infonce_tc2_launch((const bf16*)(ws + p.off_qhat_bf16), queue, B, C, K, ldq, scale2, p, parts,
-                            (bf16*)(ws + p.off_ptilde), p.k_pad, (unsigned int*)(ws + p.off_counter) + 1, argmax != nullptr, s);
+                            (bf16*)(ws + p.off_ptilde), p.k_pad, (unsigned int*)(ws + p.off_counter) + 1, argmax != nullptr,
+                            (want_grad || partial_only) ? 1 : 0, s);
   else if (tc)
     rc = infonce_tc_launch((const bf16*)(ws + p.off_qhat_bf16), queue, B, C, K, ldq, scale2, p, parts, argmax != nullptr,
                            (want_grad || partial_only) ? 1 : 0, s);

@@ -81,7 +81,7 @@ int infonce_tc_tile_cols(int C);
 bool infonce_tc2_supports(int C);
 int infonce_tc2_launch(const __nv_bfloat16* q_hat_bf16, const void* queue, int B, int C, long long K, long long ldq,
                        float scale2, const InfoNcePlan& plan, InfoNcePartials out, __nv_bfloat16* ptilde, long long k_pad,
-                       unsigned int* overflow_flag, int want_argmax, cudaStream_t s);
+                       unsigned int* overflow_flag, int want_argmax, int want_o, cudaStream_t s);
 bool infonce_tc_built();
 
 }  // namespace rmcl

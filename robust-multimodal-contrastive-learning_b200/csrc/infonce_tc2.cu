@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       // P~ row r -> scratch (16-byte chunks XOR-swizzled), then the warp stores its 32 rows coalesced:
       // 8 lanes cover the 128-byte segment of one row, 4 rows per instruction
+      if (ptilde == nullptr) continue;   // statistics-only call (no gradient requested): no P~, no PV pass
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < 8; ++c)
@@ -445,7 +446,8 @@ bool infonce_tc2_supports(int C) { return C == 512 || C == 768; }
 
 int infonce_tc2_launch(const __nv_bfloat16* q_hat, const void* queue, int B, int C, long long K, long long ldq, float scale2,
                        const InfoNcePlan& p, InfoNcePartials out, __nv_bfloat16* ptilde, long long k_pad,
-                       unsigned int* overflow_flag, int want_argmax, cudaStream_t s) {
+                       unsigned int* overflow_flag, int want_argmax, int want_o, cudaStream_t s) {
+  __nv_bfloat16* ptilde_s = want_o ? ptilde : nullptr;   // statistics-only call: the S pass alone, no P~
   if (p.row_blocks > 65535 || p.splits > 65535) {
     set_error("InfoNCE: too many rows (%d)", B);
     return RMCL_E_UNSUPPORTED_DIM;
@@ -457,16 +459,17 @@ int infonce_tc2_launch(const __nv_bfloat16* q_hat, const void* queue, int B, int
   if (rc != RMCL_OK) return rc;
   const bool dg = out.n2 != nullptr;
   if (C == 768)
-    rc = dg ? launch_s<768, true>(tq, q_hat, B, K, k_pad, scale2, p, out, ptilde, overflow_flag, want_argmax, s)
-            : launch_s<768, false>(tq, q_hat, B, K, k_pad, scale2, p, out, ptilde, overflow_flag, want_argmax, s);
+    rc = dg ? launch_s<768, true>(tq, q_hat, B, K, k_pad, scale2, p, out, ptilde_s, overflow_flag, want_argmax, s)
+            : launch_s<768, false>(tq, q_hat, B, K, k_pad, scale2, p, out, ptilde_s, overflow_flag, want_argmax, s);
   else if (C == 512)
-    rc = dg ? launch_s<512, true>(tq, q_hat, B, K, k_pad, scale2, p, out, ptilde, overflow_flag, want_argmax, s)
-            : launch_s<512, false>(tq, q_hat, B, K, k_pad, scale2, p, out, ptilde, overflow_flag, want_argmax, s);
+    rc = dg ? launch_s<512, true>(tq, q_hat, B, K, k_pad, scale2, p, out, ptilde_s, overflow_flag, want_argmax, s)
+            : launch_s<512, false>(tq, q_hat, B, K, k_pad, scale2, p, out, ptilde_s, overflow_flag, want_argmax, s);
   else {
     set_error("two-pass tcgen05 InfoNCE supports C in {512, 768} (got %d)", C);
     return RMCL_E_UNSUPPORTED_DIM;
   }
   if (rc != RMCL_OK) return rc;
+  if (!want_o) return RMCL_OK;
   const size_t smem = 4 * (size_t)(kRows * kTN * 2 + kChunkBytes) + 1024;
   RMCL_CUDA_OK(cudaFuncSetAttribute(infonce_pv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   RMCL_CUDA_OK(launch_pdl(infonce_pv_kernel, dim3(C / kChunkRows, p.row_blocks, p.splits), dim3(kThreads), smem, s, tp, tq, B,

@@ -508,6 +508,11 @@ def test_infonce_tcgen05_matches_simt_path(ops, C):
     q, k, queue = _infonce_inputs(96, C, 3000 // 8 * 8, seed=C, queue_dtype=torch.bfloat16)
     a = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.to(DEV), 0.07, path="simt")
     b = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.to(DEV), 0.07, path="tcgen05")
+    for pth in ("tcgen05", "simt"):      # statistics-only instantiations: same statistics as the full call, bit for bit
+        full = b if pth == "tcgen05" else a
+        n = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.to(DEV), 0.07, path=pth, need_grad=False,
+                                want=("loss", "lse", "argmax", "loss_per_row"))
+        assert torch.equal(n["lse"], full["lse"]) and torch.equal(n["argmax"], full["argmax"]) and torch.equal(n["loss"], full["loss"])
     assert rel_err(b["lse"], a["lse"]) < 1e-5
     assert rel_err(b["loss"], a["loss"]) < 1e-5
     assert rel_err(b["dq"], a["dq"]) < 1e-2
@@ -579,6 +584,10 @@ def test_infonce_tcgen05_two_pass_matches_simt_path(ops, C):
     q, k, queue = _infonce_inputs(96, C, 3000 // 8 * 8, seed=C, queue_dtype=torch.bfloat16)
     a = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.to(DEV), 0.07, path="simt")
     b = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.to(DEV), 0.07, path="auto")     # auto -> two-pass tcgen05
+    # statistics-only call (no gradient): the S pass alone, bit-identical statistics
+    n = ops.infonce_fwd_bwd(q.to(DEV), k.to(DEV), queue.to(DEV), 0.07, path="auto", need_grad=False,
+                            want=("loss", "lse", "argmax", "loss_per_row"))
+    assert torch.equal(n["lse"], b["lse"]) and torch.equal(n["argmax"], b["argmax"]) and torch.equal(n["loss"], b["loss"])
     assert rel_err(b["lse"], a["lse"]) < 1e-5
     assert rel_err(b["loss"], a["loss"]) < 1e-5
     assert rel_err(b["dq"], a["dq"]) < 1e-2
