@@ -294,8 +294,10 @@ class BarlowTwins(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_on, g_offs):
         dq_off, cdiag, kl = ctx.saved_tensors
-        dq_on = (2.0 * ctx.inv_bs) * (cdiag - 1.0)[None, :] * kl.float()
-        return (g_on * dq_on + (g_offs * ctx.lam) * dq_off).to(ctx.q_dtype), None, None, None, None
+        coeff = (cdiag - 1.0) * (g_on * (2.0 * ctx.inv_bs))             # [D]: d(on_diag)/dq[b, i] = coeff_i * k[b, i]
+        out = dq_off * (g_offs * ctx.lam)
+        out.addcmul_(kl.float(), coeff[None, :])
+        return out.to(ctx.q_dtype), None, None, None, None
 
 
 def barlow_twins_loss(q, k, inv_bs, lam, gather=None):
