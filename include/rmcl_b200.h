@@ -108,6 +108,12 @@ int rmcl_ema_multi(const rmcl_ema_chunk* chunks_dev, int64_t n_chunks, double m,
  */
 size_t rmcl_infonce_workspace_bytes(int B, int C, int64_t K, rmcl_dtype queue_dtype, int path);
 
+/* Writes the comma-separated names of the kernels one rmcl_infonce_fwd_bwd call with these arguments launches, in
+ * launch order, into buf (NUL-terminated, truncated to buf_bytes); returns the number of launches or a negative
+ * status.  Host-only (no device work): bench.py reports it as `launches_per_step`. */
+int rmcl_infonce_describe(int B, int C, int64_t K, rmcl_dtype queue_dtype, int path, int need_grad, char* buf,
+                          size_t buf_bytes);
+
 int rmcl_infonce_fwd_bwd(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_dtype k_dtype,
                          const void* queue, rmcl_dtype queue_dtype, int B, int C, int64_t K,
                          int64_t ldq, float tau, float loss_scale, unsigned flags, int path,
@@ -179,9 +185,14 @@ int rmcl_gather_enqueue_p2p(void* const* stage_ptrs_dev, void* const* flag_ptrs_
  *           loss_scale * (on_diag + lambda * off_diag), dq f32[Bl, D], cdiag f32[D] = diagonal(c);
  *           any may be NULL.  (cdiag lets a caller whose upstream gradients of the two sums differ
  *           combine dq = g_on * 2/bs (cdiag-1) k + g_off * dq(w_on=0, w_off=1) without a second pass.)
- * path      RMCL_BARLOW_GRAM (= AUTO): through the Gram matrices q q^T, k k^T — sum_ij c_ij^2 = <q q^T, k k^T>/bs^2,
+ * path      RMCL_BARLOW_GRAM: through the Gram matrices q q^T, k k^T — sum_ij c_ij^2 = <q q^T, k k^T>/bs^2,
  *           gradient 2/bs^2 (k k^T) q — three tcgen05 GEMMs with D as the long dimension, any Bg <= 4096,
- *           ~D/(1.5 Bg) times fewer flops.  RMCL_BARLOW_DIRECT: c evaluated tile by tile (Bg <= 256).
+ *           ~D/(1.5 Bg) times fewer flops.  off_diag is the DIFFERENCE <Gq,Gk>/bs^2 - sum_i c_ii^2: its relative error
+ *           is ~2e-6 * sum_i c_ii^2 / off_diag.  Since rank(c) <= Bg, D >= 2 Bg guarantees off_diag >= sum_i c_ii^2
+ *           (no cancellation, e.g. the reference's D = 8192 with any gathered batch <= 4096); a projector narrower
+ *           than twice the batch can reach c ~ I, where the difference cancels.
+ *           RMCL_BARLOW_DIRECT: c evaluated tile by tile, off-diagonal squares summed directly (Bg <= 256).
+ *           RMCL_BARLOW_AUTO: GRAM if D >= 2 Bg or Bg > 256, else DIRECT.
  */
 enum { RMCL_BARLOW_AUTO = 0, RMCL_BARLOW_DIRECT = 1, RMCL_BARLOW_GRAM = 2 };
 size_t rmcl_barlow_workspace_bytes(int Bg, int D);

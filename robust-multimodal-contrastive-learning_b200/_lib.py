@@ -22,7 +22,7 @@ EXPORTS = (
     "rmcl_infonce_workspace_bytes", "rmcl_infonce_fwd_bwd", "rmcl_enqueue", "rmcl_pgd_workspace_bytes", "rmcl_pgd_step", "rmcl_step_host",
     "rmcl_profile_enable", "rmcl_profile_infonce_ms", "rmcl_enqueue_shadow", "rmcl_debug_tc_timeline",
     "rmcl_debug_tc_timeline_words", "rmcl_queue_stats", "rmcl_infonce_fwd_bwd_diag",
-    "rmcl_barlow_workspace_bytes", "rmcl_barlow_fwd_bwd", "rmcl_gather_enqueue_p2p",
+    "rmcl_barlow_workspace_bytes", "rmcl_barlow_fwd_bwd", "rmcl_gather_enqueue_p2p", "rmcl_infonce_describe",
 )
 
 
@@ -61,6 +61,8 @@ def lib():
     L.rmcl_infonce_fwd_bwd.restype = i32
     L.rmcl_infonce_fwd_bwd.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i64, i64, f32, f32, u32, i32,
                                        vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.rmcl_infonce_describe.restype = i32
+    L.rmcl_infonce_describe.argtypes = [i32, i32, i64, i32, i32, i32, C.c_char_p, sz]
     L.rmcl_enqueue.restype = i32
     L.rmcl_enqueue.argtypes = [vp, i32, vp, i32, vp, i32, i32, i64, i64, vp]
     if "RMCL_B200_LIB" in os.environ and not hasattr(L, "rmcl_enqueue_shadow"):   # A/B against an older build
@@ -96,6 +98,35 @@ def lib():
     L.rmcl_profile_infonce_ms.argtypes = [C.POINTER(C.c_float)]
     _lib = L
     return L
+
+
+TORCH_LIB_PATH = os.path.join(_HERE, "rmcl_b200_torch.so")
+_torch_ops = None
+
+
+def ffi():
+    """Which binding the device-tensor wrappers use: "torch" (default) = the TORCH_LIBRARY(rmcl, ...) operators of
+    rmcl_b200_torch.so (csrc/torch_ext.cpp: C++ argument checks, ATen allocation, then the C-ABI call); "ctypes" =
+    the raw C-ABI symbols from Python (RMCL_B200_FFI=ctypes; what INTEGRATION.md's stub and tests/test_capi_cpu.py use)."""
+    v = os.environ.get("RMCL_B200_FFI", "torch")
+    if v not in ("torch", "ctypes"):
+        raise ValueError(f"RMCL_B200_FFI must be 'torch' or 'ctypes', got {v!r}")
+    return v
+
+
+def torch_ops():
+    """torch.ops.rmcl, loading rmcl_b200_torch.so on first use.  No fallback: a missing extension is an error."""
+    global _torch_ops
+    if _torch_ops is None:
+        import torch
+        lib()                                   # librmcl_b200.so first (the extension links against it)
+        if not os.path.isfile(TORCH_LIB_PATH):
+            raise ImportError(
+                f"rmcl_b200: {TORCH_LIB_PATH} is missing — the torch extension has not been built. "
+                "Run `python __graft_entry__.py build` (or set RMCL_B200_FFI=ctypes to use the raw C-ABI binding).")
+        torch.ops.load_library(TORCH_LIB_PATH)
+        _torch_ops = torch.ops.rmcl
+    return _torch_ops
 
 
 def check(rc, what):

@@ -548,7 +548,14 @@ extern "C" int rmcl_barlow_fwd_bwd(const void* q, rmcl_dtype q_dtype, const void
                  D, b0, Bl);
   RMCL_CHECK_ARG(dtype_ok(q_dtype) && dtype_ok(k_dtype), "rmcl_barlow_fwd_bwd: bad dtype");
   RMCL_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "rmcl_barlow_fwd_bwd: workspace must be 256B aligned");
-  if (path == RMCL_BARLOW_AUTO) path = RMCL_BARLOW_GRAM;
+  // AUTO: the Gram identity off_diag = <Gq,Gk>/bs^2 - sum_i c_ii^2 is a difference.  c has rank <= Bg, so with c_ii ~ 1
+  // sum_ij c_ij^2 >= D^2/Bg and off_diag/sum_i c_ii^2 >= D/Bg - 1: for D >= 2 Bg (the reference: D = 8192, gathered batch
+  // <= 4096) the difference can never cancel and the Gram path is safe at any stage of training.  For a projector narrower
+  // than twice the batch c can approach the identity; there tensor-core accumulation error (~1e-6 of sum_ij c_ij^2, truncating)
+  // is no longer small against off_diag (measured 0.5 % at off_diag/sum = 2.6e-5, tests/test_kernels_gpu.py::
+  // test_barlow_near_identity_correlation), so AUTO takes the direct kernel, which sums the off-diagonal squares themselves —
+  // while its batch limit allows.
+  if (path == RMCL_BARLOW_AUTO) path = (D >= 2 * Bg || Bg > 256) ? RMCL_BARLOW_GRAM : RMCL_BARLOW_DIRECT;
   if (path == RMCL_BARLOW_GRAM)
     return barlow_gram_run(q, q_dtype, k, k_dtype, Bg, D, b0, Bl, inv_bs, lambda, w_on, w_off, loss_scale, on_diag, off_diag, loss,
                            dq, cdiag, workspace, workspace_bytes, (cudaStream_t)stream);

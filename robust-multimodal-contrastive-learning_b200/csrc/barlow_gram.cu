@@ -79,7 +79,7 @@ int barlow_gram_plan(int Bg, int D, GramPlan* p) {
   p->off_ghi = take(G * 2);
   p->off_glo = take(G * 2);
   p->off_cdiag = take((size_t)D * 4);
-  p->off_blk = take((size_t)p->BGp * 4);
+  p->off_blk = take((size_t)p->BGp * 8);   // double: see gram_finish_kernel
   p->off_counter = take(256);
   p->total = off;
   return RMCL_OK;
@@ -246,19 +246,37 @@ __device__ __forceinline__ float block_sum_256(float v, float* red /*[8]*/) {
   return t;
 }
 
+__device__ __forceinline__ double block_sum_256_d(double v, double* red /*[8]*/) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w];
+  return t;
+}
+
+// off_diag = <Gq, Gk>/bs^2 - sum_i c_ii^2 is a difference of two sums that are both ~D when c is close to the identity
+// (a converged model on a gathered batch >= D): in fp32 one ulp of D = 128 is already 2e-3 of an off_diag of 3e-3
+// (measured: tests/test_kernels_gpu.py::test_barlow_near_identity_correlation).  The Gram entries themselves are fp32
+// tensor-core accumulations (relative error ~1e-7 each, averaged over Bg^2 terms); everything downstream of them — the
+// inner product, the two diagonal sums and the subtraction — is therefore carried in double.  That is Bg^2 + 2 D double
+// operations per call, nothing next to the GEMMs.
 __global__ void __launch_bounds__(256) gram_finish_kernel(int BGp, int splits, int D, float inv_bs, float lambda, float loss_scale,
                                                           const float* __restrict__ part, const float* __restrict__ cdiag,
                                                           __nv_bfloat16* __restrict__ ghi, __nv_bfloat16* __restrict__ glo,
-                                                          float* __restrict__ blk, unsigned int* __restrict__ counter,
+                                                          double* __restrict__ blk, unsigned int* __restrict__ counter,
                                                           float* __restrict__ on_out, float* __restrict__ off_out,
                                                           float* __restrict__ loss_out) {
-  __shared__ float red[8];
+  __shared__ double red[8];
   __shared__ bool s_last;
   const int a = blockIdx.x, tid = threadIdx.x;
   const size_t G = (size_t)BGp * BGp;
   pdl_wait();
   if (tid == 0) pdl_trigger();
-  float acc = 0.f;
+  double acc = 0.0;
   for (int b = tid; b < BGp; b += 256) {
     float gq = 0.f, gk = 0.f;
     for (int s = 0; s < splits; ++s) {
@@ -268,9 +286,9 @@ __global__ void __launch_bounds__(256) gram_finish_kernel(int BGp, int splits, i
     const __nv_bfloat16 hi = __float2bfloat16_rn(gk);
     ghi[(size_t)a * BGp + b] = hi;
     glo[(size_t)a * BGp + b] = __float2bfloat16_rn(gk - __bfloat162float(hi));
-    acc = fmaf(gq, gk, acc);
+    acc = fma((double)gq, (double)gk, acc);
   }
-  acc = block_sum_256(acc, red);
+  acc = block_sum_256_d(acc, red);
   if (tid == 0) {
     blk[a] = acc;
     __threadfence();
@@ -279,21 +297,21 @@ __global__ void __launch_bounds__(256) gram_finish_kernel(int BGp, int splits, i
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  float tot = 0.f, cd2 = 0.f, on = 0.f;
+  double tot = 0.0, cd2 = 0.0, on = 0.0;
   for (int j = tid; j < BGp; j += 256) tot += __ldcg(blk + j);
   for (int i = tid; i < D; i += 256) {
-    const float c = cdiag[i];
-    cd2 = fmaf(c, c, cd2);
-    on = fmaf(c - 1.f, c - 1.f, on);
+    const double c = (double)cdiag[i];
+    cd2 = fma(c, c, cd2);
+    on = fma(c - 1.0, c - 1.0, on);
   }
-  tot = block_sum_256(tot, red);
-  cd2 = block_sum_256(cd2, red);
-  on = block_sum_256(on, red);
+  tot = block_sum_256_d(tot, red);
+  cd2 = block_sum_256_d(cd2, red);
+  on = block_sum_256_d(on, red);
   if (tid == 0) {
-    const float off = tot * inv_bs * inv_bs - cd2;
-    if (on_out) *on_out = on;
-    if (off_out) *off_out = off;
-    if (loss_out) *loss_out = loss_scale * (on + lambda * off);
+    const double off = tot * (double)inv_bs * (double)inv_bs - cd2;
+    if (on_out) *on_out = (float)on;
+    if (off_out) *off_out = (float)off;
+    if (loss_out) *loss_out = (float)((double)loss_scale * (on + (double)lambda * off));
   }
 }
 
@@ -478,7 +496,7 @@ int barlow_gram_run(const void* q, int q_dtype, const void* k, int k_dtype, int 
 
   RMCL_CUDA_OK(launch_pdl(gram_finish_kernel, dim3(p.BGp), dim3(256), (size_t)0, s, p.BGp, p.splits, D, inv_bs, lambda, loss_scale,
                           (const float*)(ws + p.off_part), (const float*)(ws + p.off_cdiag), (bf16*)(ws + p.off_ghi),
-                          (bf16*)(ws + p.off_glo), (float*)(ws + p.off_blk), (unsigned int*)(ws + p.off_counter), on_diag,
+                          (bf16*)(ws + p.off_glo), (double*)(ws + p.off_blk), (unsigned int*)(ws + p.off_counter), on_diag,
                           off_diag, loss));
   if (dq == nullptr) return RMCL_OK;
 

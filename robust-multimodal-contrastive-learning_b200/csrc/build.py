@@ -36,9 +36,38 @@ def build(force=False, verbose=False, out=OUT, defines=()):
     return out
 
 
+TORCH_OUT = os.path.join(os.path.dirname(HERE), "rmcl_b200_torch.so")
+
+
+def build_torch_ext(force=False):
+    """rmcl_b200_torch.so: the TORCH_LIBRARY(rmcl, ...) operators of torch_ext.cpp, host C++ only (g++), linked against
+    librmcl_b200.so next to it (rpath $ORIGIN) and torch's own libraries.  In-tree like the CUDA library, so it travels
+    with the snapshot."""
+    src = os.path.join(HERE, "torch_ext.cpp")
+    deps = [src, os.path.join(os.path.dirname(os.path.dirname(HERE)), "include", "rmcl_b200.h")]
+    if not force and os.path.isfile(TORCH_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(TORCH_OUT) for d in deps):
+        return TORCH_OUT
+    import torch
+    from torch.utils import cpp_extension as ce
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", src, "-o", TORCH_OUT,
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}", "-DTORCH_API_INCLUDE_EXTENSION_H"]
+    cmd += [f"-I{p}" for p in ce.include_paths()] + [f"-I{cuda_home}/include"]
+    cmd += [f"-L{p}" for p in ce.library_paths()] + [f"-L{cuda_home}/lib64", f"-L{os.path.dirname(HERE)}"]
+    cmd += ["-l:librmcl_b200.so", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-lcudart",
+            "-Wl,-rpath,$ORIGIN"] + [f"-Wl,-rpath,{p}" for p in ce.library_paths()]
+    r = subprocess.run(cmd, cwd=HERE, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building rmcl_b200_torch.so")
+    return TORCH_OUT
+
+
 if __name__ == "__main__":
     defs = [a for a in sys.argv[1:] if a.startswith("-D")]
     out = OUT
     if "--out" in sys.argv:
         out = os.path.join(os.path.dirname(HERE), sys.argv[sys.argv.index("--out") + 1])
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=out, defines=defs))
+    if out == OUT:
+        print(build_torch_ext(force="--force" in sys.argv))

@@ -117,8 +117,11 @@ extern "C" int rmcl_enqueue_shadow(void* queue, rmcl_dtype queue_dtype, void* sh
 //   4. enqueue the world*B staged keys into my replica of the queue (+ bf16 shadow) — the transposing scatter of
 //              enqueue_kernel — and advance my pointer.
 // Two slots suffice: a peer can push step n+2 into slot n&1 only after it has seen my signal of step n+1, which I
-// send after my step-n enqueue has finished reading that slot.  All CTAs are co-resident (grid <= 2 per SM), so the
-// spin in step 3 cannot starve the pushes it waits for.
+// send after my step-n enqueue has finished reading that slot.  All CTAs are co-resident (grid = RMCL_P2P_MAX_CTAS = 16),
+// so the spin in step 3 cannot starve the pushes it waits for.
+#ifndef RMCL_P2P_MAX_CTAS
+#define RMCL_P2P_MAX_CTAS 16
+#endif
 namespace rmcl {
 
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
@@ -241,7 +244,13 @@ extern "C" int rmcl_gather_enqueue_p2p(void* const* stage_ptrs_dev, void* const*
   const int sms = rmcl::sm_count();
   if (sms <= 0) return RMCL_E_CUDA;
   const long long tiles = ((Bt + 31) / 32) * ((C + 31) / 32);
-  long long grid = 2ll * sms;          // all CTAs must be resident at once (they spin on the flag): 2 x 256 threads per SM
+  // All CTAs must be resident at once (they spin on the flag), and while they wait for the slowest rank they hold their
+  // SM's thread slots away from whatever runs beside them — in the training step that is the HBM-bound EMA the exchange is
+  // meant to hide under.  The work is tiny (world x 256 KB of pushes, world*B*C*6 bytes of scatter), so a small fixed grid
+  // loses nothing: 16 CTAs move 8 x 256 KB in ~32 sweeps of 16-byte stores.  (Round 1 launched 2 CTAs per SM = 296 spinning
+  // CTAs; 1 -> 8 GPU weak scaling of the cfg2 step was 0.93.)
+  long long grid = RMCL_P2P_MAX_CTAS;
+  if (grid > 2ll * sms) grid = 2ll * sms;
   if (grid > tiles) grid = tiles;
   cudaStream_t s = (cudaStream_t)stream;
   using bf16 = __nv_bfloat16;

@@ -508,6 +508,31 @@ extern "C" size_t rmcl_infonce_workspace_bytes(int B, int C, int64_t K, rmcl_dty
   return best;
 }
 
+extern "C" int rmcl_infonce_describe(int B, int C, int64_t K, rmcl_dtype queue_dtype, int path, int need_grad, char* buf,
+                                     size_t buf_bytes) {
+  RMCL_CHECK_ARG(B > 0 && C > 0 && K > 0 && buf && buf_bytes > 0, "rmcl_infonce_describe: bad arguments");
+  InfoNcePlan p;
+  int rc = infonce_make_plan(B, C, K, queue_dtype, path, true, &p);
+  if (rc != RMCL_OK) return rc;
+  const char* names;
+  int n;
+  if (p.path == RMCL_INFONCE_SIMT) {
+    names = "infonce_prep_kernel,infonce_simt_kernel,infonce_finalize_kernel";
+    n = 3;
+  } else if (p.two_pass && need_grad) {
+    names = "infonce_prep_kernel,infonce_s_kernel,infonce_pv_kernel,infonce_finalize_kernel";
+    n = 4;
+  } else if (p.two_pass) {
+    names = "infonce_prep_kernel,infonce_s_kernel,infonce_finalize_kernel";
+    n = 3;
+  } else {
+    names = "infonce_prep_kernel,infonce_tc_kernel,infonce_finalize_kernel";
+    n = 3;
+  }
+  snprintf(buf, buf_bytes, "%s", names);
+  return n;
+}
+
 static int infonce_impl(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_dtype k_dtype, const void* queue,
                         rmcl_dtype queue_dtype, int B, int C, int64_t K, int64_t ldq, float tau, float loss_scale,
                         unsigned flags, int path, float* loss, float* loss_per_row, float* lse, float* pos,

@@ -57,13 +57,12 @@ class MoCo(nn.Module):
             txt_k_raw, img_k_raw = self.encoder_k(batch)
         txt_q, img_q = self.encoder_q(batch)
         queue = self.txt_img_queue
-        r_txt = ops.infonce_fwd_bwd(txt_q.float(), img_k_raw.float(), queue, self.T, normalize_k=True, need_grad=False,
-                                    path=self.infonce_path, want=("k_hat",))
-        r_img = ops.infonce_fwd_bwd(img_q.float(), txt_k_raw.float(), queue, self.T, normalize_k=True, need_grad=False,
-                                    path=self.infonce_path, want=("k_hat",))
-        img_k, txt_k = r_txt["k_hat"], r_img["k_hat"]
-        loss_txt, _ = ops.infonce_loss(txt_q, img_k, queue, self.T, self.infonce_path)
-        loss_img, _ = ops.infonce_loss(img_q, txt_k, queue, self.T, self.infonce_path)
+        # the raw key projections go straight into the loss launches, which normalise them on the way
+        # (nn.functional.normalize of MoCo_RMCL.py:126-127) and hand the unit keys back for the enqueue
+        loss_txt, _, img_k = ops.infonce_loss(txt_q, img_k_raw.float(), queue, self.T, self.infonce_path,
+                                              normalize_k=True, return_k_hat=True)
+        loss_img, _, txt_k = ops.infonce_loss(img_q, txt_k_raw.float(), queue, self.T, self.infonce_path,
+                                              normalize_k=True, return_k_hat=True)
         out = {"loss_txt": loss_txt, "loss_img": loss_img}
         labels = {n: torch.zeros(txt_q.shape[0], dtype=torch.long, device=txt_q.device) for n in ("txt", "img")}
         if materialize_logits:  # debug / parity only: this is exactly what the fused path avoids

@@ -13,6 +13,7 @@ torch; what changes is everything between them:
   enqueue    int(ptr) sync + strided copy      -> ops.enqueue_     (pointer stays on device)
   gather     list all_gather + cat             -> dist.concat_all_gather
 """
+import warnings
 from copy import deepcopy
 
 import torch
@@ -60,6 +61,12 @@ def _queue_shadow(pl_module):
     opt = getattr(pl_module, "rmcl_bf16_queue", None)
     if opt is None:
         opt = torch.is_autocast_enabled()
+        if opt and not pl_module.__dict__.get("_rmcl_warned_bf16"):
+            pl_module.__dict__["_rmcl_warned_bf16"] = True
+            warnings.warn("rmcl_b200: autocast is on and pl_module.rmcl_bf16_queue is unset -> the main-step InfoNCE reads a "
+                          "bf16 shadow of proj_queue with bf16 q^ (8 mantissa bits, fp32 accumulation; the reference's "
+                          "precision=16 einsum is fp16, 11 bits). Set pl_module.rmcl_bf16_queue = True to silence this, "
+                          "or False to keep the fp32 buffer and the fp32-accurate kernels.", stacklevel=3)
     if not opt:
         return None
     sh = pl_module.__dict__.get("_rmcl_queue_shadow")
@@ -107,28 +114,42 @@ def dequeue_and_enqueue(pl_module, keys):
 
 
 def compute_pgd(pl_module, batch, loss_name, k_modality=None):
-    """objectives.py:160-188 (moco branch): run the attacker, add delta to the image, log |delta|."""
-    img_delta = pl_module.pgd_attacker.pgd_attack(pl_module, batch, k_modality=k_modality)
-    if getattr(pl_module.pgd_attacker, "space", "pixel") == "embed":
-        batch["image_embeds_delta"] = img_delta
-    else:
-        # NB the attacker already left img_init+delta_{n-1} in batch (SURVEY F5); the reference
-        # adds delta_n on top and so do we.
-        batch["image"][0] = batch["image"][0] + img_delta
+    """objectives.py:160-188: run the attacker, add delta to the image(s), log |delta|.  The ``nlvr2_attacked``
+    branch (two images, a pair of perturbations, 167-174 and 180-183) is kept; the embedding-space attacker
+    (an extension) leaves the image alone and stores delta, the embeddings it was computed against and their masks."""
+    attacker = pl_module.pgd_attacker
+    img_delta = attacker.pgd_attack(pl_module, batch, k_modality=k_modality)
     phase = "train" if pl_module.training else "val"
-    pl_module.log(f"{loss_name}_attack/{phase}/delta", torch.linalg.norm(img_delta, dim=1).mean())
+    if loss_name == "nlvr2_attacked":
+        batch["image_0"][0] = batch["image_0"][0] + img_delta[0]
+        batch["image_1"][0] = batch["image_1"][0] + img_delta[1]
+        delta_range = (torch.linalg.norm(img_delta[0], dim=1).mean() + torch.linalg.norm(img_delta[1], dim=1).mean()) \
+            / sum(pl_module.attack_idx)
+    else:
+        if getattr(attacker, "space", "pixel") != "pixel":
+            d_txt, d_img = attacker.split_delta(img_delta)
+            batch["image_embeds_delta"], batch["text_embeds_delta"] = d_img, d_txt
+            batch["image_embeds_base"], batch["image_masks_base"] = attacker.embed_base, attacker.embed_masks
+        else:
+            # NB the attacker already left img_init+delta_{n-1} in batch (SURVEY F5); the reference
+            # adds delta_n on top and so do we.
+            batch["image"][0] = batch["image"][0] + img_delta
+        delta_range = torch.linalg.norm(img_delta, dim=1).mean()
+    pl_module.log(f"{loss_name}_attack/{phase}/delta", delta_range)
     return batch
 
 
 def _attacked_view(pl_module, batch, k_hat, prediction_original, suffix, rate_name, ret, stats):
     """One attacked/augmented view: forward, then ONE fused launch chain for the InfoNCE loss, its
     gradient, the row argmax and (``stats``: ops.QueueStats) the six pos/neg diagnostics."""
-    if "image_embeds_delta" in batch:  # embedding-space PGD (extension)
-        tr = pl_module.transformer
-        emb, masks, _, _ = tr.visual_embed(batch["image"][0], max_image_len=pl_module.hparams.config["max_image_len"],
-                                           mask_it=False)
-        infer = pl_module.infer(batch, mask_text=False, mask_image=False,
-                                image_embeds=emb + batch["image_embeds_delta"], image_masks=masks)
+    if "image_embeds_delta" in batch:
+        # embedding-space PGD (extension): the perturbation belongs to the embeddings and masks the attacker saw —
+        # visual_embed samples patches randomly, so it must not be run again here (vilt_module.py:294-304)
+        from .pgd_attack import text_embeds_delta
+        with text_embeds_delta(pl_module.text_embeddings, batch.get("text_embeds_delta")):
+            infer = pl_module.infer(batch, mask_text=False, mask_image=False,
+                                    image_embeds=batch["image_embeds_base"] + batch["image_embeds_delta"],
+                                    image_masks=batch["image_masks_base"])
     else:
         infer = pl_module.infer(batch, mask_text=False, mask_image=False)
     q_raw = pl_module.moco_head(infer["cls_feats"])

@@ -41,16 +41,35 @@ class EmaPlan:
 
     Mirrors the pairing of vilt/modules/objectives.py:222 —
     ``zip(q_layer.parameters(), k_layer.parameters())`` — for any number of layers.
+
+    The device table holds raw addresses, so the plan remembers the tensors it was built from and a
+    fingerprint of their storage (address, size, dtype, device).  ``ema_multi_`` compares it on every call
+    and rebuilds the table when a parameter was re-bound in the meantime (``param.data = ...`` — the
+    reference's own EMA line does that —, ``.to()``, ``.half()``, FSDP/DeepSpeed flattening); without the
+    check the kernel would keep updating the old storage and the key encoder would silently stop tracking.
     """
 
     def __init__(self, params_k, params_q, chunk_elems=8192):
-        params_k, params_q = list(params_k), list(params_q)
-        if len(params_k) != len(params_q):
+        self.params_k, self.params_q = list(params_k), list(params_q)
+        if len(self.params_k) != len(self.params_q):
             raise ValueError("key/query parameter lists differ in length")
+        self.chunk_elems = int(chunk_elems)
+        self.rebuilds = -1
+        self._build()
+
+    @staticmethod
+    def _print(tensors):
+        return tuple((t.data_ptr(), t.numel(), t.dtype, t.device) for t in tensors)
+
+    def fingerprint(self):
+        return self._print(self.params_k) + self._print(self.params_q)
+
+    def _build(self):
         self.groups = []  # (dtype_enum, device_table, n_chunks, keepalive)
         self.n_params = 0
+        self.rebuilds += 1
         by_dtype = {}
-        for pk, pq in zip(params_k, params_q):
+        for pk, pq in zip(self.params_k, self.params_q):
             pk, pq = getattr(pk, "data", pk), getattr(pq, "data", pq)
             _need_cuda(pk, pq)
             if pk.shape != pq.shape or pk.dtype != pq.dtype:
@@ -66,23 +85,39 @@ class EmaPlan:
             qp = (C.c_void_p * n)(*[p[1].data_ptr() for p in pairs])
             ne = (C.c_uint64 * n)(*[p[0].numel() for p in pairs])
             dt = _DT[dtype]
-            cnt = L.rmcl_ema_plan(kp, qp, ne, n, dt, chunk_elems, None)
+            cnt = L.rmcl_ema_plan(kp, qp, ne, n, dt, self.chunk_elems, None)
             if cnt < 0:
                 check(int(cnt), "rmcl_ema_plan")
             host = (_lib.EmaChunk * max(cnt, 1))()
-            cnt2 = L.rmcl_ema_plan(kp, qp, ne, n, dt, chunk_elems, host)
+            cnt2 = L.rmcl_ema_plan(kp, qp, ne, n, dt, self.chunk_elems, host)
             assert cnt2 == cnt
             raw = torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8)[: cnt * C.sizeof(_lib.EmaChunk)]
             table = raw.to(pairs[0][0].device)
             self.groups.append((dt, table, int(cnt), pairs))
+        self._fp = self.fingerprint()
+
+    def refresh(self):
+        """Rebuilds the chunk table if any tensor's storage changed since it was built; returns True if it did."""
+        if self.fingerprint() == self._fp:
+            return False
+        self._build()
+        return True
 
     @property
     def n_chunks(self):
         return sum(g[2] for g in self.groups)
 
 
-def ema_multi_(plan, m):
-    """k <- k*m + q*(1-m) for every pair in the plan, one launch per dtype group."""
+def ema_multi_(plan, m, check_storage=True):
+    """k <- k*m + q*(1-m) for every pair in the plan, one launch per dtype group.  ``check_storage`` re-validates
+    the cached addresses first (a few microseconds of host time per 100 tensors; see :class:`EmaPlan`)."""
+    if check_storage:
+        plan.refresh()
+    if _lib.ffi() == "torch":
+        tx = _lib.torch_ops()
+        for dt, table, cnt, _ in plan.groups:
+            tx.ema_multi_(table, cnt, float(m), dt)
+        return
     L = _lib.lib()
     for dt, table, cnt, _ in plan.groups:
         check(L.rmcl_ema_multi(_p(table), cnt, float(m), dt, _stream()), "rmcl_ema_multi")
@@ -106,6 +141,8 @@ def _workspace(B, Cdim, K, qdt, path, device):
 
 
 DIAG_NAMES = ("pos_dist", "pos_cosine", "pos_dot", "neg_dist", "neg_cosine", "neg_dot")
+_OUT_ORDER = ("loss", "loss_per_row", "lse", "pos", "argmax", "dq", "dk", "k_hat")          # csrc/torch_ext.cpp
+_WANT_BITS = {name: 1 << i for i, name in enumerate(_OUT_ORDER)}
 
 
 class QueueStats:
@@ -119,10 +156,13 @@ class QueueStats:
         Cd, K = queue.shape
         f32 = dict(dtype=torch.float32, device=queue.device)
         self.cos_eps = float(cos_eps)
+        self.shape = (Cd, K)
+        if _lib.ffi() == "torch":
+            self.colnorm2, self.sum_vec, self.sum_unit = _lib.torch_ops().queue_stats(queue, self.cos_eps)
+            return
         self.colnorm2 = torch.empty(K, **f32)
         self.sum_vec = torch.empty(Cd, **f32)
         self.sum_unit = torch.empty(Cd, **f32)
-        self.shape = (Cd, K)
         rc = _lib.lib().rmcl_queue_stats(_p(queue), _dt(queue), Cd, K, queue.stride(0), self.cos_eps, _p(self.colnorm2),
                                          _p(self.sum_vec), _p(self.sum_unit), _stream())
         check(rc, "rmcl_queue_stats")
@@ -144,6 +184,20 @@ def infonce_fwd_bwd(q, k, queue, temperature, *, loss_scale=1.0, normalize_k=Fal
         raise ValueError(f"shape mismatch: q {tuple(q.shape)} k {tuple(k.shape)} queue {tuple(queue.shape)}")
     if queue.stride(1) != 1:
         raise ValueError("queue must be [C,K] with K contiguous (reference layout)")
+    if diag is not None and diag.shape != (q.shape[1], queue.shape[1]):
+        raise ValueError(f"QueueStats of a {diag.shape} queue used with a {(q.shape[1], queue.shape[1])} queue")
+    if _lib.ffi() == "torch":
+        mask = sum(bit for name, bit in _WANT_BITS.items() if name in want)
+        r = _lib.torch_ops().infonce_fwd_bwd(
+            q, k, queue, float(temperature), float(loss_scale), bool(normalize_k), bool(need_grad), _lib.INFONCE_PATHS[path],
+            None if diag is None else diag.colnorm2, None if diag is None else diag.sum_vec,
+            None if diag is None else diag.sum_unit, 1e-6 if diag is None else diag.cos_eps, mask, bool(_partial_only))
+        out = {name: r[i] for i, name in enumerate(_OUT_ORDER) if name in want and r[i].numel() > 0}
+        if "loss" in out:
+            out["loss"] = out["loss"].reshape(())
+        if diag is not None:
+            out["diag"] = r[8]
+        return out
     q, k = q.detach().contiguous(), k.detach().contiguous()
     if q.dtype not in _DT:      # e.g. fp16 projections under Lightning precision=16: the kernels take fp32 / bf16
         q = q.float()
@@ -202,26 +256,40 @@ class InfoNCE(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q, k, queue, temperature, path="auto", normalize_k=False, diag=None):
-        res = infonce_fwd_bwd(q, k, queue, temperature, normalize_k=normalize_k, path=path,
-                              want=("loss", "dq", "argmax", "pos", "lse"), diag=diag)
+        want = ("loss", "dq", "argmax", "pos", "lse") + (("k_hat",) if normalize_k else ())
+        res = infonce_fwd_bwd(q, k, queue, temperature, normalize_k=normalize_k, path=path, want=want, diag=diag)
         ctx.save_for_backward(res["dq"])
         ctx.q_dtype = q.dtype
         ctx.extra = res
         dg = res["diag"] if diag is not None else torch.empty(0, device=q.device)
-        ctx.mark_non_differentiable(res["argmax"], dg)
-        return res["loss"], res["argmax"], dg
+        k_hat = res["k_hat"] if normalize_k else torch.empty(0, device=q.device)
+        ctx.mark_non_differentiable(res["argmax"], dg, k_hat)
+        return res["loss"], res["argmax"], dg, k_hat
 
     @staticmethod
-    def backward(ctx, grad_loss, _grad_argmax, _grad_diag):
+    def backward(ctx, grad_loss, _grad_argmax, _grad_diag, _grad_k_hat):
         (dq,) = ctx.saved_tensors
         return (dq * grad_loss).to(ctx.q_dtype), None, None, None, None, None, None
 
 
-def infonce_loss(q, k, queue, temperature, path="auto", normalize_k=False, diag=None):
+def infonce_loss(q, k, queue, temperature, path="auto", normalize_k=False, diag=None, return_k_hat=False):
     """(loss, argmax) — or (loss, argmax, diag[6]) when ``diag`` (QueueStats) is given — with autograd
-    support for ``q``."""
-    loss, argmax, dg = InfoNCE.apply(q, k, queue, temperature, path, normalize_k, diag)
-    return (loss, argmax) if diag is None else (loss, argmax, dg)
+    support for ``q``.  ``return_k_hat`` (with ``normalize_k``) appends the normalised key the same launch
+    produced, so a caller holding raw key projections needs no separate normalisation pass."""
+    if diag is None and _lib.ffi() == "torch":      # C++ autograd function behind torch.ops.rmcl.infonce_loss
+        _need_cuda(q, k, queue)
+        loss, argmax, k_hat = _lib.torch_ops().infonce_loss(q, k, queue, float(temperature), _lib.INFONCE_PATHS[path],
+                                                            bool(normalize_k))
+        if return_k_hat and not normalize_k:
+            raise ValueError("return_k_hat needs normalize_k=True")
+        return (loss, argmax, k_hat) if return_k_hat else (loss, argmax)
+    loss, argmax, dg, k_hat = InfoNCE.apply(q, k, queue, temperature, path, normalize_k, diag)
+    out = (loss, argmax) if diag is None else (loss, argmax, dg)
+    if return_k_hat:
+        if not normalize_k:
+            raise ValueError("return_k_hat needs normalize_k=True")
+        out = out + (k_hat,)
+    return out
 
 
 # -------------------------------------------------------------------------------- Barlow Twins
@@ -243,6 +311,13 @@ def barlow_fwd_bwd(q, k, inv_bs, lam, *, b0=0, Bl=None, w_on=1.0, w_off=None, lo
     Bg, D = q.shape
     Bl = Bg - b0 if Bl is None else Bl
     w_off = lam if w_off is None else w_off
+    if _lib.ffi() == "torch":
+        names = ("on_diag", "off_diag", "loss", "dq", "cdiag")
+        mask = sum(1 << i for i, n in enumerate(names) if n in want)
+        r = _lib.torch_ops().barlow_fwd_bwd(q, k, float(inv_bs), float(lam), int(b0), int(Bl), float(w_on), float(w_off),
+                                            float(loss_scale), _lib.BARLOW_PATHS[path], mask)
+        return {n: (r[i].reshape(()) if n in ("on_diag", "off_diag", "loss") else r[i]) if n in want else None
+                for i, n in enumerate(names)}
     L = _lib.lib()
     key = (Bg, D, q.device)
     ws = _bt_ws_cache.get(key)
@@ -341,6 +416,10 @@ def enqueue_(queue, keys, ptr, shadow=None):
     if queue.stride(1) != 1 or keys.dim() != 2 or keys.shape[1] != queue.shape[0]:
         raise ValueError(f"shape mismatch: queue {tuple(queue.shape)} keys {tuple(keys.shape)}")
     keys = keys.detach().contiguous()
+    if _lib.ffi() == "torch":
+        sh = None if shadow is None else (shadow.get(queue) if isinstance(shadow, QueueShadow) else shadow)
+        _lib.torch_ops().enqueue_(queue, keys, ptr, sh)
+        return
     if shadow is not None:
         sh = shadow.get(queue) if isinstance(shadow, QueueShadow) else shadow
         _need_cuda(sh)
@@ -363,9 +442,13 @@ def pgd_step_(delta, grad, lr, eps, mode="ref_linf", _scratch={}):
         raise ValueError("delta/grad shape mismatch")
     if not (delta.is_contiguous() and grad.is_contiguous()):
         raise ValueError("delta and grad must be contiguous")
+    if _lib.ffi() == "torch":
+        _lib.torch_ops().pgd_step_(delta, grad, float(lr), float(eps), _lib.PGD_MODES[mode])
+        return delta
     B = delta.shape[0]
     N = delta.numel() // B
-    key = (delta.device, B, N, grad.dtype)
+    # the control words of the persistent kernel are self-resetting but not shareable: one workspace per stream
+    key = (delta.device, B, N, grad.dtype, torch.cuda.current_stream().cuda_stream)
     ws = _scratch.get(key)
     if ws is None:
         nbytes = _lib.lib().rmcl_pgd_workspace_bytes(B, N, _dt(grad))
@@ -418,6 +501,15 @@ class HostStep:
             C.c_void_p(self.ws.data_ptr() + self.ws_off), self.ws.numel() - self.ws_off, _stream())
         check(rc, "rmcl_step_host")
         return self.loss_host, self.dq_host
+
+
+def infonce_launch_names(B, Cdim, K, queue_dtype, path="auto", need_grad=True):
+    """Names of the kernels one InfoNCE call with these arguments launches (rmcl_infonce_describe)."""
+    buf = C.create_string_buffer(512)
+    n = _lib.lib().rmcl_infonce_describe(B, Cdim, K, _DT[queue_dtype], _lib.INFONCE_PATHS[path], 1 if need_grad else 0, buf, 512)
+    if n < 0:
+        check(n, "rmcl_infonce_describe")
+    return tuple(buf.value.decode().split(","))
 
 
 def tc_timeline(fn):

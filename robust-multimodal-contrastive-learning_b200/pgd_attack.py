@@ -116,21 +116,57 @@ class PGDAttack:
         }
 
 
+class text_embeds_delta:
+    """Context manager: while active, ``module`` (a text-embedding layer) returns its output plus ``delta``.
+    The reference's ``infer`` has a hook for perturbed *image* embeddings (``image_embeds=``, vilt_module.py:275-311)
+    but none for the text tokens; a forward hook on ``text_embeddings`` gives the embedding-space attack the same
+    access without touching ``infer``.  ``delta=None`` is a no-op."""
+
+    def __init__(self, module, delta):
+        self.module, self.delta, self.handle = module, delta, None
+
+    def __enter__(self):
+        if self.delta is not None:
+            self.handle = self.module.register_forward_hook(lambda _m, _inp, out: out + self.delta.to(out.dtype))
+        return self
+
+    def __exit__(self, *exc):
+        if self.handle is not None:
+            self.handle.remove()
+        return False
+
+
 class PGDAttack_moco(PGDAttack):
     def __init__(self, config, mode="ref_linf", space="pixel", copy_modules=False, infonce_path="auto", inner_queue="fp32"):
-        """``inner_queue="shadow"`` lets the inner InfoNCE read the module's bf16 queue shadow (the tcgen05 kernels, ~10x
+        """``space``: "pixel" (the reference: delta on ``batch['image'][0]``), "embed" (delta on the patch+token
+        embeddings, ``[B, L_text + L_image, H]`` — 185 tokens at BASELINE cfg3 — in one tensor and one update launch)
+        or "embed_image" (image tokens only).  In the embedding spaces the attack is computed against ONE call of
+        ``visual_embed``; its output and masks are kept (``embed_base`` / ``embed_masks``, also stored into the batch
+        by ``compute_pgd``) because ViLT's ``visual_embed`` samples/permutes patches randomly whenever an image has at
+        least ``max_image_len`` patches: a second call would pair delta with different tokens.
+        ``inner_queue="shadow"`` lets the inner InfoNCE read the module's bf16 queue shadow (the tcgen05 kernels, ~10x
         cheaper per PGD step) when one exists; the default keeps the reference's fp32 inner loss (pgd_attack_vilt.py:141
         disables autocast).  The perturbation stays within the bf16 tolerance of the fp32 one (signs agree >= 99.9 %)."""
         super().__init__(config, "moco")
+        if space not in ("pixel", "embed", "embed_image"):
+            raise ValueError(f"space must be 'pixel', 'embed' or 'embed_image', got {space!r}")
         self.moco_head = None
         self.mode, self.space, self.copy_modules, self.infonce_path = mode, space, copy_modules, infonce_path
         self.inner_queue = inner_queue
+        self.embed_base = self.embed_masks = None
+        self.n_text_tokens = 0
 
     def build_mini_vilt(self, pl_module):
         self._grab(pl_module, ("moco_head",))
 
     def vilt_zero_grad(self):
         self._zero_grad_all()
+
+    def split_delta(self, delta):
+        """(text part or None, image part) of an embedding-space perturbation."""
+        if self.space == "embed":
+            return delta[:, :self.n_text_tokens], delta[:, self.n_text_tokens:]
+        return None, delta
 
     def pgd_attack(self, pl_module, batch, k_modality=None):
         self.build_mini_vilt(pl_module)
@@ -140,16 +176,22 @@ class PGDAttack_moco(PGDAttack):
         if shadow is not None:
             queue = shadow.get(pl_module.proj_queue)
         img_init = batch["image"][0]
-        if self.space == "embed":
+        if self.space != "pixel":
             with torch.no_grad():
                 base, image_masks, _, _ = self.transformer.visual_embed(
                     img_init, max_image_len=self.max_image_len, mask_it=False)
+            self.embed_base, self.embed_masks = base, image_masks
+            self.n_text_tokens = batch["text_ids"].shape[1] if self.space == "embed" else 0
+            delta0 = base.new_zeros(base.shape[0], self.n_text_tokens + base.shape[1], base.shape[2])
         else:
             base, image_masks = img_init, None
+            delta0 = torch.zeros_like(base)
 
         def loss_fn(deltas):
-            if self.space == "embed":
-                infer = self.infer(batch, image_embeds=base + deltas[0], image_masks=image_masks)
+            if self.space != "pixel":
+                d_txt, d_img = self.split_delta(deltas[0])
+                with text_embeds_delta(self.text_embeddings, d_txt):
+                    infer = self.infer(batch, image_embeds=base + d_img, image_masks=image_masks)
             else:
                 batch["image"][0] = img_init + deltas[0]  # reference side effect (pgd_attack_vilt.py:144)
                 infer = self.infer(batch)
@@ -157,7 +199,7 @@ class PGDAttack_moco(PGDAttack):
             loss, _ = ops.infonce_loss(q_raw.float(), k_modality, queue, temperature, self.infonce_path)
             return loss / (1.0 * self.adv_steps_img)
 
-        return self._pgd_loop([torch.zeros_like(base)], loss_fn)[0]
+        return self._pgd_loop([delta0], loss_fn)[0]
 
 
 class PGDAttack_bartlowtwins(PGDAttack):

@@ -142,3 +142,21 @@ def test_new_entry_points_validate_arguments_without_gpu(L):
     assert L.rmcl_gather_enqueue_p2p(one, one, one, one, 0, None, 0, one, 2, 2, 8, 16, 64, 64, None) == -1
     assert L.rmcl_gather_enqueue_p2p(one, one, one, one, 0, None, 0, one, 0, 2, 8, 16, 40, 40, None) == -1
     assert b"multiple" in L.rmcl_last_error()
+
+
+def test_torch_extension_loads_and_registers_the_operators():
+    """rmcl_b200_torch.so (csrc/torch_ext.cpp): TORCH_LIBRARY(rmcl, ...) over the C-ABI.  On a CPU-only host the
+    operators exist, reject CPU tensors (there is no CPU kernel behind any of them) and nothing computes."""
+    import torch
+    from rmcl_b200 import _lib
+    tx = _lib.torch_ops()
+    for name in ("ema_multi_", "infonce_fwd_bwd", "infonce_loss", "queue_stats", "enqueue_", "pgd_step_", "barlow_fwd_bwd"):
+        assert hasattr(tx, name), name
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        tx.pgd_step_(torch.zeros(2, 4), torch.zeros(2, 4), 0.1, 0.1, 0)
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        tx.infonce_fwd_bwd(torch.zeros(2, 4), torch.zeros(2, 4), torch.zeros(4, 8), 0.07, 1.0, False, True, 0, None, None, None,
+                           1e-6, 255, False)
+    # the schema is part of the boundary: in-place ops are declared as such
+    assert "Tensor(a!) queue" in str(torch.ops.rmcl.enqueue_.default._schema)
+    assert "Tensor(a!) delta" in str(torch.ops.rmcl.pgd_step_.default._schema)
