@@ -547,7 +547,7 @@ def run_cuda(args):
     barrier()
     for _ in range(reps):
         ev[0].record()
-        ops.ema_multi_(plan, m)
+        ops.ema_multi_(plan, m, check_storage=False)   # the bracket must hold the kernel, not the host-side address check
         ev[1].record()
         r = ops.infonce_fwd_bwd(q, k_raw, queue, tau, normalize_k=True, path=path, want=("loss", "dq", "k_hat"))
         ev[2].record()

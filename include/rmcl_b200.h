@@ -35,7 +35,12 @@ typedef enum {
   RMCL_E_WORKSPACE = -5        /* workspace smaller than rmcl_infonce_workspace_bytes()        */
 } rmcl_status;
 
-typedef enum { RMCL_F32 = 0, RMCL_BF16 = 1 } rmcl_dtype;
+/* RMCL_BF16_HILO is a QUEUE layout only (rmcl_infonce_fwd_bwd*, written by rmcl_queue_split / rmcl_enqueue_shadow):
+ * an fp32 [C,K] queue held as two bf16 planes in one [2C,K] buffer — rows [0,C) hi = bf16(x), rows [C,2C)
+ * lo = bf16(x - hi) — i.e. 16 mantissa bits per element.  The InfoNCE kernels contract it as
+ * q_hi.Q_hi + q_hi.Q_lo + q_lo.Q_hi on the bf16 tensor cores: fp32-accurate logits and gradients
+ * (the reference runs the PGD inner loss in fp32, attack/pgd_attack_vilt.py:141, on its fp32 queue buffer). */
+typedef enum { RMCL_F32 = 0, RMCL_BF16 = 1, RMCL_BF16_HILO = 2 } rmcl_dtype;
 
 typedef enum {
   RMCL_PGD_REF_LINF = 0,  /* reference rule: delta += lr*g/max(|g|_inf,1e-8); clamp(+-eps) if eps>0 */
@@ -43,8 +48,9 @@ typedef enum {
   RMCL_PGD_L2 = 2         /* delta += lr*g/max(|g|_2,1e-8); project onto the eps-ball (L2)          */
 } rmcl_pgd_mode;
 
-/* InfoNCE code paths.  AUTO picks TCGEN05 when the shape/dtype allows it (bf16 queue,
- * C in {64,128,256}, K % 8 == 0, 16-byte aligned queue) and SIMT otherwise.  Both are device
+/* InfoNCE code paths.  AUTO picks TCGEN05 when the shape/dtype allows it (bf16 queue with
+ * C in {64,128,256,512,768}, or a bf16 hi/lo queue with C in {64,128,256}; K % 8 == 0, 16-byte aligned
+ * queue) and SIMT otherwise (fp32 queues: CUDA-core kernel, exact fp32 products).  All are device
  * kernels in this library; forcing TCGEN05 on an unsupported shape is RMCL_E_UNSUPPORTED_DIM. */
 typedef enum { RMCL_INFONCE_AUTO = 0, RMCL_INFONCE_SIMT = 1, RMCL_INFONCE_TCGEN05 = 2 } rmcl_infonce_path;
 
@@ -162,7 +168,7 @@ int rmcl_infonce_fwd_bwd_diag(const void* q, rmcl_dtype q_dtype, const void* k, 
  * All ranks must make the same sequence of calls.
  */
 int rmcl_gather_enqueue_p2p(void* const* stage_ptrs_dev, void* const* flag_ptrs_dev, const void* keys_local,
-                            void* queue, rmcl_dtype queue_dtype, void* shadow_bf16, int64_t lds,
+                            void* queue, rmcl_dtype queue_dtype, void* shadow_bf16, int64_t lds, int shadow_planes,
                             int64_t* ptr_dev, int rank, int world, int B_local, int C, int64_t K,
                             int64_t ldq, void* stream);
 
@@ -227,12 +233,22 @@ int rmcl_debug_tc_timeline_words(void);
 int rmcl_enqueue(void* queue, rmcl_dtype queue_dtype, const void* keys, rmcl_dtype keys_dtype,
                  int64_t* ptr_dev, int B, int C, int64_t K, int64_t ldq, void* stream);
 
+/* Splits an fp32 queue [C,K] (row stride ldq) into the bf16 hi/lo layout RMCL_BF16_HILO describes:
+ * hilo_bf16 [2C,K] (row stride ld_hilo).  One pass, 4+4 bytes per element; afterwards rmcl_enqueue_shadow
+ * (shadow_planes = 2) keeps the copy current at B*C*4 bytes per step.
+ * replaces: nothing in the reference — it is what lets the fp32 PGD-inner InfoNCE (pgd_attack_vilt.py:141,
+ *           152-158) run on the bf16 tensor cores at fp32 accuracy instead of on cuBLAS SGEMM. */
+int rmcl_queue_split(const void* queue_f32, int C, int64_t K, int64_t ldq, void* hilo_bf16, int64_t ld_hilo,
+                     void* stream);
+
 /* Same, and the same B columns are also written (rounded to bf16) into `shadow_bf16` [C,K] (row
  * stride lds): a half-precision copy of the queue kept current at B*C*2 bytes per step, so that the
  * tcgen05 InfoNCE path can run against a checkpoint-compatible fp32 queue.
  * replaces: the per-call autocast cast of the whole queue under Lightning precision=16
- *           (objectives.py:270-272, 329: `proj_queue.clone()` + half-precision einsum). */
-int rmcl_enqueue_shadow(void* queue, rmcl_dtype queue_dtype, void* shadow_bf16, int64_t lds,
+ *           (objectives.py:270-272, 329: `proj_queue.clone()` + half-precision einsum).
+ * shadow_planes = 1: shadow is [C,K] bf16(queue).  shadow_planes = 2: shadow is the [2C,K] hi/lo pair of
+ * RMCL_BF16_HILO (its first C rows are the same bf16(queue) plane, so one buffer serves both InfoNCE modes). */
+int rmcl_enqueue_shadow(void* queue, rmcl_dtype queue_dtype, void* shadow_bf16, int64_t lds, int shadow_planes,
                         const void* keys, rmcl_dtype keys_dtype, int64_t* ptr_dev, int B, int C,
                         int64_t K, int64_t ldq, void* stream);
 

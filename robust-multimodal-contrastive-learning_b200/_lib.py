@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # exist — there is still no fallback.
 LIB_PATH = os.path.join(_HERE, os.environ.get("RMCL_B200_LIB", "librmcl_b200.so"))
 
-RMCL_F32, RMCL_BF16 = 0, 1
+RMCL_F32, RMCL_BF16, RMCL_BF16_HILO = 0, 1, 2
 PGD_MODES = {"ref_linf": 0, "sign_linf": 1, "l2": 2}
 INFONCE_PATHS = {"auto": 0, "simt": 1, "tcgen05": 2}
 BARLOW_PATHS = {"auto": 0, "direct": 1, "gram": 2}
@@ -22,7 +22,7 @@ EXPORTS = (
     "rmcl_infonce_workspace_bytes", "rmcl_infonce_fwd_bwd", "rmcl_enqueue", "rmcl_pgd_workspace_bytes", "rmcl_pgd_step", "rmcl_step_host",
     "rmcl_profile_enable", "rmcl_profile_infonce_ms", "rmcl_enqueue_shadow", "rmcl_debug_tc_timeline",
     "rmcl_debug_tc_timeline_words", "rmcl_queue_stats", "rmcl_infonce_fwd_bwd_diag",
-    "rmcl_barlow_workspace_bytes", "rmcl_barlow_fwd_bwd", "rmcl_gather_enqueue_p2p", "rmcl_infonce_describe",
+    "rmcl_barlow_workspace_bytes", "rmcl_barlow_fwd_bwd", "rmcl_gather_enqueue_p2p", "rmcl_infonce_describe", "rmcl_queue_split",
 )
 
 
@@ -68,7 +68,9 @@ def lib():
     if "RMCL_B200_LIB" in os.environ and not hasattr(L, "rmcl_enqueue_shadow"):   # A/B against an older build
         L.rmcl_enqueue_shadow = L.rmcl_debug_tc_timeline = L.rmcl_debug_tc_timeline_words = L.rmcl_version
     L.rmcl_enqueue_shadow.restype = i32
-    L.rmcl_enqueue_shadow.argtypes = [vp, i32, vp, i64, vp, i32, vp, i32, i32, i64, i64, vp]
+    L.rmcl_enqueue_shadow.argtypes = [vp, i32, vp, i64, i32, vp, i32, vp, i32, i32, i64, i64, vp]
+    L.rmcl_queue_split.restype = i32
+    L.rmcl_queue_split.argtypes = [vp, i32, i64, i64, vp, i64, vp]
     L.rmcl_debug_tc_timeline.restype = i32
     L.rmcl_debug_tc_timeline.argtypes = [vp]
     L.rmcl_debug_tc_timeline_words.restype = i32
@@ -84,7 +86,7 @@ def lib():
     L.rmcl_barlow_fwd_bwd.restype = i32
     L.rmcl_barlow_fwd_bwd.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, f32, f32, f32, f32, f32, i32, vp, vp, vp, vp, vp, vp, sz, vp]
     L.rmcl_gather_enqueue_p2p.restype = i32
-    L.rmcl_gather_enqueue_p2p.argtypes = [vp, vp, vp, vp, i32, vp, i64, vp, i32, i32, i32, i32, i64, i64, vp]
+    L.rmcl_gather_enqueue_p2p.argtypes = [vp, vp, vp, vp, i32, vp, i64, i32, vp, i32, i32, i32, i32, i64, i64, vp]
     L.rmcl_pgd_step.restype = i32
     L.rmcl_pgd_step.argtypes = [vp, i32, vp, i32, i32, i64, f32, f32, i32, vp, sz, vp]
     L.rmcl_pgd_workspace_bytes.restype = sz
@@ -125,8 +127,31 @@ def torch_ops():
                 f"rmcl_b200: {TORCH_LIB_PATH} is missing — the torch extension has not been built. "
                 "Run `python __graft_entry__.py build` (or set RMCL_B200_FFI=ctypes to use the raw C-ABI binding).")
         torch.ops.load_library(TORCH_LIB_PATH)
-        _torch_ops = torch.ops.rmcl
+        _torch_ops = _TorchOps(torch.ops.rmcl)
     return _torch_ops
+
+
+class _TorchOps:
+    """torch.ops.rmcl with the library's failures re-raised as :class:`RmclError` (a RuntimeError), so that both bindings
+    report a bad shape / unsupported path the same way."""
+
+    def __init__(self, ns):
+        self._ns = ns
+
+    def __getattr__(self, name):
+        op = getattr(self._ns, name)
+
+        def call(*args):
+            try:
+                return op(*args)
+            except RuntimeError as e:
+                msg = str(e)
+                if "rmcl_" in msg and not isinstance(e, NotImplementedError):
+                    raise RmclError(msg.split("\n")[0]) from None
+                raise
+        call.__name__ = name
+        self.__dict__[name] = call
+        return call
 
 
 def check(rc, what):

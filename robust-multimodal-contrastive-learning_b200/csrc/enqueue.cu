@@ -22,11 +22,40 @@
 
 namespace rmcl {
 
+// x = the value the queue now holds.  Plane 0 (rows [0,C)): bf16(x), the operand of the bf16 tcgen05 InfoNCE;
+// plane 1 (rows [C,2C), RMCL_BF16_HILO): bf16(x - hi), the low half of the split-operand fp32-accurate path.
+__device__ __forceinline__ void write_shadow(__nv_bfloat16* __restrict__ shadow, long long lds, int C, int planes, int c,
+                                             long long col, float x) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+  shadow[(long long)c * lds + col] = hi;
+  if (planes == 2) shadow[(long long)(C + c) * lds + col] = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// One pass over an fp32 queue: the hi/lo planes of RMCL_BF16_HILO (rmcl_queue_split).
+__global__ void __launch_bounds__(256) queue_split_kernel(const float* __restrict__ queue, int C, long long K, long long ldq,
+                                                          __nv_bfloat16* __restrict__ hilo, long long ldh) {
+  const long long n4 = K / 4;     // K % 8 == 0 is checked by the caller; rows are 16-byte aligned
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4 * C; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i / n4);
+    const long long j = (i - (long long)c * n4) * 4;
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(queue + (long long)c * ldq + j));
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      h[u] = __float2bfloat16_rn(x[u]);
+      l[u] = __float2bfloat16_rn(x[u] - __bfloat162float(h[u]));
+    }
+    *reinterpret_cast<uint2*>(hilo + (long long)c * ldh + j) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(hilo + (long long)(C + c) * ldh + j) = *reinterpret_cast<const uint2*>(l);
+  }
+}
+
 template <typename TK, typename TQ>
 __global__ void __launch_bounds__(256) enqueue_kernel(TQ* __restrict__ queue, const TK* __restrict__ keys,
                                                       long long* ptr_dev, int B, int C, long long K,
                                                       long long ldq, __nv_bfloat16* __restrict__ shadow,
-                                                      long long lds) {
+                                                      long long lds, int planes) {
   __shared__ float tile[32][33];
   __shared__ long long s_ptr;
   unsigned int* ptr_words = reinterpret_cast<unsigned int*>(ptr_dev);
@@ -48,7 +77,7 @@ __global__ void __launch_bounds__(256) enqueue_kernel(TQ* __restrict__ queue, co
       if (col >= K) col -= K;  // only reachable when ptr is not a multiple of B
       const float v = tile[tx][ty + 8 * i];
       queue[(long long)c * ldq + col] = from_f32<TQ>(v);
-      if (shadow) shadow[(long long)c * lds + col] = __float2bfloat16_rn(to_f32(from_f32<TQ>(v)));   // == bf16(queue element)
+      if (shadow) write_shadow(shadow, lds, C, planes, c, col, to_f32(from_f32<TQ>(v)));
     }
   }
   if (threadIdx.x == 0) {
@@ -64,12 +93,13 @@ __global__ void __launch_bounds__(256) enqueue_kernel(TQ* __restrict__ queue, co
 }  // namespace rmcl
 
 static int enqueue_impl(void* queue, rmcl_dtype queue_dtype, const void* keys, rmcl_dtype keys_dtype, int64_t* ptr_dev,
-                        int B, int C, int64_t K, int64_t ldq, void* shadow, int64_t lds, void* stream) {
+                        int B, int C, int64_t K, int64_t ldq, void* shadow, int64_t lds, int planes, void* stream) {
   RMCL_CHECK_ARG(queue && keys && ptr_dev, "rmcl_enqueue: null pointer");
   RMCL_CHECK_ARG(B > 0 && C > 0 && K > 0 && K < (1ll << 31), "rmcl_enqueue: bad sizes B=%d C=%d K=%lld", B, C,
                  (long long)K);
   RMCL_CHECK_ARG(ldq >= K, "rmcl_enqueue: ldq < K");
   RMCL_CHECK_ARG(!shadow || lds >= K, "rmcl_enqueue_shadow: lds < K");
+  RMCL_CHECK_ARG(!shadow || planes == 1 || planes == 2, "rmcl_enqueue_shadow: shadow_planes must be 1 or 2 (got %d)", planes);
   RMCL_CHECK_ARG(rmcl::dtype_ok(queue_dtype) && rmcl::dtype_ok(keys_dtype), "rmcl_enqueue: bad dtype");
   RMCL_CHECK_ARG(B <= K && K % B == 0, "rmcl_enqueue: queue length %lld is not a multiple of the batch %d",
                  (long long)K, B);
@@ -80,27 +110,43 @@ static int enqueue_impl(void* queue, rmcl_dtype queue_dtype, const void* keys, r
   using bf16 = __nv_bfloat16;
   bf16* sh = reinterpret_cast<bf16*>(shadow);
   if (keys_dtype == RMCL_F32 && queue_dtype == RMCL_F32)
-    rmcl::enqueue_kernel<float, float><<<grid, 256, 0, s>>>((float*)queue, (const float*)keys, p, B, C, K, ldq, sh, lds);
+    rmcl::enqueue_kernel<float, float><<<grid, 256, 0, s>>>((float*)queue, (const float*)keys, p, B, C, K, ldq, sh, lds, planes);
   else if (keys_dtype == RMCL_F32 && queue_dtype == RMCL_BF16)
-    rmcl::enqueue_kernel<float, bf16><<<grid, 256, 0, s>>>((bf16*)queue, (const float*)keys, p, B, C, K, ldq, sh, lds);
+    rmcl::enqueue_kernel<float, bf16><<<grid, 256, 0, s>>>((bf16*)queue, (const float*)keys, p, B, C, K, ldq, sh, lds, planes);
   else if (keys_dtype == RMCL_BF16 && queue_dtype == RMCL_F32)
-    rmcl::enqueue_kernel<bf16, float><<<grid, 256, 0, s>>>((float*)queue, (const bf16*)keys, p, B, C, K, ldq, sh, lds);
+    rmcl::enqueue_kernel<bf16, float><<<grid, 256, 0, s>>>((float*)queue, (const bf16*)keys, p, B, C, K, ldq, sh, lds, planes);
   else
-    rmcl::enqueue_kernel<bf16, bf16><<<grid, 256, 0, s>>>((bf16*)queue, (const bf16*)keys, p, B, C, K, ldq, sh, lds);
+    rmcl::enqueue_kernel<bf16, bf16><<<grid, 256, 0, s>>>((bf16*)queue, (const bf16*)keys, p, B, C, K, ldq, sh, lds, planes);
   RMCL_LAUNCH_OK("enqueue_kernel");
   return RMCL_OK;
 }
 
 extern "C" int rmcl_enqueue(void* queue, rmcl_dtype queue_dtype, const void* keys, rmcl_dtype keys_dtype,
                             int64_t* ptr_dev, int B, int C, int64_t K, int64_t ldq, void* stream) {
-  return enqueue_impl(queue, queue_dtype, keys, keys_dtype, ptr_dev, B, C, K, ldq, nullptr, 0, stream);
+  return enqueue_impl(queue, queue_dtype, keys, keys_dtype, ptr_dev, B, C, K, ldq, nullptr, 0, 1, stream);
 }
 
-extern "C" int rmcl_enqueue_shadow(void* queue, rmcl_dtype queue_dtype, void* shadow_bf16, int64_t lds, const void* keys,
-                                   rmcl_dtype keys_dtype, int64_t* ptr_dev, int B, int C, int64_t K, int64_t ldq,
-                                   void* stream) {
+extern "C" int rmcl_enqueue_shadow(void* queue, rmcl_dtype queue_dtype, void* shadow_bf16, int64_t lds, int shadow_planes,
+                                   const void* keys, rmcl_dtype keys_dtype, int64_t* ptr_dev, int B, int C, int64_t K,
+                                   int64_t ldq, void* stream) {
   RMCL_CHECK_ARG(shadow_bf16 != nullptr, "rmcl_enqueue_shadow: null shadow");
-  return enqueue_impl(queue, queue_dtype, keys, keys_dtype, ptr_dev, B, C, K, ldq, shadow_bf16, lds, stream);
+  return enqueue_impl(queue, queue_dtype, keys, keys_dtype, ptr_dev, B, C, K, ldq, shadow_bf16, lds, shadow_planes, stream);
+}
+
+extern "C" int rmcl_queue_split(const void* queue_f32, int C, int64_t K, int64_t ldq, void* hilo_bf16, int64_t ld_hilo,
+                                void* stream) {
+  RMCL_CHECK_ARG(queue_f32 && hilo_bf16, "rmcl_queue_split: null pointer");
+  RMCL_CHECK_ARG(C > 0 && K > 0 && K % 8 == 0 && ldq >= K && ld_hilo >= K && ldq % 4 == 0 && ld_hilo % 8 == 0,
+                 "rmcl_queue_split: bad sizes C=%d K=%lld ldq=%lld ld_hilo=%lld (K %% 8, ldq %% 4, ld_hilo %% 8 must be 0)", C,
+                 (long long)K, (long long)ldq, (long long)ld_hilo);
+  RMCL_CHECK_ARG(((reinterpret_cast<uintptr_t>(queue_f32) | reinterpret_cast<uintptr_t>(hilo_bf16)) & 15u) == 0,
+                 "rmcl_queue_split: pointers must be 16-byte aligned");
+  const int sms = rmcl::sm_count();
+  if (sms <= 0) return RMCL_E_CUDA;
+  rmcl::queue_split_kernel<<<sms * 8, 256, 0, (cudaStream_t)stream>>>((const float*)queue_f32, C, K, ldq,
+                                                                       (__nv_bfloat16*)hilo_bf16, ld_hilo);
+  RMCL_LAUNCH_OK("queue_split_kernel");
+  return RMCL_OK;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -139,7 +185,7 @@ __global__ void __launch_bounds__(256) gather_enqueue_p2p_kernel(float* const* _
                                                                  const float* __restrict__ keys_local, TQ* __restrict__ queue,
                                                                  long long* ptr_dev, int rank, int world, int B, int C,
                                                                  long long K, long long ldq, __nv_bfloat16* __restrict__ shadow,
-                                                                 long long lds) {
+                                                                 long long lds, int planes) {
   __shared__ float tile[32][33];
   __shared__ long long s_ptr;
   __shared__ unsigned int s_epoch;
@@ -215,7 +261,7 @@ __global__ void __launch_bounds__(256) gather_enqueue_p2p_kernel(float* const* _
         if (col >= K) col -= K;
         const float v = tile[tx][ty + 8 * i];
         queue[(long long)c * ldq + col] = from_f32<TQ>(v);
-        if (shadow) shadow[(long long)c * lds + col] = __float2bfloat16_rn(to_f32(from_f32<TQ>(v)));
+        if (shadow) write_shadow(shadow, lds, C, planes, c, col, to_f32(from_f32<TQ>(v)));
       }
     }
   }
@@ -231,8 +277,9 @@ __global__ void __launch_bounds__(256) gather_enqueue_p2p_kernel(float* const* _
 }  // namespace rmcl
 
 extern "C" int rmcl_gather_enqueue_p2p(void* const* stage_ptrs_dev, void* const* flag_ptrs_dev, const void* keys_local,
-                                       void* queue, rmcl_dtype queue_dtype, void* shadow_bf16, int64_t lds, int64_t* ptr_dev,
-                                       int rank, int world, int B_local, int C, int64_t K, int64_t ldq, void* stream) {
+                                       void* queue, rmcl_dtype queue_dtype, void* shadow_bf16, int64_t lds, int shadow_planes,
+                                       int64_t* ptr_dev, int rank, int world, int B_local, int C, int64_t K, int64_t ldq,
+                                       void* stream) {
   RMCL_CHECK_ARG(stage_ptrs_dev && flag_ptrs_dev && keys_local && queue && ptr_dev, "rmcl_gather_enqueue_p2p: null pointer");
   RMCL_CHECK_ARG(world > 0 && rank >= 0 && rank < world && B_local > 0 && C > 0 && K > 0 && K < (1ll << 31) && ldq >= K,
                  "rmcl_gather_enqueue_p2p: bad sizes rank=%d world=%d B=%d C=%d K=%lld", rank, world, B_local, C, (long long)K);
@@ -241,6 +288,7 @@ extern "C" int rmcl_gather_enqueue_p2p(void* const* stage_ptrs_dev, void* const*
   RMCL_CHECK_ARG(Bt <= K && K % Bt == 0, "rmcl_gather_enqueue_p2p: queue length %lld is not a multiple of the gathered batch %lld",
                  (long long)K, Bt);
   RMCL_CHECK_ARG(!shadow_bf16 || lds >= K, "rmcl_gather_enqueue_p2p: lds < K");
+  RMCL_CHECK_ARG(!shadow_bf16 || shadow_planes == 1 || shadow_planes == 2, "rmcl_gather_enqueue_p2p: shadow_planes must be 1 or 2");
   const int sms = rmcl::sm_count();
   if (sms <= 0) return RMCL_E_CUDA;
   const long long tiles = ((Bt + 31) / 32) * ((C + 31) / 32);
@@ -257,11 +305,11 @@ extern "C" int rmcl_gather_enqueue_p2p(void* const* stage_ptrs_dev, void* const*
   if (queue_dtype == RMCL_F32)
     rmcl::gather_enqueue_p2p_kernel<float><<<(unsigned)grid, 256, 0, s>>>(
         (float* const*)stage_ptrs_dev, (unsigned int* const*)flag_ptrs_dev, (const float*)keys_local, (float*)queue,
-        reinterpret_cast<long long*>(ptr_dev), rank, world, B_local, C, K, ldq, (bf16*)shadow_bf16, lds);
+        reinterpret_cast<long long*>(ptr_dev), rank, world, B_local, C, K, ldq, (bf16*)shadow_bf16, lds, shadow_planes);
   else
     rmcl::gather_enqueue_p2p_kernel<bf16><<<(unsigned)grid, 256, 0, s>>>(
         (float* const*)stage_ptrs_dev, (unsigned int* const*)flag_ptrs_dev, (const float*)keys_local, (bf16*)queue,
-        reinterpret_cast<long long*>(ptr_dev), rank, world, B_local, C, K, ldq, (bf16*)shadow_bf16, lds);
+        reinterpret_cast<long long*>(ptr_dev), rank, world, B_local, C, K, ldq, (bf16*)shadow_bf16, lds, shadow_planes);
   RMCL_LAUNCH_OK("gather_enqueue_p2p_kernel");
   return RMCL_OK;
 }

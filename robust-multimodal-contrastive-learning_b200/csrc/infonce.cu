@@ -27,12 +27,18 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 int infonce_make_plan(int B, int C, long long K, int queue_dtype, int path, bool aligned_for_tc, InfoNcePlan* p) {
   const int sms = sm_count();
   if (sms <= 0) return RMCL_E_CUDA;
+  const bool hilo = (queue_dtype == RMCL_BF16_HILO);   // fp32-accurate split-operand path (two-pass kernels, SPLIT)
   const bool wide = infonce_tc2_supports(C);   // two-pass tcgen05 variant (infonce_tc2.cu)
-  const bool tc_ok = infonce_tc_built() && aligned_for_tc && queue_dtype == RMCL_BF16 &&
-                     (C == 64 || C == 128 || C == 256 || wide) && (K % 8 == 0);
-  if (path == RMCL_INFONCE_AUTO) path = tc_ok ? RMCL_INFONCE_TCGEN05 : RMCL_INFONCE_SIMT;
+  const bool tc_ok = infonce_tc_built() && aligned_for_tc && (K % 8 == 0) &&
+                     (hilo ? infonce_tc2_split_supports(C) : (queue_dtype == RMCL_BF16 && (C == 64 || C == 128 || C == 256 || wide)));
+  if (hilo && path == RMCL_INFONCE_SIMT) {
+    set_error("a bf16 hi/lo queue (RMCL_BF16_HILO) is an operand of the tcgen05 path only");
+    return RMCL_E_UNSUPPORTED_DIM;
+  }
+  if (path == RMCL_INFONCE_AUTO) path = (tc_ok || hilo) ? RMCL_INFONCE_TCGEN05 : RMCL_INFONCE_SIMT;
   if (path == RMCL_INFONCE_TCGEN05 && !tc_ok) {
-    set_error("tcgen05 InfoNCE needs a 16B-aligned bf16 queue, C in {64,128,256,512,768}, K %% 8 == 0 (got C=%d K=%lld)", C, K);
+    set_error("tcgen05 InfoNCE needs a 16B-aligned bf16 queue with C in {64,128,256,512,768} or a bf16 hi/lo queue with C in "
+              "{64,128,256}, and K %% 8 == 0 (got C=%d K=%lld)", C, K);
     return RMCL_E_UNSUPPORTED_DIM;
   }
   if (path == RMCL_INFONCE_SIMT && C > 1024) {
@@ -45,9 +51,10 @@ int infonce_make_plan(int B, int C, long long K, int queue_dtype, int path, bool
     p->tile_cols = (C <= 512) ? 64 : 32;
   } else {
     p->rows_per_cta = 128;
-    p->tile_cols = wide ? 64 : infonce_tc_tile_cols(C);
+    p->tile_cols = (wide || hilo) ? 64 : infonce_tc_tile_cols(C);
   }
-  p->two_pass = (path == RMCL_INFONCE_TCGEN05) && wide;
+  p->split = (path == RMCL_INFONCE_TCGEN05) && hilo;
+  p->two_pass = (path == RMCL_INFONCE_TCGEN05) && (wide || hilo);
   p->row_blocks = (B + p->rows_per_cta - 1) / p->rows_per_cta;
   p->b_pad = p->row_blocks * p->rows_per_cta;
   const long long tiles = (K + p->tile_cols - 1) / p->tile_cols;
@@ -66,7 +73,7 @@ int infonce_make_plan(int B, int C, long long K, int queue_dtype, int path, bool
   p->off_khat = take(Bs * C * 4);
   p->off_inv = take(Bs * 4);
   p->off_pos2 = take(Bs * 4);
-  p->off_qhat_bf16 = take((size_t)kQhatReplicas * p->b_pad * C * 2);
+  p->off_qhat_bf16 = take((size_t)kQhatReplicas * p->b_pad * C * 2 * (p->split ? 2 : 1));   // split: rows are [q_hi | q_lo]
   p->off_m = take(S * Bs * 4);
   p->off_l = take(S * Bs * 4);
   p->off_av = take(S * Bs * 4);
@@ -78,7 +85,7 @@ int infonce_make_plan(int B, int C, long long K, int queue_dtype, int path, bool
   p->off_pdist = take(S * Bs * 4);
   p->off_diagrows = take(Bs * kDiagValues * 4);
   p->k_pad = (K + 63) / 64 * 64;
-  p->off_ptilde = take(p->two_pass ? (size_t)p->b_pad * (size_t)p->k_pad * 2 : 0);
+  p->off_ptilde = take(p->two_pass ? (size_t)p->b_pad * (size_t)p->k_pad * 2 * (p->split ? 2 : 1) : 0);   // split: hi and lo planes
   p->total = off;
   return RMCL_OK;
 }
@@ -102,7 +109,7 @@ __global__ void __launch_bounds__(128) infonce_prep_kernel(const TQ* __restrict_
                                                            float* __restrict__ q_hat, float* __restrict__ k_hat,
                                                            float* __restrict__ k_hat_out, float* __restrict__ inv_norm,
                                                            float* __restrict__ pos2, float* __restrict__ qn2,
-                                                           __nv_bfloat16* __restrict__ q_hat_bf16, int b_pad,
+                                                           __nv_bfloat16* __restrict__ q_hat_bf16, int b_pad, bool split,
                                                            unsigned int* __restrict__ counter) {
   __shared__ float red[4];
   const int row = blockIdx.x;
@@ -111,10 +118,12 @@ __global__ void __launch_bounds__(128) infonce_prep_kernel(const TQ* __restrict_
     counter[0] = 0u;
     counter[1] = 0u;   // overflow flag of the two-pass tcgen05 variant
   }
-  const size_t rep_stride = (size_t)b_pad * C;   // kQhatReplicas copies of the bf16 operand (infonce.cuh)
+  // kQhatReplicas copies of the bf16 operand (infonce.cuh); split: a row is [q_hi | q_lo], 2C wide
+  const int qw = split ? 2 * C : C;
+  const size_t rep_stride = (size_t)b_pad * qw;
   if (row >= B) {  // padding rows of the bf16 operand (the tcgen05 kernel reads whole 128-row blocks)
-    for (int c = threadIdx.x; c < C; c += 128)
-      for (int rep = 0; rep < kQhatReplicas; ++rep) q_hat_bf16[rep * rep_stride + (size_t)row * C + c] = __float2bfloat16_rn(0.f);
+    for (int c = threadIdx.x; c < qw; c += 128)
+      for (int rep = 0; rep < kQhatReplicas; ++rep) q_hat_bf16[rep * rep_stride + (size_t)row * qw + c] = __float2bfloat16_rn(0.f);
     return;
   }
   const TQ* qr = q + (size_t)row * C;
@@ -139,8 +148,12 @@ __global__ void __launch_bounds__(128) infonce_prep_kernel(const TQ* __restrict_
     if (k_hat_out) k_hat_out[(size_t)row * C + c] = kh;
     if (q_hat_bf16) {
       const __nv_bfloat16 qb = __float2bfloat16_rn(qh);
+      const __nv_bfloat16 ql = __float2bfloat16_rn(qh - __bfloat162float(qb));
 #pragma unroll
-      for (int rep = 0; rep < kQhatReplicas; ++rep) q_hat_bf16[rep * rep_stride + (size_t)row * C + c] = qb;
+      for (int rep = 0; rep < kQhatReplicas; ++rep) {
+        q_hat_bf16[rep * rep_stride + (size_t)row * qw + c] = qb;
+        if (split) q_hat_bf16[rep * rep_stride + (size_t)row * qw + C + c] = ql;
+      }
     }
     dot = fmaf(round_if(qh, bf16_mode), round_if(kh, bf16_mode), dot);
   }
@@ -456,7 +469,7 @@ static int launch_prep(const void* q, const void* k, int B, int C, float scale2,
   infonce_prep_kernel<TQ, TKK><<<rows, 128, 0, s>>>(
       (const TQ*)q, (const TKK*)k, B, C, scale2, nk, bf16_mode, (float*)(ws + p.off_qhat), (float*)(ws + p.off_khat),
       k_hat_out, (float*)(ws + p.off_inv), (float*)(ws + p.off_pos2), (float*)(ws + p.off_qn2),
-      want_bf16 ? (__nv_bfloat16*)(ws + p.off_qhat_bf16) : nullptr, p.b_pad, (unsigned int*)(ws + p.off_counter));
+      want_bf16 ? (__nv_bfloat16*)(ws + p.off_qhat_bf16) : nullptr, p.b_pad, p.split, (unsigned int*)(ws + p.off_counter));
   RMCL_LAUNCH_OK("infonce_prep_kernel");
   return RMCL_OK;
 }
@@ -502,6 +515,7 @@ extern "C" size_t rmcl_infonce_workspace_bytes(int B, int C, int64_t K, rmcl_dty
   size_t best = 0;
   for (int pth : {RMCL_INFONCE_SIMT, RMCL_INFONCE_TCGEN05}) {
     if (path != RMCL_INFONCE_AUTO && path != pth) continue;
+    if (queue_dtype == RMCL_BF16_HILO && pth == RMCL_INFONCE_SIMT) continue;
     InfoNcePlan p;
     if (infonce_make_plan(B, C, K, queue_dtype, pth, true, &p) == RMCL_OK && p.total > best) best = p.total;
   }
@@ -520,7 +534,8 @@ extern "C" int rmcl_infonce_describe(int B, int C, int64_t K, rmcl_dtype queue_d
     names = "infonce_prep_kernel,infonce_simt_kernel,infonce_finalize_kernel";
     n = 3;
   } else if (p.two_pass && need_grad) {
-    names = "infonce_prep_kernel,infonce_s_kernel,infonce_pv_kernel,infonce_finalize_kernel";
+    names = p.split ? "infonce_prep_kernel,infonce_s_kernel<split>,infonce_pv_kernel<split>,infonce_finalize_kernel"
+                    : "infonce_prep_kernel,infonce_s_kernel,infonce_pv_kernel,infonce_finalize_kernel";
     n = 4;
   } else if (p.two_pass) {
     names = "infonce_prep_kernel,infonce_s_kernel,infonce_finalize_kernel";
@@ -542,7 +557,8 @@ static int infonce_impl(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_d
   RMCL_CHECK_ARG(B > 0 && C > 0 && K > 0 && K < (1ll << 31) && ldq >= K, "rmcl_infonce_fwd_bwd: bad sizes B=%d C=%d K=%lld ldq=%lld",
                  B, C, (long long)K, (long long)ldq);
   RMCL_CHECK_ARG(tau > 0.f, "rmcl_infonce_fwd_bwd: temperature must be > 0");
-  RMCL_CHECK_ARG(dtype_ok(q_dtype) && dtype_ok(k_dtype) && dtype_ok(queue_dtype), "rmcl_infonce_fwd_bwd: bad dtype");
+  RMCL_CHECK_ARG(dtype_ok(q_dtype) && dtype_ok(k_dtype) && (dtype_ok(queue_dtype) || queue_dtype == RMCL_BF16_HILO),
+                 "rmcl_infonce_fwd_bwd: bad dtype");
   RMCL_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "rmcl_infonce_fwd_bwd: workspace must be 256B aligned");
   InfoNcePlan p;
   int rc = infonce_make_plan(B, C, K, queue_dtype, path, tc_alignment_ok(queue, ldq), &p);
@@ -554,7 +570,7 @@ static int infonce_impl(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_d
   cudaStream_t s = (cudaStream_t)stream;
   char* ws = (char*)workspace;
   const float scale2 = kLog2e / tau;
-  const bool bf16_mode = (queue_dtype == RMCL_BF16);
+  const bool bf16_mode = (queue_dtype == RMCL_BF16);   // hi/lo queues keep fp32 semantics: q^, k^ are not rounded
   const bool nk = (flags & RMCL_INFONCE_NORMALIZE_K) != 0;
   const bool want_grad = (flags & RMCL_INFONCE_NO_GRAD) == 0 && (dq || dk);
   const bool tc = (p.path == RMCL_INFONCE_TCGEN05);
@@ -581,7 +597,7 @@ static int infonce_impl(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_d
   if (tc && p.two_pass)
     rc = infonce_tc2_launch((const bf16*)(ws + p.off_qhat_bf16), queue, B, C, K, ldq, scale2, p, parts,
                             (bf16*)(ws + p.off_ptilde), p.k_pad, (unsigned int*)(ws + p.off_counter) + 1, argmax != nullptr,
-                            (want_grad || partial_only) ? 1 : 0, s);
+                            (want_grad || partial_only) ? 1 : 0, p.split, s);
   else if (tc)
     rc = infonce_tc_launch((const bf16*)(ws + p.off_qhat_bf16), queue, B, C, K, ldq, scale2, p, parts, argmax != nullptr,
                            (want_grad || partial_only) ? 1 : 0, s);
@@ -592,9 +608,10 @@ static int infonce_impl(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_d
   if (partial_only) return RMCL_OK;
 
   // merge weights + per-group partial rows: (groups-1) rows of the scalar path, kFinThreads/(C/8) rows of the 16-byte path
-  const size_t fin_rows = tc ? (size_t)(kFinThreads / (C / 8)) : (size_t)(kFinGroups - 1);
+  const bool bf16_partials = tc && !p.split;   // the split-operand path keeps its partials in fp32
+  const size_t fin_rows = bf16_partials ? (size_t)(kFinThreads / (C / 8)) : (size_t)(kFinGroups - 1);
   const size_t fin_smem = ((size_t)((p.splits + 3) & ~3) + fin_rows * C) * sizeof(float);
-  if (tc) {
+  if (bf16_partials) {
     RMCL_CUDA_OK(launch_pdl(infonce_finalize_kernel<__nv_bfloat16>, dim3(B), dim3(kFinThreads), fin_smem, s,
         B, C, p.splits, 1.f / tau, loss_scale / (float)B, loss_scale, bf16_mode, want_grad, (const float*)(ws + p.off_qhat),
         (const float*)(ws + p.off_khat), (const float*)(ws + p.off_inv), (const float*)(ws + p.off_pos2), parts.m, parts.l,

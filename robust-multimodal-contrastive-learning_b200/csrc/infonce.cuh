@@ -34,7 +34,8 @@ struct InfoNcePlan {
   int row_blocks;
   int tile_cols;        // queue columns per inner tile
   int b_pad;            // B rounded up to rows_per_cta
-  bool two_pass;        // tcgen05 with C > 256: S pass + PV pass through P~ (infonce_tc2.cu)
+  bool two_pass;        // tcgen05 with C > 256, or the split-operand path: S pass + PV pass through P~ (infonce_tc2.cu)
+  bool split;           // fp32-accurate split-operand path: queue is RMCL_BF16_HILO, Q^ and P~ are hi/lo pairs, fp32 partials
   long long k_pad;      // K rounded up to 64: row stride of P~
   // workspace carve-up (byte offsets)
   size_t off_qhat, off_khat, off_inv, off_pos2, off_qhat_bf16, off_m, off_l, off_av, off_ai, off_o, off_rowloss,
@@ -81,7 +82,8 @@ int infonce_tc_tile_cols(int C);
 bool infonce_tc2_supports(int C);
 int infonce_tc2_launch(const __nv_bfloat16* q_hat_bf16, const void* queue, int B, int C, long long K, long long ldq,
                        float scale2, const InfoNcePlan& plan, InfoNcePartials out, __nv_bfloat16* ptilde, long long k_pad,
-                       unsigned int* overflow_flag, int want_argmax, int want_o, cudaStream_t s);
+                       unsigned int* overflow_flag, int want_argmax, int want_o, bool split, cudaStream_t s);
+bool infonce_tc2_split_supports(int C);
 bool infonce_tc_built();
 
 }  // namespace rmcl

@@ -119,20 +119,53 @@ struct PgdItem {
   int chunk;
 };
 
-// ticket -> (phase, sample, chunk) in the round order described at the top of the file
+// ticket -> (phase, sample, chunk) in the round order described at the top of the file.
+// RMCL_PGD_INTERLEAVE: inside a round the items of the two phases alternate (P1 item, P2 item, P1 item, ...) instead of
+// all P1 items followed by all P2 items, so that at any moment the resident CTAs are a mix of DRAM-streaming norm items
+// and L2-served update items rather than all in the same phase.  The dependency argument is unchanged: a P2 item of batch
+// r-1 only waits for P1 items of batch r-1, which belong to the previous round, i.e. have smaller tickets.
+#ifndef RMCL_PGD_INTERLEAVE
+#define RMCL_PGD_INTERLEAVE 0
+#endif
 __device__ __forceinline__ PgdItem pgd_decode(const PgdPlan& p, long long t) {
   const int first_phase = (p.phases == 1) ? 1 : 0;  // sign mode has no norm phase
   const int rounds = p.n_batches + p.phases - 1;
   for (int r = 0; r < rounds; ++r) {
+    long long cnt[2] = {0, 0};
+    int s0[2] = {0, 0};
     for (int k = 0; k < p.phases; ++k) {
       const int b = r - k;
       if (b < 0 || b >= p.n_batches) continue;
-      const int s0 = b * p.batch;
-      const int ns = (s0 + p.batch <= p.B ? p.batch : p.B - s0);
-      const long long cnt = (long long)ns * p.chunks;
-      if (t < cnt) return PgdItem{first_phase + k, s0 + (int)(t / p.chunks), (int)(t % p.chunks)};
-      t -= cnt;
+      s0[k] = b * p.batch;
+      const int ns = (s0[k] + p.batch <= p.B ? p.batch : p.B - s0[k]);
+      cnt[k] = (long long)ns * p.chunks;
     }
+    const long long tot = cnt[0] + cnt[1];
+    if (t >= tot) {
+      t -= tot;
+      continue;
+    }
+    int k;
+    long long idx;
+#if RMCL_PGD_INTERLEAVE
+    const long long both = cnt[0] < cnt[1] ? cnt[0] : cnt[1];
+    if (t < 2 * both) {
+      k = (int)(t & 1);
+      idx = t >> 1;
+    } else {
+      k = cnt[0] > cnt[1] ? 0 : 1;
+      idx = t - both;
+    }
+#else
+    if (t < cnt[0]) {
+      k = 0;
+      idx = t;
+    } else {
+      k = 1;
+      idx = t - cnt[0];
+    }
+#endif
+    return PgdItem{first_phase + k, s0[k] + (int)(idx / p.chunks), (int)(idx % p.chunks)};
   }
   return PgdItem{-1, 0, 0};
 }

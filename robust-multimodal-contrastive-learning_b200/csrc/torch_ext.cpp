@@ -101,7 +101,9 @@ std::vector<Tensor> infonce_fwd_bwd(const Tensor& q_in, const Tensor& k_in, cons
   need_cuda(q_in, "q");
   need_cuda(k_in, "k");
   need_cuda(queue, "queue");
-  TORCH_CHECK(q_in.dim() == 2 && k_in.sizes() == q_in.sizes() && queue.dim() == 2 && queue.size(0) == q_in.size(1),
+  // queue: [C,K] fp32 / bf16, or the [2C,K] bf16 hi/lo planes of an fp32 queue (RMCL_BF16_HILO: fp32-accurate path)
+  const bool hilo = queue.dim() == 2 && q_in.dim() == 2 && queue.scalar_type() == at::kBFloat16 && queue.size(0) == 2 * q_in.size(1);
+  TORCH_CHECK(q_in.dim() == 2 && k_in.sizes() == q_in.sizes() && queue.dim() == 2 && (hilo || queue.size(0) == q_in.size(1)),
               "shape mismatch: q ", q_in.sizes(), " k ", k_in.sizes(), " queue ", queue.sizes());
   TORCH_CHECK(queue.stride(1) == 1, "queue must be [C,K] with K contiguous (reference layout)");
   c10::cuda::CUDAGuard guard(q_in.device());
@@ -109,7 +111,7 @@ std::vector<Tensor> infonce_fwd_bwd(const Tensor& q_in, const Tensor& k_in, cons
   if (q.scalar_type() != at::kFloat && q.scalar_type() != at::kBFloat16) q = q.to(at::kFloat);   // fp16 under precision=16
   if (k.scalar_type() != at::kFloat && k.scalar_type() != at::kBFloat16) k = k.to(at::kFloat);
   const int64_t B = q.size(0), C = q.size(1), K = queue.size(1), ldq = queue.stride(0);
-  const rmcl_dtype qdt = dt_of(queue, "queue");
+  const rmcl_dtype qdt = hilo ? RMCL_BF16_HILO : dt_of(queue, "queue");
   const size_t need = rmcl_infonce_workspace_bytes((int)B, (int)C, K, qdt, (int)path);
   TORCH_CHECK(need > 0, "rmcl_infonce_workspace_bytes failed: ", rmcl_last_error());
   auto ws = workspace(WsKey{0, q.get_device(), B, C, K, (int64_t)qdt * 8 + path, (int64_t)(uintptr_t)stream_of(q)}, need, q, false);
@@ -208,9 +210,11 @@ void enqueue_(Tensor& queue, const Tensor& keys_in, Tensor& ptr, const c10::opti
   Tensor keys = keys_in.detach().contiguous();
   if (shadow.has_value() && shadow->defined()) {
     const Tensor& sh = *shadow;
-    TORCH_CHECK(sh.is_cuda() && sh.scalar_type() == at::kBFloat16 && sh.sizes() == queue.sizes() && sh.stride(1) == 1,
-                "shadow must be a bf16 [C,K] CUDA tensor with K contiguous");
-    check(rmcl_enqueue_shadow(queue.data_ptr(), dt_of(queue, "queue"), sh.data_ptr(), sh.stride(0), keys.data_ptr(), dt_of(keys, "keys"),
+    TORCH_CHECK(sh.is_cuda() && sh.scalar_type() == at::kBFloat16 && sh.dim() == 2 && sh.size(1) == queue.size(1) && sh.stride(1) == 1 &&
+                    (sh.size(0) == queue.size(0) || sh.size(0) == 2 * queue.size(0)),
+                "shadow must be a bf16 [C,K] or hi/lo [2C,K] CUDA tensor with K contiguous");
+    check(rmcl_enqueue_shadow(queue.data_ptr(), dt_of(queue, "queue"), sh.data_ptr(), sh.stride(0), (int)(sh.size(0) / queue.size(0)),
+                              keys.data_ptr(), dt_of(keys, "keys"),
                               ptr.data_ptr<int64_t>(), (int)keys.size(0), (int)keys.size(1), queue.size(1), queue.stride(0),
                               stream_of(queue)),
           "rmcl_enqueue_shadow");

@@ -74,9 +74,12 @@ class P2PKeyExchange:
         from . import _lib, ops
         if keys_local.dtype != torch.float32 or not keys_local.is_contiguous() or tuple(keys_local.shape) != (self.B, self.C):
             raise ValueError("keys_local must be a contiguous fp32 [B_local, C] tensor")
-        sh = None if shadow is None else (shadow.get(queue) if isinstance(shadow, ops.QueueShadow) else shadow)
+        if shadow is None:
+            shadow = ops._find_shadow(queue)      # a registered shadow is always kept current
+        sh = None if shadow is None else (shadow.full(queue) if isinstance(shadow, ops.QueueShadow) else shadow)
         rc = _lib.lib().rmcl_gather_enqueue_p2p(
             self.stage_hdl.buffer_ptrs_dev, self.flags_hdl.buffer_ptrs_dev, keys_local.data_ptr(), queue.data_ptr(), ops._dt(queue),
-            None if sh is None else sh.data_ptr(), 0 if sh is None else sh.stride(0), ptr.data_ptr(), self.rank, self.world,
+            None if sh is None else sh.data_ptr(), 0 if sh is None else sh.stride(0),
+            1 if sh is None else sh.shape[0] // queue.shape[0], ptr.data_ptr(), self.rank, self.world,
             self.B, self.C, queue.shape[1], queue.stride(0), ops._stream())
         _lib.check(rc, "rmcl_gather_enqueue_p2p")

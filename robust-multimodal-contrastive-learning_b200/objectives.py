@@ -70,8 +70,8 @@ def _queue_shadow(pl_module):
     if not opt:
         return None
     sh = pl_module.__dict__.get("_rmcl_queue_shadow")
-    if sh is None:
-        sh = pl_module.__dict__["_rmcl_queue_shadow"] = ops.QueueShadow()
+    if sh is None:    # adopt the copy an earlier fp32-accurate call may have registered for this buffer
+        sh = pl_module.__dict__["_rmcl_queue_shadow"] = ops._find_shadow(pl_module.proj_queue) or ops.QueueShadow()
     return sh
 
 
@@ -83,9 +83,11 @@ def _enqueue_shadow(pl_module):
 
 
 def infonce_queue(pl_module):
-    """The queue operand of the main-step InfoNCE calls: the fp32 buffer (exact reference numerics,
-    SIMT path) or its bf16 shadow (tcgen05 path) when the module opted in.  The PGD inner loss always
-    uses the fp32 buffer: the reference runs it under ``autocast(False)`` (pgd_attack_vilt.py:141)."""
+    """The queue operand of the main-step InfoNCE calls: the fp32 buffer, or the bf16 plane of its shadow when the module
+    opted in / runs under autocast.  An fp32 operand is evaluated at fp32 accuracy either way: by the split-operand tcgen05
+    kernels on the shadow's hi/lo planes (C in {64,128,256}; ``infonce_path="auto"``) or by the CUDA-core kernel with exact
+    fp32 products (``infonce_path="simt"``).  The PGD inner loss always gets the fp32 buffer: the reference runs it under
+    ``autocast(False)`` (pgd_attack_vilt.py:141)."""
     sh = _queue_shadow(pl_module)
     return pl_module.proj_queue if sh is None else sh.get(pl_module.proj_queue)
 

@@ -57,12 +57,10 @@ class EmaPlan:
         self.rebuilds = -1
         self._build()
 
-    @staticmethod
-    def _print(tensors):
-        return tuple((t.data_ptr(), t.numel(), t.dtype, t.device) for t in tensors)
-
     def fingerprint(self):
-        return self._print(self.params_k) + self._print(self.params_q)
+        """Storage addresses of every tensor (~25 us of host time for the 322 tensors of ViLT-B/32): a re-bound or
+        re-allocated parameter shows up as a different address; shapes and dtypes are validated when the table is built."""
+        return [t.data_ptr() for t in self.params_k] + [t.data_ptr() for t in self.params_q]
 
     def _build(self):
         self.groups = []  # (dtype_enum, device_table, n_chunks, keepalive)
@@ -140,6 +138,10 @@ def _workspace(B, Cdim, K, qdt, path, device):
     return ws, off
 
 
+def _split_ok(queue):
+    return queue.shape[0] in (64, 128, 256) and queue.shape[1] % 8 == 0 and queue.stride(0) % 8 == 0 and queue.data_ptr() % 16 == 0
+
+
 DIAG_NAMES = ("pos_dist", "pos_cosine", "pos_dot", "neg_dist", "neg_cosine", "neg_dot")
 _OUT_ORDER = ("loss", "loss_per_row", "lse", "pos", "argmax", "dq", "dk", "k_hat")          # csrc/torch_ext.cpp
 _WANT_BITS = {name: 1 << i for i, name in enumerate(_OUT_ORDER)}
@@ -184,12 +186,21 @@ def infonce_fwd_bwd(q, k, queue, temperature, *, loss_scale=1.0, normalize_k=Fal
         raise ValueError(f"shape mismatch: q {tuple(q.shape)} k {tuple(k.shape)} queue {tuple(queue.shape)}")
     if queue.stride(1) != 1:
         raise ValueError("queue must be [C,K] with K contiguous (reference layout)")
+    if queue.dtype not in _DT:
+        raise TypeError(f"rmcl_b200 supports float32 and bfloat16 queues, got {queue.dtype}")
     if diag is not None and diag.shape != (q.shape[1], queue.shape[1]):
         raise ValueError(f"QueueStats of a {diag.shape} queue used with a {(q.shape[1], queue.shape[1])} queue")
+    hilo = False
+    if queue.dtype == torch.float32 and path != "simt" and _split_ok(queue):
+        # fp32 queue on the tensor cores: the split-operand path reads its bf16 hi/lo planes (QueueShadow), fp32-accurate
+        queue, hilo = hilo_of(queue), True
+    elif queue.dtype == torch.float32 and path == "tcgen05":
+        raise _lib.RmclError("tcgen05 InfoNCE on an fp32 queue needs C in {64,128,256}, K % 8 == 0 and a 16-byte aligned, "
+                             f"contiguous-row queue (got C={queue.shape[0]} K={queue.shape[1]})")
     if _lib.ffi() == "torch":
         mask = sum(bit for name, bit in _WANT_BITS.items() if name in want)
-        r = _lib.torch_ops().infonce_fwd_bwd(
-            q, k, queue, float(temperature), float(loss_scale), bool(normalize_k), bool(need_grad), _lib.INFONCE_PATHS[path],
+        r = _lib.torch_ops().infonce_fwd_bwd(        # detached: this op is not differentiable (the loss op is infonce_loss)
+            q.detach(), k.detach(), queue, float(temperature), float(loss_scale), bool(normalize_k), bool(need_grad), _lib.INFONCE_PATHS[path],
             None if diag is None else diag.colnorm2, None if diag is None else diag.sum_vec,
             None if diag is None else diag.sum_unit, 1e-6 if diag is None else diag.cos_eps, mask, bool(_partial_only))
         out = {name: r[i] for i, name in enumerate(_OUT_ORDER) if name in want and r[i].numel() > 0}
@@ -206,7 +217,8 @@ def infonce_fwd_bwd(q, k, queue, temperature, *, loss_scale=1.0, normalize_k=Fal
     B, Cd = q.shape
     K, ldq = queue.shape[1], queue.stride(0)
     pth = _lib.INFONCE_PATHS[path]
-    ws, off = _workspace(B, Cd, K, _dt(queue), pth, q.device)
+    qdt = _lib.RMCL_BF16_HILO if hilo else _dt(queue)
+    ws, off = _workspace(B, Cd, K, qdt, pth, q.device)
     f32 = dict(dtype=torch.float32, device=q.device)
     out = {}
     if "loss" in want:
@@ -230,7 +242,7 @@ def infonce_fwd_bwd(q, k, queue, temperature, *, loss_scale=1.0, normalize_k=Fal
             raise ValueError(f"QueueStats of a {diag.shape} queue used with a {(Cd, K)} queue")
         out["diag"] = torch.empty(len(DIAG_NAMES), **f32)
         rc = _lib.lib().rmcl_infonce_fwd_bwd_diag(
-            _p(q), _dt(q), _p(k), _dt(k), _p(queue), _dt(queue), B, Cd, K, ldq, float(temperature), float(loss_scale),
+            _p(q), _dt(q), _p(k), _dt(k), _p(queue), qdt, B, Cd, K, ldq, float(temperature), float(loss_scale),
             flags, pth, _p(out.get("loss")), _p(out.get("loss_per_row")), _p(out.get("lse")), _p(out.get("pos")),
             _p(out.get("argmax")), _p(out.get("dq")), _p(out.get("dk")), _p(out.get("k_hat")),
             _p(diag.colnorm2), _p(diag.sum_vec), _p(diag.sum_unit), diag.cos_eps, _p(out["diag"]),
@@ -238,7 +250,7 @@ def infonce_fwd_bwd(q, k, queue, temperature, *, loss_scale=1.0, normalize_k=Fal
         check(rc, "rmcl_infonce_fwd_bwd_diag")
         return out
     rc = _lib.lib().rmcl_infonce_fwd_bwd(
-        _p(q), _dt(q), _p(k), _dt(k), _p(queue), _dt(queue), B, Cd, K, ldq, float(temperature), float(loss_scale),
+        _p(q), _dt(q), _p(k), _dt(k), _p(queue), qdt, B, Cd, K, ldq, float(temperature), float(loss_scale),
         flags, pth, _p(out.get("loss")), _p(out.get("loss_per_row")), _p(out.get("lse")), _p(out.get("pos")),
         _p(out.get("argmax")), _p(out.get("dq")), _p(out.get("dk")), _p(out.get("k_hat")),
         C.c_void_p(ws.data_ptr() + off), ws.numel() - off, _stream())
@@ -278,6 +290,12 @@ def infonce_loss(q, k, queue, temperature, path="auto", normalize_k=False, diag=
     produced, so a caller holding raw key projections needs no separate normalisation pass."""
     if diag is None and _lib.ffi() == "torch":      # C++ autograd function behind torch.ops.rmcl.infonce_loss
         _need_cuda(q, k, queue)
+        if queue.dim() != 2 or queue.shape[0] != q.shape[-1]:
+            raise ValueError(f"shape mismatch: q {tuple(q.shape)} queue {tuple(queue.shape)}")
+        if queue.dtype == torch.float32 and path != "simt" and _split_ok(queue):
+            queue = hilo_of(queue)                 # fp32-accurate split-operand path (see infonce_fwd_bwd)
+        elif queue.dtype == torch.float32 and path == "tcgen05":
+            raise _lib.RmclError("tcgen05 InfoNCE on an fp32 queue needs C in {64,128,256}, K % 8 == 0 and an aligned queue")
         loss, argmax, k_hat = _lib.torch_ops().infonce_loss(q, k, queue, float(temperature), _lib.INFONCE_PATHS[path],
                                                             bool(normalize_k))
         if return_k_hat and not normalize_k:
@@ -382,14 +400,17 @@ def barlow_twins_loss(q, k, inv_bs, lam, gather=None):
 
 # -------------------------------------------------------------------------------- enqueue
 class QueueShadow:
-    """bf16 copy of an fp32 queue buffer, kept current by ``enqueue_(..., shadow=...)``.
+    """bf16 hi/lo copy of an fp32 queue buffer, kept current by ``enqueue_``.
 
-    The reference's ``proj_queue`` is an fp32 buffer (vilt_module.py:92) and its half-precision
-    einsum under Lightning ``precision=16`` re-casts all C*K elements on every call
-    (objectives.py:270-272).  The shadow is that cast done once; afterwards each enqueue writes the
-    B new columns into both copies in the same launch, so the tcgen05 InfoNCE kernel has its
-    bf16 operand for B*C*2 bytes per step.  ``get()`` rebuilds the copy if the fp32 buffer was
-    replaced or modified in place by anything else (``load_state_dict``, ``.to()``)."""
+    The reference's ``proj_queue`` is an fp32 buffer (vilt_module.py:92).  Its half-precision einsum under Lightning
+    ``precision=16`` re-casts all C*K elements on every call (objectives.py:270-272), and its fp32 PGD-inner einsum
+    (pgd_attack_vilt.py:141,152-158) is a CUDA-core / SGEMM contraction.  The shadow is one [2C, K] bf16 buffer:
+      rows [0, C)   hi = bf16(queue)          -> ``get()``: the operand of the bf16 tcgen05 InfoNCE (main step under autocast)
+      rows [C, 2C)  lo = bf16(queue - hi)     -> ``get_hilo()``: with hi, 16 mantissa bits per element — the operand of the
+                                                 fp32-accurate split-operand tcgen05 InfoNCE (RMCL_BF16_HILO)
+    built by one pass (``rmcl_queue_split``); afterwards each enqueue writes the B new columns into the queue and both
+    planes in the same launch (B*C*4 bytes per step).  The copy is rebuilt if the fp32 buffer was replaced or modified
+    in place by anything else (``load_state_dict``, ``.to()``).  A queue that is not fp32 gets a one-plane copy."""
 
     def __init__(self):
         self.tensor, self._key = None, None
@@ -398,35 +419,113 @@ class QueueShadow:
     def _state(queue):
         return (queue.data_ptr(), tuple(queue.shape), queue._version)
 
-    def get(self, queue):
+    def _current(self, queue):
         _need_cuda(queue)
         if self.tensor is None or self._key != self._state(queue):
-            self.tensor = queue.detach().to(torch.bfloat16).contiguous()   # one-off cast (init / checkpoint load)
+            self.tensor = queue_split(queue)      # one-off (init / checkpoint load)
             self._key = self._state(queue)
+            _register_shadow(queue, self)
         return self.tensor
+
+    def get(self, queue):
+        """[C, K] bf16(queue): the hi plane (a view of the first C rows)."""
+        return self._current(queue)[: queue.shape[0]]
+
+    def get_hilo(self, queue):
+        """[2C, K] hi/lo planes, or None when the queue is not an fp32 buffer (nothing to split)."""
+        t = self._current(queue)
+        return t if t.shape[0] == 2 * queue.shape[0] else None
+
+    def full(self, queue):
+        """The whole shadow buffer ([C, K] or [2C, K]) — what the enqueue kernels keep current."""
+        return self._current(queue)
+
+
+def queue_split(queue):
+    """[2C, K] bf16 hi/lo planes of an fp32 ``queue`` [C, K] (rmcl_queue_split); a non-fp32 queue yields its plain
+    [C, K] bf16 copy."""
+    _need_cuda(queue)
+    if queue.dim() != 2 or queue.stride(1) != 1:
+        raise ValueError("queue must be [C,K] with K contiguous (reference layout)")
+    if queue.dtype != torch.float32:
+        return queue.detach().to(torch.bfloat16).contiguous()
+    Cd, K = queue.shape
+    out = torch.empty(2 * Cd, K, dtype=torch.bfloat16, device=queue.device)
+    if K % 8 == 0 and queue.stride(0) % 4 == 0 and queue.data_ptr() % 16 == 0:
+        rc = _lib.lib().rmcl_queue_split(_p(queue), Cd, K, queue.stride(0), _p(out), out.stride(0), _stream())
+        check(rc, "rmcl_queue_split")
+    else:       # ragged queue: shapes the tensor-core paths do not take anyway; same arithmetic in torch
+        hi = queue.detach().to(torch.bfloat16)
+        out[:Cd] = hi
+        out[Cd:] = (queue.detach() - hi.float()).to(torch.bfloat16)
+    return out
+
+
+# queue storage -> its shadow: lets the fp32-accurate InfoNCE find the hi/lo planes of a queue it is handed, and lets
+# every enqueue keep a shadow current even when the caller did not pass it (the kernels write through raw pointers, so
+# torch's version counter would not notice the change).
+_shadows = {}
+
+
+def _register_shadow(queue, shadow):
+    import weakref
+    for key in [k for k, (wr, _) in _shadows.items() if wr() is None]:
+        del _shadows[key]
+    _shadows[queue.data_ptr()] = (weakref.ref(queue), shadow)
+
+
+def _find_shadow(queue):
+    ent = _shadows.get(queue.data_ptr())
+    if ent is None:
+        return None
+    wr, shadow = ent
+    alive = wr()
+    if alive is None or alive.data_ptr() != queue.data_ptr() or alive.shape != queue.shape:
+        del _shadows[queue.data_ptr()]
+        return None
+    return shadow
+
+
+def hilo_of(queue, create=True):
+    """The [2C, K] hi/lo planes of an fp32 ``queue`` from its registered shadow (created and registered on first use)."""
+    shadow = _find_shadow(queue)
+    if shadow is None:
+        if not create:
+            return None
+        shadow = QueueShadow()
+    return shadow.get_hilo(queue)
 
 
 def enqueue_(queue, keys, ptr, shadow=None):
     """queue[:, ptr:ptr+B] = keys.T; ptr = (ptr+B) % K — on device, no host sync
     (objectives.py:244-248).  ``ptr`` is the int64[1] buffer ``proj_queue_ptr``.
-    ``shadow`` (a :class:`QueueShadow` or a bf16 [C,K] tensor) receives the same columns."""
+    ``shadow`` (a :class:`QueueShadow`, or a bf16 [C,K] / hi-lo [2C,K] tensor) receives the same columns; a shadow
+    registered for this queue (``hilo_of`` / ``QueueShadow.get``) is kept current even when not passed."""
     _need_cuda(queue, keys, ptr)
     if ptr.dtype != torch.int64 or ptr.numel() != 1:
         raise TypeError("ptr must be an int64 tensor with one element")
     if queue.stride(1) != 1 or keys.dim() != 2 or keys.shape[1] != queue.shape[0]:
         raise ValueError(f"shape mismatch: queue {tuple(queue.shape)} keys {tuple(keys.shape)}")
     keys = keys.detach().contiguous()
+    registered = _find_shadow(queue)
+    if shadow is None:
+        shadow = registered
+    elif registered is not None and registered is not shadow:
+        registered._key = None        # another copy is being kept current instead: rebuild this one on its next use
+    sh = None
+    if shadow is not None:
+        sh = shadow.full(queue) if isinstance(shadow, QueueShadow) else shadow
+        _need_cuda(sh)
+        if sh.dtype != torch.bfloat16 or sh.shape[1] != queue.shape[1] or sh.stride(1) != 1 or \
+                sh.shape[0] not in (queue.shape[0], 2 * queue.shape[0]):
+            raise ValueError("shadow must be a bf16 [C,K] or hi/lo [2C,K] tensor with K contiguous")
     if _lib.ffi() == "torch":
-        sh = None if shadow is None else (shadow.get(queue) if isinstance(shadow, QueueShadow) else shadow)
         _lib.torch_ops().enqueue_(queue, keys, ptr, sh)
         return
-    if shadow is not None:
-        sh = shadow.get(queue) if isinstance(shadow, QueueShadow) else shadow
-        _need_cuda(sh)
-        if sh.dtype != torch.bfloat16 or sh.shape != queue.shape or sh.stride(1) != 1:
-            raise ValueError("shadow must be a bf16 [C,K] tensor with K contiguous")
-        rc = _lib.lib().rmcl_enqueue_shadow(_p(queue), _dt(queue), _p(sh), sh.stride(0), _p(keys), _dt(keys), _p(ptr),
-                                            keys.shape[0], keys.shape[1], queue.shape[1], queue.stride(0), _stream())
+    if sh is not None:
+        rc = _lib.lib().rmcl_enqueue_shadow(_p(queue), _dt(queue), _p(sh), sh.stride(0), sh.shape[0] // queue.shape[0], _p(keys),
+                                            _dt(keys), _p(ptr), keys.shape[0], keys.shape[1], queue.shape[1], queue.stride(0),
+                                            _stream())
         check(rc, "rmcl_enqueue_shadow")
         return
     rc = _lib.lib().rmcl_enqueue(_p(queue), _dt(queue), _p(keys), _dt(keys), _p(ptr), keys.shape[0], keys.shape[1],
@@ -506,7 +605,8 @@ class HostStep:
 def infonce_launch_names(B, Cdim, K, queue_dtype, path="auto", need_grad=True):
     """Names of the kernels one InfoNCE call with these arguments launches (rmcl_infonce_describe)."""
     buf = C.create_string_buffer(512)
-    n = _lib.lib().rmcl_infonce_describe(B, Cdim, K, _DT[queue_dtype], _lib.INFONCE_PATHS[path], 1 if need_grad else 0, buf, 512)
+    qdt = _lib.RMCL_BF16_HILO if queue_dtype == "hilo" else _DT[queue_dtype]
+    n = _lib.lib().rmcl_infonce_describe(B, Cdim, K, qdt, _lib.INFONCE_PATHS[path], 1 if need_grad else 0, buf, 512)
     if n < 0:
         check(n, "rmcl_infonce_describe")
     return tuple(buf.value.decode().split(","))

@@ -144,9 +144,11 @@ class PGDAttack_moco(PGDAttack):
         ``visual_embed``; its output and masks are kept (``embed_base`` / ``embed_masks``, also stored into the batch
         by ``compute_pgd``) because ViLT's ``visual_embed`` samples/permutes patches randomly whenever an image has at
         least ``max_image_len`` patches: a second call would pair delta with different tokens.
-        ``inner_queue="shadow"`` lets the inner InfoNCE read the module's bf16 queue shadow (the tcgen05 kernels, ~10x
-        cheaper per PGD step) when one exists; the default keeps the reference's fp32 inner loss (pgd_attack_vilt.py:141
-        disables autocast).  The perturbation stays within the bf16 tolerance of the fp32 one (signs agree >= 99.9 %)."""
+        The inner loss keeps the reference's fp32 semantics (pgd_attack_vilt.py:141 disables autocast): with
+        ``infonce_path="auto"`` it runs on the tensor cores at fp32 accuracy (split bf16 operands over the hi/lo planes of the
+        queue shadow, C in {64,128,256}), with ``"simt"`` on the CUDA cores with exact fp32 products.
+        ``inner_queue="shadow"`` trades that for the plain bf16 kernels on the shadow's bf16 plane (cheapest; the
+        perturbation stays within the bf16 tolerance of the fp32 one, signs agree >= 99.9 %)."""
         super().__init__(config, "moco")
         if space not in ("pixel", "embed", "embed_image"):
             raise ValueError(f"space must be 'pixel', 'embed' or 'embed_image', got {space!r}")

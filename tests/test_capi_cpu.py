@@ -139,9 +139,16 @@ def test_new_entry_points_validate_arguments_without_gpu(L):
                                  one, 0, None) == -1
     assert b"bad path" in L.rmcl_last_error()
     # peer-memory exchange: rank inside the world, queue length a multiple of the gathered batch
-    assert L.rmcl_gather_enqueue_p2p(one, one, one, one, 0, None, 0, one, 2, 2, 8, 16, 64, 64, None) == -1
-    assert L.rmcl_gather_enqueue_p2p(one, one, one, one, 0, None, 0, one, 0, 2, 8, 16, 40, 40, None) == -1
+    assert L.rmcl_gather_enqueue_p2p(one, one, one, one, 0, None, 0, 1, one, 2, 2, 8, 16, 64, 64, None) == -1
+    assert L.rmcl_gather_enqueue_p2p(one, one, one, one, 0, None, 0, 1, one, 0, 2, 8, 16, 40, 40, None) == -1
     assert b"multiple" in L.rmcl_last_error()
+    assert L.rmcl_gather_enqueue_p2p(one, one, one, one, 0, one, 64, 3, one, 0, 2, 8, 16, 64, 64, None) == -1
+    assert b"shadow_planes" in L.rmcl_last_error()
+    # hi/lo queue planes: sizes and alignment are checked before anything is launched
+    assert L.rmcl_queue_split(one, 64, 100, 100, one, 100, None) == -1            # K % 8 != 0
+    assert b"rmcl_queue_split" in L.rmcl_last_error()
+    assert L.rmcl_enqueue_shadow(one, 0, one, 64, 3, one, 0, one, 8, 16, 64, 64, None) == -1
+    assert b"shadow_planes" in L.rmcl_last_error()
 
 
 def test_torch_extension_loads_and_registers_the_operators():

@@ -92,9 +92,11 @@ def test_other_ops_bindings_agree(ops, monkeypatch):
         a, b = _both(monkeypatch, lambda: ops.barlow_fwd_bwd(qb, kb, 1 / 64, 0.0051, path=bpath))
         for name in a:
             assert torch.equal(a[name], b[name]), (bpath, name)
-    with pytest.raises(RuntimeError):
-        monkeypatch.setenv("RMCL_B200_FFI", "torch")
-        ops.pgd_step_(torch.zeros(2, 4, device=DEV), torch.zeros(2, 5, device=DEV), 0.1, 0.1)
+    from rmcl_b200._lib import RmclError
+    for ffi in ("ctypes", "torch"):                     # both bindings report a library error as RmclError
+        monkeypatch.setenv("RMCL_B200_FFI", ffi)
+        with pytest.raises(RmclError):
+            ops.enqueue_(torch.zeros(16, 30, device=DEV), torch.zeros(8, 16, device=DEV), torch.zeros(1, dtype=torch.int64, device=DEV))
 
 
 def test_cxx_autograd_loss_matches_the_oracle(ops, monkeypatch):
