@@ -574,9 +574,13 @@ def run_cuda(args):
     traffic, traffic_meta = traffic_table()
     kernels = {}
     kernels["ema"] = hbm_entry(12.0 * n_params, kern_ms["ema"], pk_peak)                 # read k, read q, write k (fp32)
-    kernels["infonce_partial"] = tensor_entry(flops_infonce, kern_ms["infonce_partial"], pk_peak)
-    kernels["infonce_call"] = dict(tensor_entry(flops_infonce, kern_ms["infonce_call"], pk_peak),
-                                   what="the whole rmcl_infonce_fwd_bwd call (every launch of it) inside the step")
+    infonce_names = ops.infonce_launch_names(B, C, K, queue.dtype, path)
+    fused = infonce_names == ("infonce_fused_kernel",)
+    if not fused:       # three-launch chain: the split-K flash kernel bracketed on its own
+        kernels["infonce_partial"] = tensor_entry(flops_infonce, kern_ms["infonce_partial"], pk_peak)
+    kernels["infonce_call"] = dict(tensor_entry(flops_infonce, kern_ms["infonce_call"], pk_peak), launches=list(infonce_names),
+                                   what="the whole rmcl_infonce_fwd_bwd call inside the step" +
+                                        (": ONE cooperative kernel (prep rows | tcgen05 flash pass | finalize rows)" if fused else ""))
     kernels["enqueue"] = hbm_entry(world * B * C * (4 + 2), kern_ms["enqueue"], pk_peak)  # read fp32 keys, write bf16 columns
     kernels["enqueue"]["kernel"] = ("gather_enqueue_p2p_kernel" if p2p is not None else
                                     ("ncclAllGather + enqueue_kernel" if world > 1 else "enqueue_kernel"))
@@ -602,6 +606,9 @@ def run_cuda(args):
             for j in range(n_b2b):
                 ops.infonce_fwd_bwd(q, k_raw, queues[j % n_copies], tau, normalize_k=True, path=path, want=("loss", "dq", "k_hat"))
 
+        if "infonce_partial" not in kernels:    # fused build: the flash pass alone exists only as this measurement
+            kernels["infonce_partial"] = {"bound": "tensor", "unit": "TFLOP/s", "traffic": traffic.get("infonce_partial"),
+                                          "what": "the tcgen05 flash pass alone (RMCL_INFONCE_DEBUG_PARTIAL_ONLY), consecutive launches"}
         for tag, fn in (("infonce_partial", partial_batch), ("infonce_call", call_batch)):
             fn()
             torch.cuda.synchronize()
@@ -729,14 +736,14 @@ def run_cuda(args):
             kernels[tag] = dict(ent, traffic=traffic.get(tag), shape=[Bb, Db], timing="CUDA graph of 10 calls")
             del graph, qb_, kb_
     for name in ("infonce_prep", "infonce_finalize"):
-        if kern_ms[name] > 0:
+        if kern_ms[name] > 0 and not fused:
             kernels[name] = {"ms": kern_ms[name]}
-    dominant = max(("ema", "infonce_partial", "enqueue"), key=lambda n: kern_ms[n])
-    roofline = dict(kernels[dominant], kernel={"ema": "ema_multi_kernel", "infonce_partial": "infonce_tc_kernel",
+    dominant = max(("ema", "infonce_call", "enqueue"), key=lambda n: kern_ms[n])
+    roofline = dict(kernels[dominant], kernel={"ema": "ema_multi_kernel", "infonce_call": "+".join(infonce_names),
                                                "enqueue": kernels["enqueue"]["kernel"]}[dominant],
                     peak_source=pk_peak["source"], traffic_capture=traffic_meta)
 
-    launches = ["ema_multi_kernel"] + list(ops.infonce_launch_names(B, C, K, queue.dtype, path)) + \
+    launches = ["ema_multi_kernel"] + list(infonce_names) + \
                ["gather_enqueue_p2p_kernel" if p2p is not None else "enqueue_kernel"]
     n_blocks = len(blocks)
     line = {

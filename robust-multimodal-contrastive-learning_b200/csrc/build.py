@@ -22,17 +22,46 @@ def needs_rebuild():
 
 
 def build(force=False, verbose=False, out=OUT, defines=()):
-    """``out``/``defines`` build an experiment variant next to the product library (tools/ab_*.py)."""
+    """``out``/``defines`` build an experiment variant next to the product library (tools/ab_*.py).
+    Every source is compiled to its own object (in parallel, cached by modification time under build/obj) and the
+    objects are linked into the shared library: a change to one kernel costs one nvcc invocation."""
     if out == OUT and not force and not needs_rebuild():
         return OUT
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + FLAGS + list(defines) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES
-    r = subprocess.run(cmd, cwd=HERE, capture_output=True, text=True)
+    tag = "product" if (out == OUT and not defines) else os.path.splitext(os.path.basename(out))[0]
+    objdir = os.path.join(os.path.dirname(os.path.dirname(HERE)), "build", "obj", tag)
+    os.makedirs(objdir, exist_ok=True)
+    cflags = [f for f in FLAGS if f not in ("-shared", "-cudart", "static")] + list(defines) + (["-Xptxas", "-v"] if verbose else [])
+    headers = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(".cuh")]
+    headers.append(os.path.join(os.path.dirname(os.path.dirname(HERE)), "include", "rmcl_b200.h"))
+    newest_header = max(os.path.getmtime(h) for h in headers)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        stale = force or not os.path.isfile(obj) or os.path.getmtime(obj) < max(newest_header, os.path.getmtime(os.path.join(HERE, src)))
+        if not stale:
+            return obj, None
+        r = subprocess.run([nvcc] + cflags + ["-c", src, "-o", obj], cwd=HERE, capture_output=True, text=True)
+        return obj, r
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    log = ""
+    for obj, r in results:
+        if r is None:
+            continue
+        log += r.stdout + r.stderr
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError(f"nvcc failed compiling {os.path.basename(obj)}")
+    r = subprocess.run([nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] +
+                       [obj for obj, _ in results], cwd=HERE, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building librmcl_b200.so")
+        raise RuntimeError("nvcc failed linking librmcl_b200.so")
     if verbose:
-        print(r.stderr)
+        print(log)
     return out
 
 

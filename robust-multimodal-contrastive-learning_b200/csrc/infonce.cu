@@ -15,12 +15,12 @@
 //
 // bf16 mode (queue_dtype == bf16) mirrors the reference under autocast: q^ and k^ are rounded to
 // bf16 before the dot products, accumulation is fp32, the Jacobian uses the fp32 q^.
+#include <stdlib.h>
+
 #include "infonce.cuh"
+#include "infonce_rows.cuh"
 
 namespace rmcl {
-
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -90,27 +90,9 @@ int infonce_make_plan(int B, int C, long long K, int queue_dtype, int path, bool
   return RMCL_OK;
 }
 
-__device__ __forceinline__ float round_if(float x, bool to_bf16) {
-  return to_bf16 ? __bfloat162float(__float2bfloat16_rn(x)) : x;
-}
-
-__device__ __forceinline__ float block_sum_128(float v, float* red) {
-  v = warp_sum(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  return red[0] + red[1] + red[2] + red[3];
-}
-
 // ------------------------------------------------------------------------------------ prep
 template <typename TQ, typename TKK>
-__global__ void __launch_bounds__(128) infonce_prep_kernel(const TQ* __restrict__ q, const TKK* __restrict__ k, int B,
-                                                           int C, float scale2, bool normalize_k, bool bf16_mode,
-                                                           float* __restrict__ q_hat, float* __restrict__ k_hat,
-                                                           float* __restrict__ k_hat_out, float* __restrict__ inv_norm,
-                                                           float* __restrict__ pos2, float* __restrict__ qn2,
-                                                           __nv_bfloat16* __restrict__ q_hat_bf16, int b_pad, bool split,
-                                                           unsigned int* __restrict__ counter) {
+__global__ void __launch_bounds__(128) infonce_prep_kernel(const PrepArgs a, unsigned int* __restrict__ counter) {
   __shared__ float red[4];
   const int row = blockIdx.x;
   if (threadIdx.x == 0) pdl_trigger();   // the partial kernel may set itself up while this one runs
@@ -118,358 +100,46 @@ __global__ void __launch_bounds__(128) infonce_prep_kernel(const TQ* __restrict_
     counter[0] = 0u;
     counter[1] = 0u;   // overflow flag of the two-pass tcgen05 variant
   }
-  // kQhatReplicas copies of the bf16 operand (infonce.cuh); split: a row is [q_hi | q_lo], 2C wide
-  const int qw = split ? 2 * C : C;
-  const size_t rep_stride = (size_t)b_pad * qw;
-  if (row >= B) {  // padding rows of the bf16 operand (the tcgen05 kernel reads whole 128-row blocks)
-    for (int c = threadIdx.x; c < qw; c += 128)
-      for (int rep = 0; rep < kQhatReplicas; ++rep) q_hat_bf16[rep * rep_stride + (size_t)row * qw + c] = __float2bfloat16_rn(0.f);
-    return;
-  }
-  const TQ* qr = q + (size_t)row * C;
-  const TKK* kr = k + (size_t)row * C;
-  float sq = 0.f, sk = 0.f;
-  for (int c = threadIdx.x; c < C; c += 128) {
-    const float a = to_f32(qr[c]), b = to_f32(kr[c]);
-    sq = fmaf(a, a, sq);
-    sk = fmaf(b, b, sk);
-  }
-  sq = block_sum_128(sq, red);
-  sk = block_sum_128(sk, red);
-  const float qn = fmaxf(sqrtf(sq), 1e-12f);
-  const float kn = normalize_k ? fmaxf(sqrtf(sk), 1e-12f) : 1.f;
-  float dot = 0.f, qq = 0.f;
-  for (int c = threadIdx.x; c < C; c += 128) {
-    const float qh = __fdiv_rn(to_f32(qr[c]), qn);
-    qq = fmaf(qh, qh, qq);
-    const float kh = normalize_k ? __fdiv_rn(to_f32(kr[c]), kn) : to_f32(kr[c]);
-    q_hat[(size_t)row * C + c] = qh;
-    k_hat[(size_t)row * C + c] = kh;
-    if (k_hat_out) k_hat_out[(size_t)row * C + c] = kh;
-    if (q_hat_bf16) {
-      const __nv_bfloat16 qb = __float2bfloat16_rn(qh);
-      const __nv_bfloat16 ql = __float2bfloat16_rn(qh - __bfloat162float(qb));
-#pragma unroll
-      for (int rep = 0; rep < kQhatReplicas; ++rep) {
-        q_hat_bf16[rep * rep_stride + (size_t)row * qw + c] = qb;
-        if (split) q_hat_bf16[rep * rep_stride + (size_t)row * qw + C + c] = ql;
-      }
-    }
-    dot = fmaf(round_if(qh, bf16_mode), round_if(kh, bf16_mode), dot);
-  }
-  dot = block_sum_128(dot, red);
-  qq = block_sum_128(qq, red);
-  if (threadIdx.x == 0) {
-    inv_norm[row] = __fdiv_rn(1.f, qn);
-    pos2[row] = dot * scale2;
-    qn2[row] = qq;
-  }
+  prep_row<TQ, TKK>(a, row, red);
 }
 
 // -------------------------------------------------------------------------------- finalize
-constexpr int kFinGroups = 2;                 // split groups streaming the partials concurrently (512 threads:
-                                              // two CTAs per SM, so B=256 rows are one wave on 148 SMs)
-constexpr int kFinThreads = 256 * kFinGroups;
+constexpr int kFinThreads = 512;              // two CTAs per SM, so B=256 rows are one wave on 148 SMs
 
-__device__ __forceinline__ float ld_partial(const float* p) { return __ldcs(p); }
-__device__ __forceinline__ float ld_partial(const __nv_bfloat16* p) {
-  return __bfloat162float(__ushort_as_bfloat16(__ldcs(reinterpret_cast<const unsigned short*>(p))));
+// TP: element type of the partial accumulators (fp32 from the SIMT / split-operand kernels, bf16 from the bf16 tcgen05 kernels)
+template <typename TP>
+__global__ void __launch_bounds__(kFinThreads, 2) infonce_finalize_kernel(const FinArgs a) {
+  extern __shared__ float fin_smem[];
+  pdl_wait();                                 // launched early (PDL): the partials must be complete
+  finalize_row<TP, kFinThreads>(a, blockIdx.x, fin_smem);
 }
 
-// TP: element type of the partial accumulators (fp32 from the SIMT kernel, bf16 from the tcgen05 kernel)
-template <typename TP>
-__global__ void __launch_bounds__(kFinThreads, 2) infonce_finalize_kernel(
-    int B, int C, int splits, float inv_tau, float grad_scale /* loss_scale / B */, float loss_scale, bool bf16_mode,
-    bool want_grad, const float* __restrict__ q_hat, const float* __restrict__ k_hat, const float* __restrict__ inv_norm,
-    const float* __restrict__ pos2, const float* __restrict__ pm, const float* __restrict__ pl,
-    const float* __restrict__ pav, const int* __restrict__ pai, const TP* __restrict__ po,
-    float* __restrict__ row_loss, unsigned int* __restrict__ counter, float* __restrict__ loss,
-    float* __restrict__ loss_per_row, float* __restrict__ lse_out, float* __restrict__ pos_out,
-    long long* __restrict__ argmax_out, float* __restrict__ dq, float* __restrict__ dk, const float* __restrict__ pdist,
-    const float* __restrict__ qn2, float inv_K, const InfoNceDiag diag) {
-  // counter[1]: raised by the two-pass tcgen05 S kernel when a fixed split reference could not hold the
-  // row maximum; nothing computed from those partials is meaningful, so every output becomes NaN.
-  extern __shared__ float fin_smem[];
-  float* sw = fin_smem;                       // [splits] merge weights
-  float* part = fin_smem + ((splits + 3) & ~3);  // [kFinGroups-1][C] partial column sums of groups 1..
-  __shared__ float red[8];
-  __shared__ float dred[kFinThreads / 32][5];
-  __shared__ float s_stats[4];   // 0: scale applied to O  1: p_pos - 1  2: sum over the queue of |q^ - queue_j|
-  __shared__ bool s_last;
-  const int row = blockIdx.x;
-  const int tid = threadIdx.x;
-  const int grp = tid >> 8, ct = tid & 255;   // split group, column thread
-  pdl_wait();                                 // launched early (PDL): the partials must be complete
-
-  // The partial stream does not depend on the merge weights until the multiply: put the first
-  // batch of loads (column ct, splits grp, grp+G, ...) in flight before waiting for the statistics.
-  constexpr int kPre = 8;
-  float pre[kPre];
-  // bf16 partials (tcgen05 kernels; C % 8 == 0): 16-byte loads, 8 columns per thread, C/8 threads per pass over a row and
-  // kFinThreads / (C/8) split groups, so that a thread needs only ~splits/groups loads (5 at cfg2) and all of them are in
-  // flight before the statistics barrier.  (The scalar path below issued 37 two-byte loads per thread in 5 dependent rounds.)
-  constexpr bool kVec = (sizeof(TP) == 2);
-  constexpr int kPreV = 6;
-  uint4 prev[kVec ? kPreV : 1];
-  const int vpr = C >> 3;                           // threads per row pass
-  const int vgroups = kVec ? kFinThreads / vpr : 1;  // split groups
-  const int vg = tid / vpr, vc = tid - vg * vpr;
-  const bool vactive = kVec && want_grad && vg < vgroups;
-  if (kVec) {
-    const uint4* prow4 = reinterpret_cast<const uint4*>(po + (size_t)row * C) + vc;
-    const size_t sstride4 = (size_t)B * C / 8;
-#pragma unroll
-    for (int u = 0; u < kPreV; ++u) {
-      const int s = vg + u * vgroups;
-      prev[u] = (vactive && s < splits) ? __ldcs(prow4 + (size_t)s * sstride4) : make_uint4(0u, 0u, 0u, 0u);
-    }
-  } else {
-    const TP* pcol = po + (size_t)row * C + ct;
-    const size_t sstride = (size_t)B * C;
-#pragma unroll
-    for (int u = 0; u < kPre; ++u) {
-      const int s = grp + u * kFinGroups;
-      pre[u] = (want_grad && ct < C && s < splits) ? ld_partial(pcol + (size_t)s * sstride) : 0.f;
-    }
-  }
-
-  // row data needed after the merge: in flight now
-  const bool own0 = want_grad && grp == 0 && ct < C;
-  float qh_pre = 0.f, kh_pre = 0.f;
-  if (own0) {
-    qh_pre = q_hat[(size_t)row * C + ct];
-    kh_pre = k_hat[(size_t)row * C + ct];
-  }
-
-  if (tid < 32) {
-    // merge the split statistics (one warp; a row's statistics are contiguous => coalesced loads)
-    const float* rm = pm + (size_t)row * splits;
-    const float* rl = pl + (size_t)row * splits;
-    const float* rav = pav + (size_t)row * splits;
-    const int* rai = pai + (size_t)row * splits;
-    float mmax = -INFINITY;
-    for (int s = tid; s < splits; s += 32) mmax = fmaxf(mmax, __ldcg(rm + s));
-    mmax = warp_max(mmax);
-    float lsum = 0.f;
-    float bv = -INFINITY;
-    int bi = 0x7fffffff;
-    if (diag.out) {   // the split sums of the L2 distances: plain sum, in fixed lane order
-      float dsum = 0.f;
-      for (int s = tid; s < splits; s += 32) dsum += __ldcg(pdist + (size_t)row * splits + s);
-      dsum = warp_sum(dsum);
-      if (tid == 0) s_stats[2] = dsum;
-    }
-    for (int s = tid; s < splits; s += 32) {
-      const float ms = __ldcg(rm + s), ls = __ldcg(rl + s), v = __ldcg(rav + s);
-      const int i = __ldcg(rai + s);
-      const float w = (ms == -INFINITY) ? 0.f : exp2f(ms - mmax);
-      sw[s] = w;
-      lsum = fmaf(ls, w, lsum);
-      if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
-    }
-    lsum = warp_sum(lsum);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-    }
-    if (tid == 0) {
-      const float p2 = pos2[row];
-      const float M = fmaxf(mmax, p2);
-      const float wneg = exp2f(mmax - M), wpos = exp2f(p2 - M);
-      const float L = fmaf(lsum, wneg, wpos);
-      const float lse = (M + log2f(L)) * kLn2;
-      const float pos = p2 * kLn2;
-      // lse - pos cancels catastrophically when the positive dominates (p_pos -> 1); take the
-      // difference before the log instead: positive is the max -> log1p of the remaining mass.
-      const float poison = (__ldcg(counter + 1) != 0u) ? __int_as_float(0x7fc00000) : 0.f;
-      const float lrow = ((p2 >= mmax) ? log1pf(lsum * wneg) : fmaf(M - p2, kLn2, logf(L))) + poison;
-      row_loss[row] = lrow;
-      if (loss_per_row) loss_per_row[row] = lrow;
-      if (lse_out) lse_out[row] = lse;
-      if (pos_out) pos_out[row] = pos;
-      if (argmax_out) argmax_out[row] = (p2 >= bv) ? 0ll : (long long)bi + 1;
-      s_stats[0] = wneg / L + poison;
-      s_stats[1] = -(lsum * wneg) / L + poison;  // p_pos - 1 without the cancellation of wpos/L - 1
-    }
-  }
-  __syncthreads();
-
-  if (want_grad) {
-    // Column sums of the partials: group g streams splits g, g+G, ... with 4 independent loads in
-    // flight per owned column; groups are then added in group order (deterministic).
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const size_t sstride = (size_t)B * C;
-    const TP* prow = po + (size_t)row * C;
-    if (kVec) {
-      // 8 columns per thread, weighted sum over this group's splits, then one row of partial sums per group in shared memory
-      float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (vactive) {
-        const uint4* prow4 = reinterpret_cast<const uint4*>(prow) + vc;
-        const size_t sstride4 = sstride / 8;
-        auto fma8 = [&](const uint4& u, float w) {
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = __bfloat1622float2(h[j]);
-            a8[2 * j] = fmaf(f.x, w, a8[2 * j]);
-            a8[2 * j + 1] = fmaf(f.y, w, a8[2 * j + 1]);
-          }
-        };
-#pragma unroll
-        for (int u = 0; u < kPreV; ++u) {
-          const int sp = vg + u * vgroups;
-          if (sp < splits) fma8(prev[u], sw[sp]);
-        }
-        for (int sp = vg + kPreV * vgroups; sp < splits; sp += vgroups) fma8(__ldcs(prow4 + (size_t)sp * sstride4), sw[sp]);
-        float4* dst = reinterpret_cast<float4*>(part + (size_t)vg * C + vc * 8);
-        dst[0] = make_float4(a8[0], a8[1], a8[2], a8[3]);
-        dst[1] = make_float4(a8[4], a8[5], a8[6], a8[7]);
-      }
-    } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c = ct + 256 * i;
-      if (c < C) {
-        const TP* pcol = prow + c;
-        int s = grp;
-        if (i == 0) {  // the prefetched batch
-#pragma unroll
-          for (int u = 0; u < kPre; ++u) {
-            const int sp = grp + u * kFinGroups;
-            if (sp < splits) acc[0] = fmaf(pre[u], sw[sp], acc[0]);
-          }
-          s = grp + kPre * kFinGroups;
-        }
-        for (; s + 3 * kFinGroups < splits; s += 4 * kFinGroups) {
-          float v[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = ld_partial(pcol + (size_t)(s + u * kFinGroups) * sstride);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) acc[i] = fmaf(v[u], sw[s + u * kFinGroups], acc[i]);
-        }
-        for (; s < splits; s += kFinGroups) acc[i] = fmaf(ld_partial(pcol + (size_t)s * sstride), sw[s], acc[i]);
-        if (grp > 0) part[(size_t)(grp - 1) * C + c] = acc[i];
-      }
-    }
-    }
-    __syncthreads();
-    if (grp == 0) {
-      const float o_scale = s_stats[0], pm1 = s_stats[1];
-      const float gs = grad_scale * inv_tau;
-      float dqh[4], qh[4];
-      float dot = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = ct + 256 * i;
-        dqh[i] = 0.f;
-        qh[i] = 0.f;
-        if (c < C) {
-          float a = acc[i];
-          if (kVec) {
-            a = 0.f;
-            for (int g = 0; g < vgroups; ++g) a += part[(size_t)g * C + c];     // fixed order: deterministic
-          } else {
-#pragma unroll
-            for (int g = 1; g < kFinGroups; ++g) a += part[(size_t)(g - 1) * C + c];
-          }
-          const float kh = round_if(i == 0 ? kh_pre : k_hat[(size_t)row * C + c], bf16_mode);
-          qh[i] = (i == 0) ? qh_pre : q_hat[(size_t)row * C + c];
-          dqh[i] = gs * fmaf(a, o_scale, pm1 * kh);
-          dot = fmaf(qh[i], dqh[i], dot);
-          if (dk) dk[(size_t)row * C + c] = gs * pm1 * round_if(qh[i], bf16_mode);
-        }
-      }
-      dot = warp_sum(dot);
-      if ((ct & 31) == 0) red[ct >> 5] = dot;
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 warps of group 0 only
-      dot = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) dot += red[w];
-      const float inv = inv_norm[row];
-      if (dq) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c = ct + 256 * i;
-          if (c < C) dq[(size_t)row * C + c] = (dqh[i] - qh[i] * dot) * inv;
-        }
-      }
-    }
-  }
-
-  // ---- diagnostics of this row (objectives.py:337-349): five dot products over C, then closed forms
-  if (diag.out) {
-    float a[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // q.k, |q-k|^2, |k|^2, q.sum_vec, q.sum_unit
-    for (int c = tid; c < C; c += kFinThreads) {
-      const float qh = q_hat[(size_t)row * C + c], kh = k_hat[(size_t)row * C + c];
-      const float df = qh - kh;
-      a[0] = fmaf(qh, kh, a[0]);
-      a[1] = fmaf(df, df, a[1]);
-      a[2] = fmaf(kh, kh, a[2]);
-      a[3] = fmaf(qh, diag.sum_vec[c], a[3]);
-      a[4] = fmaf(qh, diag.sum_unit[c], a[4]);
-    }
-#pragma unroll
-    for (int i = 0; i < 5; ++i) a[i] = warp_sum(a[i]);
-    if ((tid & 31) == 0) {
-#pragma unroll
-      for (int i = 0; i < 5; ++i) dred[tid >> 5][i] = a[i];
-    }
-    __syncthreads();
-    if (tid == 0) {
-      float t[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int w = 0; w < kFinThreads / 32; ++w)
-#pragma unroll
-        for (int i = 0; i < 5; ++i) t[i] += dred[w][i];
-      const float qn = sqrtf(qn2[row]), kn = sqrtf(t[2]);
-      float* o = diag.rows + (size_t)row * kDiagValues;
-      o[0] = sqrtf(t[1]);                                                       // |q^ - k^|
-      o[1] = t[0] / (fmaxf(qn, diag.cos_eps) * fmaxf(kn, diag.cos_eps));        // cosine(q^, k^)
-      o[2] = t[0];                                                              // q^ . k^
-      o[3] = s_stats[2] * inv_K;                                                // mean_j |q^ - queue_j|
-      o[4] = t[4] * inv_K / fmaxf(qn, diag.cos_eps);                            // mean_j cosine(q^, queue_j)
-      o[5] = t[3] * inv_K;                                                      // mean_j q^ . queue_j
-    }
-  }
-
-  // deterministic loss (and diagnostics) reduction by the last row-CTA
-  if (loss || diag.out) {
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(counter, 1u) == (unsigned)B - 1u);
-    __syncthreads();
-    if (s_last && tid < 256) {
-      __threadfence();
-      const int n_red = diag.out ? 1 + kDiagValues : 1;
-      for (int which = loss ? 0 : 1; which < n_red; ++which) {
-        float acc = 0.f;
-        for (int r = tid; r < B; r += 256)
-          acc += (which == 0) ? __ldcg(row_loss + r) : __ldcg(diag.rows + (size_t)r * kDiagValues + (which - 1));
-        // fixed-shape tree: warp shuffle then 8 partials in order
-        acc = warp_sum(acc);
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        if ((tid & 31) == 0) red[tid >> 5] = acc;
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        if (tid == 0) {
-          float t = 0.f;
-          for (int w = 0; w < 8; ++w) t += red[w];
-          if (which == 0) *loss = t * (loss_scale / (float)B);
-          else diag.out[which - 1] = t / (float)B;
-        }
-      }
-    }
-  }
+static PrepArgs make_prep_args(const void* q, const void* k, int B, int C, float scale2, bool nk, bool bf16_mode, char* ws,
+                               const InfoNcePlan& p, float* k_hat_out, bool want_bf16) {
+  PrepArgs a;
+  a.q = q;
+  a.k = k;
+  a.B = B;
+  a.C = C;
+  a.scale2 = scale2;
+  a.normalize_k = nk;
+  a.bf16_mode = bf16_mode;
+  a.q_hat = (float*)(ws + p.off_qhat);
+  a.k_hat = (float*)(ws + p.off_khat);
+  a.k_hat_out = k_hat_out;
+  a.inv_norm = (float*)(ws + p.off_inv);
+  a.pos2 = (float*)(ws + p.off_pos2);
+  a.qn2 = (float*)(ws + p.off_qn2);
+  a.q_hat_bf16 = want_bf16 ? (__nv_bfloat16*)(ws + p.off_qhat_bf16) : nullptr;
+  a.b_pad = p.b_pad;
+  a.split = p.split;
+  return a;
 }
 
 template <typename TQ, typename TKK>
-static int launch_prep(const void* q, const void* k, int B, int C, float scale2, bool nk, bool bf16_mode, char* ws,
-                       const InfoNcePlan& p, float* k_hat_out, bool want_bf16, cudaStream_t s) {
-  const int rows = want_bf16 ? p.b_pad : B;
-  infonce_prep_kernel<TQ, TKK><<<rows, 128, 0, s>>>(
-      (const TQ*)q, (const TKK*)k, B, C, scale2, nk, bf16_mode, (float*)(ws + p.off_qhat), (float*)(ws + p.off_khat),
-      k_hat_out, (float*)(ws + p.off_inv), (float*)(ws + p.off_pos2), (float*)(ws + p.off_qn2),
-      want_bf16 ? (__nv_bfloat16*)(ws + p.off_qhat_bf16) : nullptr, p.b_pad, p.split, (unsigned int*)(ws + p.off_counter));
+static int launch_prep(const PrepArgs& a, char* ws, const InfoNcePlan& p, cudaStream_t s) {
+  const int rows = a.q_hat_bf16 ? p.b_pad : a.B;
+  infonce_prep_kernel<TQ, TKK><<<rows, 128, 0, s>>>(a, (unsigned int*)(ws + p.off_counter));
   RMCL_LAUNCH_OK("infonce_prep_kernel");
   return RMCL_OK;
 }
@@ -504,6 +174,15 @@ extern "C" int rmcl_profile_infonce_ms(float* out3) {
   do {                                                           \
     if (g_prof_on) RMCL_CUDA_OK(cudaEventRecord(g_prof_ev[i], s)); \
   } while (0)
+
+// RMCL_B200_INFONCE_FUSED=0 keeps the three-launch chain (prep -> tcgen05 partial -> finalize) for A/B measurements
+static bool infonce_fused_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("RMCL_B200_INFONCE_FUSED");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 
 static bool tc_alignment_ok(const void* queue, int64_t ldq) {
   return (reinterpret_cast<uintptr_t>(queue) & 15u) == 0 && (ldq % 8 == 0);
@@ -540,6 +219,9 @@ extern "C" int rmcl_infonce_describe(int B, int C, int64_t K, rmcl_dtype queue_d
   } else if (p.two_pass) {
     names = "infonce_prep_kernel,infonce_s_kernel,infonce_finalize_kernel";
     n = 3;
+  } else if (infonce_fused_enabled() && p.splits * p.row_blocks <= sm_count()) {
+    names = "infonce_fused_kernel";
+    n = 1;
   } else {
     names = "infonce_prep_kernel,infonce_tc_kernel,infonce_finalize_kernel";
     n = 3;
@@ -576,24 +258,69 @@ static int infonce_impl(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_d
   const bool tc = (p.path == RMCL_INFONCE_TCGEN05);
   using bf16 = __nv_bfloat16;
   const bool partial_only = (flags & RMCL_INFONCE_DEBUG_PARTIAL_ONLY) != 0;   // measurement aid, see the header
-  RMCL_PROF_MARK(0);
-  if (partial_only)
-    rc = RMCL_OK;
-  else if (q_dtype == RMCL_F32 && k_dtype == RMCL_F32)
-    rc = launch_prep<float, float>(q, k, B, C, scale2, nk, bf16_mode, ws, p, k_hat_out, tc, s);
-  else if (q_dtype == RMCL_F32)
-    rc = launch_prep<float, bf16>(q, k, B, C, scale2, nk, bf16_mode, ws, p, k_hat_out, tc, s);
-  else if (k_dtype == RMCL_F32)
-    rc = launch_prep<bf16, float>(q, k, B, C, scale2, nk, bf16_mode, ws, p, k_hat_out, tc, s);
-  else
-    rc = launch_prep<bf16, bf16>(q, k, B, C, scale2, nk, bf16_mode, ws, p, k_hat_out, tc, s);
-  if (rc != RMCL_OK) return rc;
-  RMCL_PROF_MARK(1);
-
+  const PrepArgs pa = make_prep_args(q, k, B, C, scale2, nk, bf16_mode, ws, p, k_hat_out, tc);
   diag.rows = diag.out ? (float*)(ws + p.off_diagrows) : nullptr;
   InfoNcePartials parts{(float*)(ws + p.off_m), (float*)(ws + p.off_l), (float*)(ws + p.off_av), (int*)(ws + p.off_ai),
                         (float*)(ws + p.off_o), diag.out ? diag.colnorm2 : nullptr, (const float*)(ws + p.off_qn2),
                         (float*)(ws + p.off_pdist)};
+  FinArgs fa;
+  fa.B = B;
+  fa.C = C;
+  fa.splits = p.splits;
+  fa.inv_tau = 1.f / tau;
+  fa.grad_scale = loss_scale / (float)B;
+  fa.loss_scale = loss_scale;
+  fa.bf16_mode = bf16_mode;
+  fa.want_grad = want_grad;
+  fa.q_hat = pa.q_hat;
+  fa.k_hat = pa.k_hat;
+  fa.inv_norm = pa.inv_norm;
+  fa.pos2 = pa.pos2;
+  fa.pm = parts.m;
+  fa.pl = parts.l;
+  fa.pav = parts.av;
+  fa.pai = parts.ai;
+  fa.po = parts.o;
+  fa.row_loss = (float*)(ws + p.off_rowloss);
+  fa.counter = (unsigned int*)(ws + p.off_counter);
+  fa.loss = loss;
+  fa.loss_per_row = loss_per_row;
+  fa.lse_out = lse;
+  fa.pos_out = pos;
+  fa.argmax_out = reinterpret_cast<long long*>(argmax);
+  fa.dq = dq;
+  fa.dk = dk;
+  fa.pdist = parts.dist;
+  fa.qn2 = parts.qn2;
+  fa.inv_K = 1.f / (float)K;
+  fa.diag = diag;
+
+  // ---- single launch: prep rows, the tcgen05 flash pass and the finalize rows as three phases of ONE cooperative kernel
+  //      (grid-wide barriers between them) whenever the whole grid is co-resident
+  RMCL_PROF_MARK(0);
+  if (tc && !p.two_pass && !partial_only && infonce_fused_enabled() && p.splits * p.row_blocks <= sm_count()) {
+    RMCL_PROF_MARK(1);
+    rc = infonce_tc_fused_launch(pa, q_dtype == RMCL_BF16, k_dtype == RMCL_BF16, fa, queue, B, C, K, ldq, scale2, p, parts,
+                                 argmax != nullptr, want_grad ? 1 : 0, s);
+    if (rc != RMCL_OK) return rc;
+    RMCL_PROF_MARK(2);
+    RMCL_PROF_MARK(3);
+    if (g_prof_on) g_prof_valid = true;
+    return RMCL_OK;
+  }
+  if (partial_only)
+    rc = RMCL_OK;
+  else if (q_dtype == RMCL_F32 && k_dtype == RMCL_F32)
+    rc = launch_prep<float, float>(pa, ws, p, s);
+  else if (q_dtype == RMCL_F32)
+    rc = launch_prep<float, bf16>(pa, ws, p, s);
+  else if (k_dtype == RMCL_F32)
+    rc = launch_prep<bf16, float>(pa, ws, p, s);
+  else
+    rc = launch_prep<bf16, bf16>(pa, ws, p, s);
+  if (rc != RMCL_OK) return rc;
+  RMCL_PROF_MARK(1);
+
   if (tc && p.two_pass)
     rc = infonce_tc2_launch((const bf16*)(ws + p.off_qhat_bf16), queue, B, C, K, ldq, scale2, p, parts,
                             (bf16*)(ws + p.off_ptilde), p.k_pad, (unsigned int*)(ws + p.off_counter) + 1, argmax != nullptr,
@@ -607,25 +334,12 @@ static int infonce_impl(const void* q, rmcl_dtype q_dtype, const void* k, rmcl_d
   RMCL_PROF_MARK(2);
   if (partial_only) return RMCL_OK;
 
-  // merge weights + per-group partial rows: (groups-1) rows of the scalar path, kFinThreads/(C/8) rows of the 16-byte path
   const bool bf16_partials = tc && !p.split;   // the split-operand path keeps its partials in fp32
-  const size_t fin_rows = bf16_partials ? (size_t)(kFinThreads / (C / 8)) : (size_t)(kFinGroups - 1);
-  const size_t fin_smem = ((size_t)((p.splits + 3) & ~3) + fin_rows * C) * sizeof(float);
-  if (bf16_partials) {
-    RMCL_CUDA_OK(launch_pdl(infonce_finalize_kernel<__nv_bfloat16>, dim3(B), dim3(kFinThreads), fin_smem, s,
-        B, C, p.splits, 1.f / tau, loss_scale / (float)B, loss_scale, bf16_mode, want_grad, (const float*)(ws + p.off_qhat),
-        (const float*)(ws + p.off_khat), (const float*)(ws + p.off_inv), (const float*)(ws + p.off_pos2), parts.m, parts.l,
-        parts.av, parts.ai, reinterpret_cast<const __nv_bfloat16*>(parts.o), (float*)(ws + p.off_rowloss),
-        (unsigned int*)(ws + p.off_counter), loss, loss_per_row, lse, pos, reinterpret_cast<long long*>(argmax), dq, dk,
-        (const float*)parts.dist, parts.qn2, 1.f / (float)K, diag));
-  } else {
-    RMCL_CUDA_OK(launch_pdl(infonce_finalize_kernel<float>, dim3(B), dim3(kFinThreads), fin_smem, s,
-        B, C, p.splits, 1.f / tau, loss_scale / (float)B, loss_scale, bf16_mode, want_grad, (const float*)(ws + p.off_qhat),
-        (const float*)(ws + p.off_khat), (const float*)(ws + p.off_inv), (const float*)(ws + p.off_pos2), parts.m, parts.l,
-        parts.av, parts.ai, (const float*)parts.o, (float*)(ws + p.off_rowloss), (unsigned int*)(ws + p.off_counter), loss,
-        loss_per_row, lse, pos, reinterpret_cast<long long*>(argmax), dq, dk, (const float*)parts.dist, parts.qn2,
-        1.f / (float)K, diag));
-  }
+  const size_t fin_smem = finalize_smem_bytes(C, p.splits, bf16_partials, kFinThreads);
+  if (bf16_partials)
+    RMCL_CUDA_OK(launch_pdl(infonce_finalize_kernel<__nv_bfloat16>, dim3(B), dim3(kFinThreads), fin_smem, s, fa));
+  else
+    RMCL_CUDA_OK(launch_pdl(infonce_finalize_kernel<float>, dim3(B), dim3(kFinThreads), fin_smem, s, fa));
   RMCL_PROF_MARK(3);
   if (g_prof_on) g_prof_valid = true;
   return RMCL_OK;

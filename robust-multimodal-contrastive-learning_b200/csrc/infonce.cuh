@@ -78,6 +78,12 @@ int infonce_simt_launch(const float* q_hat, const void* queue, int queue_dtype, 
 int infonce_tc_launch(const __nv_bfloat16* q_hat_bf16, const void* queue, int B, int C, long long K, long long ldq,
                       float scale2, const InfoNcePlan& plan, InfoNcePartials out, int want_argmax, int want_o,
                       cudaStream_t s);
+struct PrepArgs;
+struct FinArgs;
+// single launch: prep rows -> flash pass -> finalize rows in one cooperative kernel (grid <= SM count)
+int infonce_tc_fused_launch(const PrepArgs& prep, bool q_bf16, bool k_bf16, const FinArgs& fin, const void* queue, int B, int C,
+                            long long K, long long ldq, float scale2, const InfoNcePlan& plan, InfoNcePartials out,
+                            int want_argmax, int want_o, cudaStream_t s);
 int infonce_tc_tile_cols(int C);
 bool infonce_tc2_supports(int C);
 int infonce_tc2_launch(const __nv_bfloat16* q_hat_bf16, const void* queue, int B, int C, long long K, long long ldq,

@@ -24,7 +24,17 @@
 // maximum grows by more than 2^40 (everything is floating point, so a stale reference costs no
 // precision until it threatens overflow), which keeps the correction off the critical path while
 // the final (m, l, O) triple stays exact up to fp32 rounding.
+//
+// FUSED instantiations are the whole InfoNCE call in ONE launch (cooperative: every CTA is resident, grid <= SM count):
+//   phase A  the CTAs share out the B rows of the prep stage (normalise q and k, positive logit, bf16 Q^ copies) while
+//            their TMA warps already fill the queue ring;  grid barrier
+//   phase B  the flash pass above (Q^ into tensor memory, tile loop, split partials)            ;  grid barrier
+//   phase C  the CTAs share out the B rows of the finalize stage (merge the splits, loss, dq, dk), the last row's team
+//            reduces the loss.
+// Against the three-launch chain (prep -> partial -> finalize under programmatic dependent launch) this removes two
+// launch latencies and the drain/fill between the kernels; the row code is the same (infonce_rows.cuh).
 #include "infonce.cuh"
+#include "infonce_rows.cuh"
 #include "tc_ptx.cuh"
 
 namespace rmcl {
@@ -67,6 +77,7 @@ struct TcShared {
   float xav[kTcRows];
   int xai[kTcRows];
   float xd[kTcRows];           // diagnostics: the odd-tile warp's distance sum
+  float red4[4];               // FUSED: scratch of the prep rows
 };
 
 
@@ -102,13 +113,13 @@ __device__ __forceinline__ void tl_stamp(long long* tl, int idx) {
 }
 
 // ----------------------------------------------------------------------------------- kernel
-template <int C, int TN, bool DIAG, bool WANT_O>
+template <int C, int TN, bool DIAG, bool WANT_O, bool FUSED>
 __global__ void __launch_bounds__(kTcThreads, 1)
     infonce_tc_kernel(const __grid_constant__ CUtensorMap tmap_queue, const __nv_bfloat16* __restrict__ q_hat, int B,
                       long long K, float scale2, long long cols_per_split, int want_argmax, float* __restrict__ pm,
                       float* __restrict__ pl, float* __restrict__ pav, int* __restrict__ pai, __nv_bfloat16* __restrict__ po,
                       long long* __restrict__ timeline, const float* __restrict__ n2, const float* __restrict__ qn2,
-                      float* __restrict__ pdist) {
+                      float* __restrict__ pdist, const FusedArgs fz) {
   constexpr bool want_o = WANT_O;   // compile-time: the with-gradient instantiation is the tuned kernel, untouched
   // want_o == false (no gradient requested: the clean-query argmax call, the greedy attack's candidate losses): the statistics
   // pass only — no P tile, no O GEMM, no partial write-out; ring stages are released by the S GEMM's own commit.
@@ -140,8 +151,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const int n_tiles = (int)((k_end - k_begin + TN - 1) / TN);
   long long* tl = (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) ? timeline : nullptr;   // lane 0 of every warp of CTA (0,0)
   if (tid == 0) tl_stamp(tl, 0);
-#if RMCL_TC_TIMELINE
   const int cta_linear = blockIdx.y * gridDim.x + blockIdx.x;
+  const int n_ctas = gridDim.x * gridDim.y;
+#if RMCL_TC_TIMELINE
   if (timeline != nullptr && tid == 0 && cta_linear < kTimelineCtas) timeline[kTimelineHead + 2 * cta_linear] = global_ns();
 #endif
 
@@ -187,6 +199,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const uint32_t dec_mine = 1 + quad * 2 + par;         // "decision of one of my tiles is published"
     const uint32_t dec_other = 1 + quad * 2 + (par ^ 1);
 
+    if (FUSED && warp < 4) {
+      // ---- phase A: this CTA's share of the prep rows (threads 0..127), padding rows of the bf16 operand included
+      if (cta_linear == 0 && tid == 0) {
+        fz.fin.counter[0] = 0u;   // rows finalized
+        fz.fin.counter[1] = 0u;   // overflow flag (two-pass kernels only; kept clean)
+      }
+      for (int row = cta_linear; row < fz.prep.b_pad; row += n_ctas) prep_row_rt(fz.prep, fz.q_bf16, fz.k_bf16, row, sh.red4);
+    }
+
     // m_mine: the reference maximum this warp's row sum l_run is expressed in
     float m_mine = -INFINITY, l_run = 0.f, av_raw = -INFINITY;
     int ai = 0;
@@ -210,7 +231,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         // Coalesced global loads (8 lanes cover one 128-byte row segment), all issued before the first
         // use, transposed through this warp's 4 KB of the (still unused) P buffers with the same
         // 16-byte XOR swizzle that keeps the segment writes and the row-per-lane reads conflict free.
-        pdl_wait();   // launched early (PDL): q_hat is written by the prep kernel that may still be running
+        if (FUSED) grid_barrier(fz.bar_words, (unsigned)n_ctas, 15, kSoftmaxWarps * 32);   // every CTA's prep rows are written
+        else pdl_wait();   // launched early (PDL): q_hat is written by the prep kernel that may still be running
         if (tid == 0) tl_stamp(tl, 2);
         {
           constexpr int kChunks = C / 64;                     // 64-column chunks of a row
@@ -225,7 +247,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             if (ch < kChunks) {
     #pragma unroll
               for (int j = 0; j < 8; ++j)
-                v[t][j] = __ldg(reinterpret_cast<const uint4*>(qw + (size_t)(4 * j + (lane >> 3)) * C + ch * 64) + (lane & 7));
+                v[t][j] = FUSED ? __ldcg(reinterpret_cast<const uint4*>(qw + (size_t)(4 * j + (lane >> 3)) * C + ch * 64) + (lane & 7))
+                                : __ldg(reinterpret_cast<const uint4*>(qw + (size_t)(4 * j + (lane >> 3)) * C + ch * 64) + (lane & 7));
             }
           }
     #pragma unroll
@@ -256,7 +279,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
         m_mine = -INFINITY; l_run = 0.f; av_raw = -INFINITY; ai = 0;   // discard the dry pass
         dsum = 0.f;
-        if (DIAG) qn2_r = (row0 + r < B) ? qn2[row0 + r] : 0.f;   // after pdl_wait: written by the prep kernel
+        if (DIAG) qn2_r = (row0 + r < B) ? __ldcg(qn2 + row0 + r) : 0.f;   // after the wait: written by the prep stage
       }
       if (live && i >= n_tiles) break;
       const int b = par;                                  // == i & 1
@@ -441,8 +464,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       bulk_store_row(po + ((size_t)split * B + row0 + r) * C + par * HC, stage, HC * 2);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (FUSED) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the WRITES must have landed: other CTAs read them in phase C
+      else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
+    if (FUSED) __threadfence();   // statistics and partials of this CTA are visible before it arrives at the grid barrier
     if (tid == 0) tl_stamp(tl, 6);
     tc_fence_before();
   } else if (warp == kTmaWarp) {
@@ -549,14 +574,36 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
+  if (FUSED) {
+    // ---- phase C: every split partial of every row block is in global memory once all CTAs have passed this barrier
+    grid_barrier(fz.bar_words, (unsigned)n_ctas, 0, kTcThreads);
+    if (warp < kSoftmaxWarps)
+      for (int row = cta_linear; row < fz.fin.B; row += n_ctas)
+        finalize_row<__nv_bfloat16, kSoftmaxWarps * 32>(fz.fin, row, reinterpret_cast<float*>(ring));
+  }
 }
 
 // ------------------------------------------------------------------------------ host side
 thread_local long long* g_tc_timeline = nullptr;
 
-template <int C, int TN, bool DIAG, bool WANT_O>
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_cooperative(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;     // all CTAs resident at once: the grid barriers cannot deadlock
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+template <int C, int TN, bool DIAG, bool WANT_O, bool FUSED>
 int launch_tc(const __nv_bfloat16* q_hat, const void* queue, int B, long long K, long long ldq, float scale2,
-              const InfoNcePlan& p, InfoNcePartials out, int want_argmax, cudaStream_t s) {
+              const InfoNcePlan& p, InfoNcePartials out, int want_argmax, const FusedArgs& fz, cudaStream_t s) {
   alignas(64) CUtensorMap tmap;
   const int trc = make_tmap_bf16(&tmap, queue, (uint64_t)C, (uint64_t)K, (uint64_t)ldq, (uint32_t)C);
   if (trc != RMCL_OK) return trc;
@@ -564,13 +611,43 @@ int launch_tc(const __nv_bfloat16* q_hat, const void* queue, int B, long long K,
   constexpr int kPBytes = (TN / 64) * 16384;
   constexpr int kStages = ((kSmemBudget - 2 * kPBytes) / kStageBytes) < 8 ? ((kSmemBudget - 2 * kPBytes) / kStageBytes) : 8;
   const size_t smem = (size_t)kStages * kStageBytes + 2 * kPBytes + 1024;
-  auto kern = infonce_tc_kernel<C, TN, DIAG, WANT_O>;
+  auto kern = infonce_tc_kernel<C, TN, DIAG, WANT_O, FUSED>;
   RMCL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(p.splits, p.row_blocks);
-  RMCL_CUDA_OK(launch_pdl(kern, grid, dim3(kTcThreads), smem, s, tmap, q_hat, B, K, scale2, p.cols_per_split, want_argmax,
-                          out.m, out.l, out.av, out.ai, reinterpret_cast<__nv_bfloat16*>(out.o), g_tc_timeline, out.n2,
-                          out.qn2, out.dist));
+  if (FUSED)
+    RMCL_CUDA_OK(launch_cooperative(kern, grid, dim3(kTcThreads), smem, s, tmap, q_hat, B, K, scale2, p.cols_per_split, want_argmax,
+                                    out.m, out.l, out.av, out.ai, reinterpret_cast<__nv_bfloat16*>(out.o), g_tc_timeline, out.n2,
+                                    out.qn2, out.dist, fz));
+  else
+    RMCL_CUDA_OK(launch_pdl(kern, grid, dim3(kTcThreads), smem, s, tmap, q_hat, B, K, scale2, p.cols_per_split, want_argmax,
+                            out.m, out.l, out.av, out.ai, reinterpret_cast<__nv_bfloat16*>(out.o), g_tc_timeline, out.n2,
+                            out.qn2, out.dist, fz));
   return RMCL_OK;
+}
+
+template <bool FUSED>
+int dispatch_tc(const __nv_bfloat16* q_hat, const void* queue, int B, int C, long long K, long long ldq, float scale2,
+                const InfoNcePlan& p, InfoNcePartials out, int want_argmax, int want_o, const FusedArgs& fz, cudaStream_t s) {
+  if (p.row_blocks > 65535) {
+    set_error("InfoNCE: too many rows (%d)", B);
+    return RMCL_E_UNSUPPORTED_DIM;
+  }
+  const bool dg = out.n2 != nullptr;
+#define RMCL_TC_CASE(CC, TT)                                                                                              \
+  case CC:                                                                                                                \
+    if (want_o)                                                                                                           \
+      return dg ? launch_tc<CC, TT, true, true, FUSED>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, fz, s)       \
+                : launch_tc<CC, TT, false, true, FUSED>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, fz, s);     \
+    return dg ? launch_tc<CC, TT, true, false, FUSED>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, fz, s)        \
+              : launch_tc<CC, TT, false, false, FUSED>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, fz, s);
+  switch (C) {
+    RMCL_TC_CASE(256, 64)
+    RMCL_TC_CASE(128, 128)
+    RMCL_TC_CASE(64, 128)
+  }
+#undef RMCL_TC_CASE
+  set_error("tcgen05 InfoNCE supports C in {64,128,256} (got %d)", C);
+  return RMCL_E_UNSUPPORTED_DIM;
 }
 
 }  // namespace
@@ -598,26 +675,20 @@ namespace rmcl {
 
 int infonce_tc_launch(const __nv_bfloat16* q_hat, const void* queue, int B, int C, long long K, long long ldq,
                       float scale2, const InfoNcePlan& p, InfoNcePartials out, int want_argmax, int want_o, cudaStream_t s) {
-  if (p.row_blocks > 65535) {
-    set_error("InfoNCE: too many rows (%d)", B);
-    return RMCL_E_UNSUPPORTED_DIM;
-  }
-  const bool dg = out.n2 != nullptr;
-#define RMCL_TC_CASE(CC, TT)                                                                                              \
-  case CC:                                                                                                                \
-    if (want_o)                                                                                                           \
-      return dg ? launch_tc<CC, TT, true, true>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s)                  \
-                : launch_tc<CC, TT, false, true>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s);                \
-    return dg ? launch_tc<CC, TT, true, false>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s)                   \
-              : launch_tc<CC, TT, false, false>(q_hat, queue, B, K, ldq, scale2, p, out, want_argmax, s);
-  switch (C) {
-    RMCL_TC_CASE(256, 64)
-    RMCL_TC_CASE(128, 128)
-    RMCL_TC_CASE(64, 128)
-  }
-#undef RMCL_TC_CASE
-  set_error("tcgen05 InfoNCE supports C in {64,128,256} (got %d)", C);
-  return RMCL_E_UNSUPPORTED_DIM;
+  FusedArgs none = {};
+  return dispatch_tc<false>(q_hat, queue, B, C, K, ldq, scale2, p, out, want_argmax, want_o, none, s);
+}
+
+int infonce_tc_fused_launch(const PrepArgs& prep, bool q_bf16, bool k_bf16, const FinArgs& fin, const void* queue, int B, int C,
+                            long long K, long long ldq, float scale2, const InfoNcePlan& p, InfoNcePartials out, int want_argmax,
+                            int want_o, cudaStream_t s) {
+  FusedArgs fz;
+  fz.prep = prep;
+  fz.fin = fin;
+  fz.bar_words = fin.counter + 2;     // [0], [1] of the counter block belong to the finalize stage
+  fz.q_bf16 = q_bf16;
+  fz.k_bf16 = k_bf16;
+  return dispatch_tc<true>(prep.q_hat_bf16, queue, B, C, K, ldq, scale2, p, out, want_argmax, want_o, fz, s);
 }
 
 }  // namespace rmcl

@@ -124,8 +124,10 @@ struct PgdItem {
 // all P1 items followed by all P2 items, so that at any moment the resident CTAs are a mix of DRAM-streaming norm items
 // and L2-served update items rather than all in the same phase.  The dependency argument is unchanged: a P2 item of batch
 // r-1 only waits for P1 items of batch r-1, which belong to the previous round, i.e. have smaller tickets.
+// Same-box sweep (tools/pgd_sweep.py, profiles/r2_pgd_sweep.txt): interleaved 142.8 / 171.0 us against 145.3 / 179.1 us for the
+// pixel ref_linf / l2 cases.
 #ifndef RMCL_PGD_INTERLEAVE
-#define RMCL_PGD_INTERLEAVE 0
+#define RMCL_PGD_INTERLEAVE 1
 #endif
 __device__ __forceinline__ PgdItem pgd_decode(const PgdPlan& p, long long t) {
   const int first_phase = (p.phases == 1) ? 1 : 0;  // sign mode has no norm phase
@@ -168,6 +170,21 @@ __device__ __forceinline__ PgdItem pgd_decode(const PgdPlan& p, long long t) {
     return PgdItem{first_phase + k, s0[k] + (int)(idx / p.chunks), (int)(idx % p.chunks)};
   }
   return PgdItem{-1, 0, 0};
+}
+
+// Bytes in flight: a CTA's register-held loads (4 x 16 B per thread) come to ~80 KB per SM at 5 CTAs, against the ~45 KB per SM
+// that keep 6.5 TB/s busy at ~1 us of DRAM latency — no slack for the update phase, where half of those loads are L2 hits.
+// RMCL_PGD_L2_PREFETCH: the CTA already holds its NEXT ticket while it works on the current item (see the work loop), so
+// thread 0 asks the L2 for the next item's DRAM-resident operand(s) with one cp.async.bulk.prefetch.L2 per operand: no
+// registers, no shared memory, and the item's own loads then hit in L2.
+// Measured (profiles/r2_pgd_sweep.txt): it helps the single-phase sign mode (36.5 -> 34.5 us, 97-98 % of the HBM roof) and
+// HURTS the two-phase modes (pixel ref_linf 146 -> 182 us: the prefetched lines compete with the evict_last residents the
+// second phase depends on), so it is compiled in only for the mode it helps.
+#ifndef RMCL_PGD_L2_PREFETCH
+#define RMCL_PGD_L2_PREFETCH 1
+#endif
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes, uint64_t policy) {
+  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(p), "r"(bytes), "l"(policy) : "memory");
 }
 
 __device__ __forceinline__ void spin_until(const unsigned int* counter, unsigned int target) {
@@ -260,7 +277,25 @@ __global__ void __launch_bounds__(kPgdThreads, (sizeof(TD) + sizeof(TG) == 8) ? 
       break;
     }
 #if RMCL_PGD_PREFETCH
-    if (threadIdx.x == 0) t_next = (long long)atomicAdd(p.ticket, 1u);
+    if (threadIdx.x == 0) {
+      t_next = (long long)atomicAdd(p.ticket, 1u);
+#if RMCL_PGD_L2_PREFETCH
+      if (vec && p.phases == 1 && t_next < p.total_items) {     // single-phase (sign) mode only, see above
+        const PgdItem nx = pgd_decode(p, t_next);
+        const long long ne0 = (long long)nx.chunk * p.chunk_elems;
+        long long nn = p.N - ne0;
+        if (nn > p.chunk_elems) nn = p.chunk_elems;
+        const TG* ng = grad + (long long)nx.sample * p.N + ne0;
+        const TD* nd = delta + (long long)nx.sample * p.N + ne0;
+        if (nx.phase == 0) {            // norm item: g comes from DRAM (and delta too under the L2 projection); both are re-read later
+          l2_prefetch_bulk(ng, (unsigned)(nn * sizeof(TG)), keep);
+          if (l2proj) l2_prefetch_bulk(nd, (unsigned)(nn * sizeof(TD)), keep);
+        } else if (!l2proj) {           // update item: g is L2-resident already, delta comes from DRAM, used once
+          l2_prefetch_bulk(nd, (unsigned)(nn * sizeof(TD)), stream);
+        }
+      }
+#endif
+    }
 #endif
     const long long e0 = (long long)it.chunk * p.chunk_elems;
     long long n = p.N - e0;

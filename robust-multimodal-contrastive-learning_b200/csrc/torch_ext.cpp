@@ -114,7 +114,7 @@ std::vector<Tensor> infonce_fwd_bwd(const Tensor& q_in, const Tensor& k_in, cons
   const rmcl_dtype qdt = hilo ? RMCL_BF16_HILO : dt_of(queue, "queue");
   const size_t need = rmcl_infonce_workspace_bytes((int)B, (int)C, K, qdt, (int)path);
   TORCH_CHECK(need > 0, "rmcl_infonce_workspace_bytes failed: ", rmcl_last_error());
-  auto ws = workspace(WsKey{0, q.get_device(), B, C, K, (int64_t)qdt * 8 + path, (int64_t)(uintptr_t)stream_of(q)}, need, q, false);
+  auto ws = workspace(WsKey{0, q.get_device(), B, C, K, (int64_t)qdt * 8 + path, (int64_t)(uintptr_t)stream_of(q)}, need, q, true);
   auto f32 = q.options().dtype(at::kFloat);
   Tensor none;
   Tensor loss = (want & W_LOSS) ? at::empty({}, f32) : none;

@@ -132,7 +132,7 @@ def _workspace(B, Cdim, K, qdt, path, device):
         nbytes = _lib.lib().rmcl_infonce_workspace_bytes(B, Cdim, K, qdt, path)
         if nbytes == 0:
             check(-3, "rmcl_infonce_workspace_bytes")
-        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+        ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=device)     # zero-filled once: grid-barrier words (header)
         _ws_cache[key] = ws
     off = (-ws.data_ptr()) % 256
     return ws, off

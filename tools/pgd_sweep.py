@@ -1,23 +1,39 @@
-"""Same-box sweep of PGD-kernel build variants (csrc/pgd.cu macros): builds each variant next to the product library
-(cross-compiled beforehand with `python tools/pgd_sweep.py --build`, so that the .so files travel with the snapshot) and
-times tools/pgd_time.py against each through the ctypes binding."""
+"""Same-box sweep of PGD-kernel build variants (csrc/pgd.cu macros).  `--build` (run here, nvcc cross-compiles) links one
+library per variant next to the product library — only pgd.cu is recompiled per variant — so that the .so files travel with
+the snapshot; without arguments (on the GPU box) tools/pgd_time.py is timed against each through the ctypes binding."""
 import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "robust-multimodal-contrastive-learning_b200")
 VARIANTS = {
     "base": [],
     "ilv": ["-DRMCL_PGD_INTERLEAVE=1"],
-    "ilv_c64": ["-DRMCL_PGD_INTERLEAVE=1", "-DRMCL_PGD_CHUNK_KB=64"],
-    "ilv_c16": ["-DRMCL_PGD_INTERLEAVE=1", "-DRMCL_PGD_CHUNK_KB=16"],
-    "ilv_b80": ["-DRMCL_PGD_INTERLEAVE=1", "-DRMCL_PGD_BATCH_MB=80", "-DRMCL_PGD_BATCH_MB_L2=80"],
-    "ilv_b12": ["-DRMCL_PGD_INTERLEAVE=1", "-DRMCL_PGD_BATCH_MB=12", "-DRMCL_PGD_BATCH_MB_L2=24"],
-    "ilv_cta6": ["-DRMCL_PGD_INTERLEAVE=1", "-DRMCL_PGD_MIN_CTAS=6"],
-    "ilv_cta4": ["-DRMCL_PGD_INTERLEAVE=1", "-DRMCL_PGD_MIN_CTAS=4"],
+    "pf": ["-DRMCL_PGD_L2_PREFETCH=1"],
+    "pf_ilv": ["-DRMCL_PGD_L2_PREFETCH=1", "-DRMCL_PGD_INTERLEAVE=1"],
+    "pf_ilv_cta6": ["-DRMCL_PGD_L2_PREFETCH=1", "-DRMCL_PGD_INTERLEAVE=1", "-DRMCL_PGD_MIN_CTAS=6"],
+    "pf_ilv_cta4": ["-DRMCL_PGD_L2_PREFETCH=1", "-DRMCL_PGD_INTERLEAVE=1", "-DRMCL_PGD_MIN_CTAS=4"],
+    "pf_ilv_b16": ["-DRMCL_PGD_L2_PREFETCH=1", "-DRMCL_PGD_INTERLEAVE=1", "-DRMCL_PGD_BATCH_MB=16", "-DRMCL_PGD_BATCH_MB_L2=32"],
+    "pf_ilv_b32": ["-DRMCL_PGD_L2_PREFETCH=1", "-DRMCL_PGD_INTERLEAVE=1", "-DRMCL_PGD_BATCH_MB=32", "-DRMCL_PGD_BATCH_MB_L2=48"],
 }
 if "--build" in sys.argv:
-    sys.path.insert(0, os.path.join(ROOT, "robust-multimodal-contrastive-learning_b200", "csrc"))
+    sys.path.insert(0, os.path.join(PKG, "csrc"))
     import build
+    objdir = os.path.join(ROOT, "build", "sweep")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in build.FLAGS if f not in ("-shared", "-cudart", "static")]
+    objs = []
+    for src in build.SOURCES:
+        if src == "pgd.cu":
+            continue
+        o = os.path.join(objdir, src.replace(".cu", ".o"))
+        if not os.path.isfile(o) or os.path.getmtime(o) < max(os.path.getmtime(os.path.join(build.HERE, f)) for f in os.listdir(build.HERE)):
+            subprocess.run(["nvcc"] + flags + ["-c", src, "-o", o], cwd=build.HERE, check=True)
+        objs.append(o)
     for name, defs in VARIANTS.items():
-        print(build.build(force=True, out=os.path.join(os.path.dirname(build.OUT), f"librmcl_b200_pgd_{name}.so"), defines=defs))
+        o = os.path.join(objdir, f"pgd_{name}.o")
+        subprocess.run(["nvcc"] + flags + defs + ["-c", "pgd.cu", "-o", o], cwd=build.HERE, check=True)
+        out = os.path.join(PKG, f"librmcl_b200_pgd_{name}.so")
+        subprocess.run(["nvcc", "-shared", "-cudart", "static", "-o", out, o] + objs, check=True)
+        print(out, flush=True)
 else:
     for name in VARIANTS:
         env = dict(os.environ, RMCL_B200_LIB=f"librmcl_b200_pgd_{name}.so", RMCL_B200_FFI="ctypes")
