@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(128) infonce_prep_kernel(const PrepArgs a, uns
     counter[0] = 0u;
     counter[1] = 0u;   // overflow flag of the two-pass tcgen05 variant
   }
-  prep_row<TQ, TKK>(a, row, red);
+  prep_row<TQ, TKK>(a, row, red, threadIdx.x, kBarPrep);
 }
 
 // -------------------------------------------------------------------------------- finalize
@@ -110,8 +110,9 @@ constexpr int kFinThreads = 512;              // two CTAs per SM, so B=256 rows 
 template <typename TP>
 __global__ void __launch_bounds__(kFinThreads, 2) infonce_finalize_kernel(const FinArgs a) {
   extern __shared__ float fin_smem[];
+  __shared__ FinShared fs;
   pdl_wait();                                 // launched early (PDL): the partials must be complete
-  finalize_row<TP, kFinThreads>(a, blockIdx.x, fin_smem);
+  finalize_row<TP, kFinThreads>(a, blockIdx.x, fin_smem, &fs, threadIdx.x, kBarFin);
 }
 
 static PrepArgs make_prep_args(const void* q, const void* k, int B, int C, float scale2, bool nk, bool bf16_mode, char* ws,
@@ -175,11 +176,18 @@ extern "C" int rmcl_profile_infonce_ms(float* out3) {
     if (g_prof_on) RMCL_CUDA_OK(cudaEventRecord(g_prof_ev[i], s)); \
   } while (0)
 
-// RMCL_B200_INFONCE_FUSED=0 keeps the three-launch chain (prep -> tcgen05 partial -> finalize) for A/B measurements
+// RMCL_B200_INFONCE_FUSED=1 selects the single-launch cooperative kernel (prep rows | flash pass | finalize rows with grid
+// barriers in between) for bf16 queues with C <= 256.  It is correct (the whole GPU suite passes with it) but measured
+// SLOWER than the three-launch chain under programmatic dependent launch — 39.5 vs 34.5 us per call at cfg2 by CUDA-graph
+// replay, 30.8 vs 25.6 us at the cfg4 shape (profiles/r2_ab_fused.txt) — so the chain stays the default.  The in-kernel
+// timeline says why (profiles/r2_timeline_fused.txt): a CTA owns one or two rows of each row phase and runs that code once,
+// with a cold instruction cache (~7 cycles per instruction the first time through) and every dependent L2 round trip on the
+// critical path (prep rows + grid barrier 9 us, finalize rows 10-12 us), while the separate kernels spread the same rows over
+// 256 CTAs whose latencies overlap and whose launches are hidden by PDL.
 static bool infonce_fused_enabled() {
   static const bool on = [] {
     const char* e = getenv("RMCL_B200_INFONCE_FUSED");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   return on;
 }

@@ -28,11 +28,11 @@ __device__ __forceinline__ float round_if(float x, bool to_bf16) {
   return to_bf16 ? __bfloat162float(__float2bfloat16_rn(x)) : x;
 }
 
-__device__ __forceinline__ float team_sum_128(float v, float* red) {
+__device__ __forceinline__ float team_sum_128(float v, float* red, int tid, uint32_t bar) {
   v = warp_sum(v);
-  team_sync(kBarPrep, 128);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  team_sync(kBarPrep, 128);
+  team_sync(bar, 128);
+  if ((tid & 31) == 0) red[tid >> 5] = v;
+  team_sync(bar, 128);
   return red[0] + red[1] + red[2] + red[3];
 }
 
@@ -54,32 +54,33 @@ struct PrepArgs {
   bool split;
 };
 
-// Threads 0..127 of the CTA; `red` = 4 floats of shared memory.  row may be a padding row (>= B): zero operand rows.
+// A team of 128 threads (tid = 0..127 inside the team, synchronising on named barrier `bar`); `red` = the team's 4 floats of
+// shared memory.  row may be a padding row (>= B): zero operand rows.
 template <typename TQ, typename TKK>
-__device__ __forceinline__ void prep_row(const PrepArgs& a, int row, float* red) {
+__device__ __forceinline__ void prep_row(const PrepArgs& a, int row, float* red, int tid, uint32_t bar) {
   const int C = a.C;
   const int qw = a.split ? 2 * C : C;
   const size_t rep_stride = (size_t)a.b_pad * qw;   // kQhatReplicas copies of the bf16 operand (infonce.cuh)
   if (row >= a.B) {  // padding rows of the bf16 operand (the tcgen05 kernels read whole 128-row blocks)
     if (a.q_hat_bf16)
-      for (int c = threadIdx.x; c < qw; c += 128)
+      for (int c = tid; c < qw; c += 128)
         for (int rep = 0; rep < kQhatReplicas; ++rep) a.q_hat_bf16[rep * rep_stride + (size_t)row * qw + c] = __float2bfloat16_rn(0.f);
     return;
   }
   const TQ* qr = reinterpret_cast<const TQ*>(a.q) + (size_t)row * C;
   const TKK* kr = reinterpret_cast<const TKK*>(a.k) + (size_t)row * C;
   float sq = 0.f, sk = 0.f;
-  for (int c = threadIdx.x; c < C; c += 128) {
+  for (int c = tid; c < C; c += 128) {
     const float x = to_f32(qr[c]), y = to_f32(kr[c]);
     sq = fmaf(x, x, sq);
     sk = fmaf(y, y, sk);
   }
-  sq = team_sum_128(sq, red);
-  sk = team_sum_128(sk, red);
+  sq = team_sum_128(sq, red, tid, bar);
+  sk = team_sum_128(sk, red, tid, bar);
   const float qn = fmaxf(sqrtf(sq), 1e-12f);
   const float kn = a.normalize_k ? fmaxf(sqrtf(sk), 1e-12f) : 1.f;
   float dot = 0.f, qq = 0.f;
-  for (int c = threadIdx.x; c < C; c += 128) {
+  for (int c = tid; c < C; c += 128) {
     const float qh = __fdiv_rn(to_f32(qr[c]), qn);
     qq = fmaf(qh, qh, qq);
     const float kh = a.normalize_k ? __fdiv_rn(to_f32(kr[c]), kn) : to_f32(kr[c]);
@@ -97,21 +98,82 @@ __device__ __forceinline__ void prep_row(const PrepArgs& a, int row, float* red)
     }
     dot = fmaf(round_if(qh, a.bf16_mode), round_if(kh, a.bf16_mode), dot);
   }
-  dot = team_sum_128(dot, red);
-  qq = team_sum_128(qq, red);
-  if (threadIdx.x == 0) {
+  dot = team_sum_128(dot, red, tid, bar);
+  qq = team_sum_128(qq, red, tid, bar);
+  if (tid == 0) {
     a.inv_norm[row] = __fdiv_rn(1.f, qn);
     a.pos2[row] = dot * a.scale2;
     a.qn2[row] = qq;
   }
 }
 
+// The same row by ONE WARP (the single-launch kernel: a CTA owns one or two rows, latency is what counts): a lane keeps its
+// C/32 elements of q and k in flight together, the reductions are shuffles, nothing synchronises beyond the warp.
+template <typename TQ, typename TKK>
+__device__ __forceinline__ void prep_row_warp(const PrepArgs& a, int row, int lane) {
+  const int C = a.C;
+  const int qw = a.split ? 2 * C : C;
+  const size_t rep_stride = (size_t)a.b_pad * qw;
+  if (row >= a.B) {
+    if (a.q_hat_bf16)
+      for (int c = lane; c < qw; c += 32)
+        for (int rep = 0; rep < kQhatReplicas; ++rep) a.q_hat_bf16[rep * rep_stride + (size_t)row * qw + c] = __float2bfloat16_rn(0.f);
+    return;
+  }
+  const TQ* qr = reinterpret_cast<const TQ*>(a.q) + (size_t)row * C;
+  const TKK* kr = reinterpret_cast<const TKK*>(a.k) + (size_t)row * C;
+  float sq = 0.f, sk = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float x = to_f32(qr[c]), y = to_f32(kr[c]);
+    sq = fmaf(x, x, sq);
+    sk = fmaf(y, y, sk);
+  }
+  sq = warp_sum(sq);
+  sk = warp_sum(sk);
+  const float qn = fmaxf(sqrtf(sq), 1e-12f);
+  const float kn = a.normalize_k ? fmaxf(sqrtf(sk), 1e-12f) : 1.f;
+  float dot = 0.f, qq = 0.f;
+  for (int c = lane; c < C; c += 32) {       // second pass: L1 hits
+    const float qh = __fdiv_rn(to_f32(qr[c]), qn);
+    qq = fmaf(qh, qh, qq);
+    const float kh = a.normalize_k ? __fdiv_rn(to_f32(kr[c]), kn) : to_f32(kr[c]);
+    a.q_hat[(size_t)row * C + c] = qh;
+    a.k_hat[(size_t)row * C + c] = kh;
+    if (a.k_hat_out) a.k_hat_out[(size_t)row * C + c] = kh;
+    if (a.q_hat_bf16) {
+      const __nv_bfloat16 qb = __float2bfloat16_rn(qh);
+      const __nv_bfloat16 ql = __float2bfloat16_rn(qh - __bfloat162float(qb));
+#pragma unroll
+      for (int rep = 0; rep < kQhatReplicas; ++rep) {
+        a.q_hat_bf16[rep * rep_stride + (size_t)row * qw + c] = qb;
+        if (a.split) a.q_hat_bf16[rep * rep_stride + (size_t)row * qw + C + c] = ql;
+      }
+    }
+    dot = fmaf(round_if(qh, a.bf16_mode), round_if(kh, a.bf16_mode), dot);
+  }
+  dot = warp_sum(dot);
+  qq = warp_sum(qq);
+  if (lane == 0) {
+    a.inv_norm[row] = __fdiv_rn(1.f, qn);
+    a.pos2[row] = dot * a.scale2;
+    a.qn2[row] = qq;
+  }
+}
+
+__device__ __forceinline__ void prep_row_warp_rt(const PrepArgs& a, bool q_bf16, bool k_bf16, int row, int lane) {
+  if (!q_bf16 && !k_bf16) prep_row_warp<float, float>(a, row, lane);
+  else if (!q_bf16) prep_row_warp<float, __nv_bfloat16>(a, row, lane);
+  else if (!k_bf16) prep_row_warp<__nv_bfloat16, float>(a, row, lane);
+  else prep_row_warp<__nv_bfloat16, __nv_bfloat16>(a, row, lane);
+}
+
 // dtype dispatch for callers that carry the dtypes at run time (the single-launch kernel)
-__device__ __forceinline__ void prep_row_rt(const PrepArgs& a, bool q_bf16, bool k_bf16, int row, float* red) {
-  if (!q_bf16 && !k_bf16) prep_row<float, float>(a, row, red);
-  else if (!q_bf16) prep_row<float, __nv_bfloat16>(a, row, red);
-  else if (!k_bf16) prep_row<__nv_bfloat16, float>(a, row, red);
-  else prep_row<__nv_bfloat16, __nv_bfloat16>(a, row, red);
+__device__ __forceinline__ void prep_row_rt(const PrepArgs& a, bool q_bf16, bool k_bf16, int row, float* red, int tid,
+                                            uint32_t bar) {
+  if (!q_bf16 && !k_bf16) prep_row<float, float>(a, row, red, tid, bar);
+  else if (!q_bf16) prep_row<float, __nv_bfloat16>(a, row, red, tid, bar);
+  else if (!k_bf16) prep_row<__nv_bfloat16, float>(a, row, red, tid, bar);
+  else prep_row<__nv_bfloat16, __nv_bfloat16>(a, row, red, tid, bar);
 }
 
 // -------------------------------------------------------------------------------- finalize
@@ -150,47 +212,59 @@ __device__ __forceinline__ float ld_partial(const __nv_bfloat16* p) {
 
 // shared memory a finalize team needs: merge weights + per-group partial rows
 __host__ __device__ inline size_t finalize_smem_bytes(int C, int splits, bool bf16_partials, int team_threads) {
-  const size_t rows = bf16_partials ? (size_t)(team_threads / (C / 8)) : (size_t)(team_threads / 256 - 1);
+  const int col_threads = team_threads < 256 ? team_threads : 256;
+  const size_t rows = bf16_partials ? (size_t)(team_threads / (C / 8)) : (size_t)(team_threads / col_threads - 1);
   return ((size_t)((splits + 3) & ~3) + rows * C) * sizeof(float);
 }
 
-// Threads 0..NT-1 of the CTA (NT a multiple of 256).  TP: element type of the partial accumulators (fp32 from the SIMT and
-// split-operand kernels, bf16 from the bf16 tcgen05 kernels).  fin_smem: finalize_smem_bytes() of shared memory.
-// Re-entrant: a team may call it for several rows in turn.
+// per-team scratch of finalize_row
+struct FinShared {
+  float red[8];
+  float dred[16][5];
+  float s_stats[4];   // 0: scale applied to O  1: p_pos - 1  2: sum over the queue of |q^ - queue_j|
+  int last;
+};
+
+// A team of NT threads (128, 256 or 512; tid = 0..NT-1 inside the team) synchronising on named barrier `bar`.  TP: element
+// type of the partial accumulators (fp32 from the SIMT and split-operand kernels, bf16 from the bf16 tcgen05 kernels).
+// fin_smem: finalize_smem_bytes() of shared memory, fs: the team's FinShared.  Re-entrant: a team may call it for several
+// rows in turn, several teams of one CTA may run it concurrently on different rows (distinct bar / fin_smem / fs).
 template <typename TP, int NT>
-__device__ __forceinline__ void finalize_row(const FinArgs& a, const int row, float* fin_smem) {
+__device__ __forceinline__ void finalize_row(const FinArgs& a, const int row, float* fin_smem, FinShared* fs, const int tid,
+                                             const uint32_t bar, long long* dbg = nullptr) {
+#define RMCL_FIN_STAMP(i) do { if (dbg != nullptr && tid == 0) dbg[i] = clock64(); } while (0)
   // counter[1]: raised by the two-pass tcgen05 S kernel when a fixed split reference could not hold the
   // row maximum; nothing computed from those partials is meaningful, so every output becomes NaN.
-  constexpr int kGroups = NT / 256;             // split groups of the scalar path
+  constexpr int kColThreads = NT < 256 ? NT : 256;   // "group 0": the threads that own output columns (c = ct + kColThreads*i)
+  constexpr int kColsPer = 1024 / kColThreads;       // C <= 1024
+  constexpr int kGroups = NT / kColThreads;          // split groups of the scalar path
+  const uint32_t bar0 = (NT > 256) ? 1u : bar;       // barrier of group 0 alone (the whole team when NT <= 256)
+  const uint32_t bar_last = (NT > 256) ? 2u : bar;
   const int B = a.B, C = a.C, splits = a.splits;
   const TP* po = reinterpret_cast<const TP*>(a.po);
   float* sw = fin_smem;                          // [splits] merge weights
   float* part = fin_smem + ((splits + 3) & ~3);  // per-group partial column sums
-  __shared__ float red[8];
-  __shared__ float dred[NT / 32][5];
-  __shared__ float s_stats[4];   // 0: scale applied to O  1: p_pos - 1  2: sum over the queue of |q^ - queue_j|
-  __shared__ bool s_last;
-  const int tid = threadIdx.x;
-  const int grp = tid >> 8, ct = tid & 255;   // split group, column thread
-  team_sync(kBarFin, NT);                     // the previous row of this team is completely done with the shared arrays
+  const int grp = tid / kColThreads, ct = tid - grp * kColThreads;   // split group, column thread
+  team_sync(bar, NT);                            // the previous row of this team is completely done with the shared arrays
+  RMCL_FIN_STAMP(0);
 
   // The partial stream does not depend on the merge weights until the multiply: put the first
-  // batch of loads (column ct, splits grp, grp+G, ...) in flight before waiting for the statistics.
+  // batch of loads in flight before waiting for the statistics.
   constexpr int kPre = 8;
   float pre[kPre];
   // bf16 partials (tcgen05 kernels; C % 8 == 0): 16-byte loads, 8 columns per thread, C/8 threads per pass over a row and
-  // NT / (C/8) split groups, so that a thread needs only ~splits/groups loads and all of them are in
-  // flight before the statistics barrier.
+  // NT / (C/8) split groups; a thread's loads are issued in batches of kPreV, the first batch before the statistics barrier
+  // (NT = 512 at cfg2: 5 loads per thread, one batch; a 128-thread team of the single-launch kernel: 19 loads, two batches).
   constexpr bool kVec = (sizeof(TP) == 2);
-  constexpr int kPreV = 6;
+  constexpr int kPreV = NT >= 512 ? 6 : 20;   // every load of a row in flight at once (registers are free in the row phases)
   uint4 prev[kVec ? kPreV : 1];
   const int vpr = C >> 3;                           // threads per row pass
   const int vgroups = kVec ? NT / vpr : 1;          // split groups
   const int vg = tid / vpr, vc = tid - vg * vpr;
   const bool vactive = kVec && a.want_grad && vg < vgroups;
+  const size_t sstride4 = (size_t)B * C / 8;
+  const uint4* prow4 = reinterpret_cast<const uint4*>(po + (size_t)row * C) + vc;
   if (kVec) {
-    const uint4* prow4 = reinterpret_cast<const uint4*>(po + (size_t)row * C) + vc;
-    const size_t sstride4 = (size_t)B * C / 8;
 #pragma unroll
     for (int u = 0; u < kPreV; ++u) {
       const int s = vg + u * vgroups;
@@ -208,20 +282,41 @@ __device__ __forceinline__ void finalize_row(const FinArgs& a, const int row, fl
 
   // row data needed after the merge: in flight now
   const bool own0 = a.want_grad && grp == 0 && ct < C;
-  float qh_pre = 0.f, kh_pre = 0.f;
-  if (own0) {
-    qh_pre = __ldcg(a.q_hat + (size_t)row * C + ct);
-    kh_pre = __ldcg(a.k_hat + (size_t)row * C + ct);
+  float qh_pre[kColsPer], kh_pre[kColsPer], inv_pre = 0.f;
+#pragma unroll
+  for (int i = 0; i < kColsPer; ++i) {
+    const int c = ct + kColThreads * i;
+    const bool ok = a.want_grad && grp == 0 && c < C;
+    qh_pre[i] = ok ? __ldcg(a.q_hat + (size_t)row * C + c) : 0.f;
+    kh_pre[i] = ok ? __ldcg(a.k_hat + (size_t)row * C + c) : 0.f;
   }
+  if (own0) inv_pre = __ldcg(a.inv_norm + row);
 
   if (tid < 32) {
-    // merge the split statistics (one warp; a row's statistics are contiguous => coalesced loads)
+    // merge the split statistics (one warp; a row's statistics are contiguous => coalesced loads, all issued up front:
+    // up to 8 per lane covers 256 splits, the rare longer rows take the second loop)
     const float* rm = a.pm + (size_t)row * splits;
     const float* rl = a.pl + (size_t)row * splits;
     const float* rav = a.pav + (size_t)row * splits;
     const int* rai = a.pai + (size_t)row * splits;
+    const float p2 = __ldcg(a.pos2 + row);
+    const unsigned poison_flag = __ldcg(a.counter + 1);
+    constexpr int kS = 8;
+    float vm[kS], vl[kS], vv[kS];
+    int vi[kS];
+#pragma unroll
+    for (int u = 0; u < kS; ++u) {
+      const int s = tid + 32 * u;
+      const bool ok = s < splits;
+      vm[u] = ok ? __ldcg(rm + s) : -INFINITY;
+      vl[u] = ok ? __ldcg(rl + s) : 0.f;
+      vv[u] = ok ? __ldcg(rav + s) : -INFINITY;
+      vi[u] = ok ? __ldcg(rai + s) : 0x7fffffff;
+    }
     float mmax = -INFINITY;
-    for (int s = tid; s < splits; s += 32) mmax = fmaxf(mmax, __ldcg(rm + s));
+#pragma unroll
+    for (int u = 0; u < kS; ++u) mmax = fmaxf(mmax, vm[u]);
+    for (int s = tid + 32 * kS; s < splits; s += 32) mmax = fmaxf(mmax, __ldcg(rm + s));
     mmax = warp_max(mmax);
     float lsum = 0.f;
     float bv = -INFINITY;
@@ -230,16 +325,18 @@ __device__ __forceinline__ void finalize_row(const FinArgs& a, const int row, fl
       float dsum = 0.f;
       for (int s = tid; s < splits; s += 32) dsum += __ldcg(a.pdist + (size_t)row * splits + s);
       dsum = warp_sum(dsum);
-      if (tid == 0) s_stats[2] = dsum;
+      if (tid == 0) fs->s_stats[2] = dsum;
     }
-    for (int s = tid; s < splits; s += 32) {
-      const float ms = __ldcg(rm + s), ls = __ldcg(rl + s), v = __ldcg(rav + s);
-      const int i = __ldcg(rai + s);
+    auto merge = [&](int s, float ms, float ls, float v, int i) {
       const float w = (ms == -INFINITY) ? 0.f : exp2f(ms - mmax);
       sw[s] = w;
       lsum = fmaf(ls, w, lsum);
       if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
-    }
+    };
+#pragma unroll
+    for (int u = 0; u < kS; ++u)
+      if (tid + 32 * u < splits) merge(tid + 32 * u, vm[u], vl[u], vv[u], vi[u]);
+    for (int s = tid + 32 * kS; s < splits; s += 32) merge(s, __ldcg(rm + s), __ldcg(rl + s), __ldcg(rav + s), __ldcg(rai + s));
     lsum = warp_sum(lsum);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -248,7 +345,6 @@ __device__ __forceinline__ void finalize_row(const FinArgs& a, const int row, fl
       if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
     }
     if (tid == 0) {
-      const float p2 = __ldcg(a.pos2 + row);
       const float M = fmaxf(mmax, p2);
       const float wneg = exp2f(mmax - M), wpos = exp2f(p2 - M);
       const float L = fmaf(lsum, wneg, wpos);
@@ -256,31 +352,32 @@ __device__ __forceinline__ void finalize_row(const FinArgs& a, const int row, fl
       const float pos = p2 * kLn2;
       // lse - pos cancels catastrophically when the positive dominates (p_pos -> 1); take the
       // difference before the log instead: positive is the max -> log1p of the remaining mass.
-      const float poison = (__ldcg(a.counter + 1) != 0u) ? __int_as_float(0x7fc00000) : 0.f;
+      const float poison = (poison_flag != 0u) ? __int_as_float(0x7fc00000) : 0.f;
       const float lrow = ((p2 >= mmax) ? log1pf(lsum * wneg) : fmaf(M - p2, kLn2, logf(L))) + poison;
       a.row_loss[row] = lrow;
       if (a.loss_per_row) a.loss_per_row[row] = lrow;
       if (a.lse_out) a.lse_out[row] = lse;
       if (a.pos_out) a.pos_out[row] = pos;
       if (a.argmax_out) a.argmax_out[row] = (p2 >= bv) ? 0ll : (long long)bi + 1;
-      s_stats[0] = wneg / L + poison;
-      s_stats[1] = -(lsum * wneg) / L + poison;  // p_pos - 1 without the cancellation of wpos/L - 1
+      fs->s_stats[0] = wneg / L + poison;
+      fs->s_stats[1] = -(lsum * wneg) / L + poison;  // p_pos - 1 without the cancellation of wpos/L - 1
     }
+    RMCL_FIN_STAMP(1);
   }
-  team_sync(kBarFin, NT);
+  team_sync(bar, NT);
+  RMCL_FIN_STAMP(2);
 
   if (a.want_grad) {
-    // Column sums of the partials: group g streams splits g, g+G, ... with 4 independent loads in
-    // flight per owned column; groups are then added in group order (deterministic).
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // Column sums of the partials: group g streams splits g, g+G, ...; groups are then added in group order (deterministic).
+    float acc[kColsPer];
+#pragma unroll
+    for (int i = 0; i < kColsPer; ++i) acc[i] = 0.f;
     const size_t sstride = (size_t)B * C;
     const TP* prow = po + (size_t)row * C;
     if (kVec) {
       // 8 columns per thread, weighted sum over this group's splits, then one row of partial sums per group in shared memory
       float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (vactive) {
-        const uint4* prow4 = reinterpret_cast<const uint4*>(prow) + vc;
-        const size_t sstride4 = sstride / 8;
         auto fma8 = [&](const uint4& u, float w) {
           const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -290,20 +387,28 @@ __device__ __forceinline__ void finalize_row(const FinArgs& a, const int row, fl
             a8[2 * j + 1] = fmaf(f.y, w, a8[2 * j + 1]);
           }
         };
+        for (int base = 0; base < splits; base += kPreV * vgroups) {
+          if (base > 0) {   // next batch: all of its loads in flight before the first use
 #pragma unroll
-        for (int u = 0; u < kPreV; ++u) {
-          const int sp = vg + u * vgroups;
-          if (sp < splits) fma8(prev[u], sw[sp]);
+            for (int u = 0; u < kPreV; ++u) {
+              const int sp = base + vg + u * vgroups;
+              prev[u] = (sp < splits) ? __ldcs(prow4 + (size_t)sp * sstride4) : make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kPreV; ++u) {
+            const int sp = base + vg + u * vgroups;
+            if (sp < splits) fma8(prev[u], sw[sp]);
+          }
         }
-        for (int sp = vg + kPreV * vgroups; sp < splits; sp += vgroups) fma8(__ldcs(prow4 + (size_t)sp * sstride4), sw[sp]);
         float4* dst = reinterpret_cast<float4*>(part + (size_t)vg * C + vc * 8);
         dst[0] = make_float4(a8[0], a8[1], a8[2], a8[3]);
         dst[1] = make_float4(a8[4], a8[5], a8[6], a8[7]);
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = ct + 256 * i;
+      for (int i = 0; i < kColsPer; ++i) {
+        const int c = ct + kColThreads * i;
         if (c < C) {
           const TP* pcol = prow + c;
           int s = grp;
@@ -327,15 +432,17 @@ __device__ __forceinline__ void finalize_row(const FinArgs& a, const int row, fl
         }
       }
     }
-    team_sync(kBarFin, NT);
+    RMCL_FIN_STAMP(3);
+    team_sync(bar, NT);
+    RMCL_FIN_STAMP(4);
     if (grp == 0) {
-      const float o_scale = s_stats[0], pm1 = s_stats[1];
+      const float o_scale = fs->s_stats[0], pm1 = fs->s_stats[1];
       const float gs = a.grad_scale * a.inv_tau;
-      float dqh[4], qh[4];
+      float dqh[kColsPer], qh[kColsPer];
       float dot = 0.f;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = ct + 256 * i;
+      for (int i = 0; i < kColsPer; ++i) {
+        const int c = ct + kColThreads * i;
         dqh[i] = 0.f;
         qh[i] = 0.f;
         if (c < C) {
@@ -347,30 +454,31 @@ __device__ __forceinline__ void finalize_row(const FinArgs& a, const int row, fl
 #pragma unroll
             for (int g = 1; g < kGroups; ++g) s += part[(size_t)(g - 1) * C + c];
           }
-          const float kh = round_if(i == 0 ? kh_pre : __ldcg(a.k_hat + (size_t)row * C + c), a.bf16_mode);
-          qh[i] = (i == 0) ? qh_pre : __ldcg(a.q_hat + (size_t)row * C + c);
+          const float kh = round_if(kh_pre[i], a.bf16_mode);
+          qh[i] = qh_pre[i];
           dqh[i] = gs * fmaf(s, o_scale, pm1 * kh);
           dot = fmaf(qh[i], dqh[i], dot);
           if (a.dk) a.dk[(size_t)row * C + c] = gs * pm1 * round_if(qh[i], a.bf16_mode);
         }
       }
       dot = warp_sum(dot);
-      if ((ct & 31) == 0) red[ct >> 5] = dot;
-      asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 warps of group 0 only
+      if ((ct & 31) == 0) fs->red[ct >> 5] = dot;
+      team_sync(bar0, kColThreads);   // the warps of group 0 only
       dot = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) dot += red[w];
-      const float inv = __ldcg(a.inv_norm + row);
+      for (int w = 0; w < kColThreads / 32; ++w) dot += fs->red[w];
+      const float inv = own0 ? inv_pre : __ldcg(a.inv_norm + row);
       if (a.dq) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c = ct + 256 * i;
+        for (int i = 0; i < kColsPer; ++i) {
+          const int c = ct + kColThreads * i;
           if (c < C) a.dq[(size_t)row * C + c] = (dqh[i] - qh[i] * dot) * inv;
         }
       }
     }
   }
 
+  RMCL_FIN_STAMP(5);
   // ---- diagnostics of this row (objectives.py:337-349): five dot products over C, then closed forms
   if (a.diag.out) {
     float d5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // q.k, |q-k|^2, |k|^2, q.sum_vec, q.sum_unit
@@ -387,20 +495,20 @@ __device__ __forceinline__ void finalize_row(const FinArgs& a, const int row, fl
     for (int i = 0; i < 5; ++i) d5[i] = warp_sum(d5[i]);
     if ((tid & 31) == 0) {
 #pragma unroll
-      for (int i = 0; i < 5; ++i) dred[tid >> 5][i] = d5[i];
+      for (int i = 0; i < 5; ++i) fs->dred[tid >> 5][i] = d5[i];
     }
-    team_sync(kBarFin, NT);
+    team_sync(bar, NT);
     if (tid == 0) {
       float t[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
       for (int w = 0; w < NT / 32; ++w)
 #pragma unroll
-        for (int i = 0; i < 5; ++i) t[i] += dred[w][i];
+        for (int i = 0; i < 5; ++i) t[i] += fs->dred[w][i];
       const float qn = sqrtf(__ldcg(a.qn2 + row)), kn = sqrtf(t[2]);
       float* o = a.diag.rows + (size_t)row * kDiagValues;
       o[0] = sqrtf(t[1]);                                                           // |q^ - k^|
       o[1] = t[0] / (fmaxf(qn, a.diag.cos_eps) * fmaxf(kn, a.diag.cos_eps));        // cosine(q^, k^)
       o[2] = t[0];                                                                  // q^ . k^
-      o[3] = s_stats[2] * a.inv_K;                                                  // mean_j |q^ - queue_j|
+      o[3] = fs->s_stats[2] * a.inv_K;                                              // mean_j |q^ - queue_j|
       o[4] = t[4] * a.inv_K / fmaxf(qn, a.diag.cos_eps);                            // mean_j cosine(q^, queue_j)
       o[5] = t[3] * a.inv_K;                                                        // mean_j q^ . queue_j
     }
@@ -408,31 +516,36 @@ __device__ __forceinline__ void finalize_row(const FinArgs& a, const int row, fl
 
   // deterministic loss (and diagnostics) reduction by whoever finalizes the last row
   if (a.loss || a.diag.out) {
-    __threadfence();
-    team_sync(kBarFin, NT);
-    if (tid == 0) s_last = (atomicAdd(a.counter, 1u) == (unsigned)B - 1u);
-    team_sync(kBarFin, NT);
-    if (s_last && tid < 256) {
+    // thread 0 wrote this row's loss and diagnostics itself: its own fence + the counter is all the ordering the final
+    // reduction needs (dq / dk rows of the other threads are not read by it)
+    if (tid == 0) {
+      __threadfence();
+      fs->last = (atomicAdd(a.counter, 1u) == (unsigned)B - 1u) ? 1 : 0;
+    }
+    team_sync(bar, NT);
+    if (fs->last && tid < kColThreads) {
       __threadfence();
       const int n_red = a.diag.out ? 1 + kDiagValues : 1;
       for (int which = a.loss ? 0 : 1; which < n_red; ++which) {
         float acc = 0.f;
-        for (int r = tid; r < B; r += 256)
+        for (int r = tid; r < B; r += kColThreads)
           acc += (which == 0) ? __ldcg(a.row_loss + r) : __ldcg(a.diag.rows + (size_t)r * kDiagValues + (which - 1));
-        // fixed-shape tree: warp shuffle then 8 partials in order
+        // fixed-shape tree: warp shuffle then the warps' partials in order
         acc = warp_sum(acc);
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        if ((tid & 31) == 0) red[tid >> 5] = acc;
-        asm volatile("bar.sync 2, 256;" ::: "memory");
+        team_sync(bar_last, kColThreads);
+        if ((tid & 31) == 0) fs->red[tid >> 5] = acc;
+        team_sync(bar_last, kColThreads);
         if (tid == 0) {
           float t = 0.f;
-          for (int w = 0; w < 8; ++w) t += red[w];
+          for (int w = 0; w < kColThreads / 32; ++w) t += fs->red[w];
           if (which == 0) *a.loss = t * (a.loss_scale / (float)B);
           else a.diag.out[which - 1] = t / (float)B;
         }
       }
     }
   }
+  RMCL_FIN_STAMP(6);
+#undef RMCL_FIN_STAMP
 }
 
 // ---- grid-wide barrier of a kernel whose CTAs are all co-resident (cooperative launch).  words[0] = arrival count (zero

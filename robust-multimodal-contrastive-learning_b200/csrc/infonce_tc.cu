@@ -33,6 +33,8 @@
 //            reduces the loss.
 // Against the three-launch chain (prep -> partial -> finalize under programmatic dependent launch) this removes two
 // launch latencies and the drain/fill between the kernels; the row code is the same (infonce_rows.cuh).
+#include <stdlib.h>
+
 #include "infonce.cuh"
 #include "infonce_rows.cuh"
 #include "tc_ptx.cuh"
@@ -77,7 +79,7 @@ struct TcShared {
   float xav[kTcRows];
   int xai[kTcRows];
   float xd[kTcRows];           // diagnostics: the odd-tile warp's distance sum
-  float red4[4];               // FUSED: scratch of the prep rows
+  FinShared fin[2];            // FUSED: scratch of the two finalize teams
 };
 
 
@@ -199,13 +201,16 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const uint32_t dec_mine = 1 + quad * 2 + par;         // "decision of one of my tiles is published"
     const uint32_t dec_other = 1 + quad * 2 + (par ^ 1);
 
-    if (FUSED && warp < 4) {
-      // ---- phase A: this CTA's share of the prep rows (threads 0..127), padding rows of the bf16 operand included
+    if (FUSED) {
+      // ---- phase A: this CTA's share of the prep rows, one WARP per row (a CTA owns at most a handful of rows: what counts is
+      //      the latency of one row, not throughput); padding rows of the bf16 operand included
       if (cta_linear == 0 && tid == 0) {
         fz.fin.counter[0] = 0u;   // rows finalized
         fz.fin.counter[1] = 0u;   // overflow flag (two-pass kernels only; kept clean)
       }
-      for (int row = cta_linear; row < fz.prep.b_pad; row += n_ctas) prep_row_rt(fz.prep, fz.q_bf16, fz.k_bf16, row, sh.red4);
+      for (int row = cta_linear + warp * n_ctas; row < fz.prep.b_pad; row += kSoftmaxWarps * n_ctas)
+        prep_row_warp_rt(fz.prep, fz.q_bf16, fz.k_bf16, row, lane);
+      if (warp == 0) tl_stamp(tl, 320);   // this CTA's prep rows are written (warp 0's row)
     }
 
     // m_mine: the reference maximum this warp's row sum l_run is expressed in
@@ -577,9 +582,24 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (FUSED) {
     // ---- phase C: every split partial of every row block is in global memory once all CTAs have passed this barrier
     grid_barrier(fz.bar_words, (unsigned)n_ctas, 0, kTcThreads);
-    if (warp < kSoftmaxWarps)
-      for (int row = cta_linear; row < fz.fin.B; row += n_ctas)
-        finalize_row<__nv_bfloat16, kSoftmaxWarps * 32>(fz.fin, row, reinterpret_cast<float*>(ring));
+    if (tid == 0) tl_stamp(tl, 7);
+    if (warp < kSoftmaxWarps) {
+      // two teams of 128 threads on alternate rows, each with its own 64 KB of the (now idle) TMA ring
+      const int team = warp >> 2;
+      float* fsm = reinterpret_cast<float*>(ring + (size_t)team * 65536);
+      for (int row = cta_linear + team * n_ctas; row < fz.fin.B; row += 2 * n_ctas) {
+#if RMCL_TC_TIMELINE
+        finalize_row<__nv_bfloat16, 128>(fz.fin, row, fsm, &sh.fin[team], tid & 127, kBarFin + team,
+                                         (timeline != nullptr && cta_linear == 0 && team == 0) ? timeline + 312 : nullptr);
+#else
+        finalize_row<__nv_bfloat16, 128>(fz.fin, row, fsm, &sh.fin[team], tid & 127, kBarFin + team);
+#endif
+      }
+    }
+#if RMCL_TC_TIMELINE
+    __syncthreads();
+    if (timeline != nullptr && tid == 0 && cta_linear < kTimelineCtas) timeline[kTimelineHead + 2 * cta_linear + 1] = global_ns();
+#endif
   }
 }
 
@@ -614,7 +634,14 @@ int launch_tc(const __nv_bfloat16* q_hat, const void* queue, int B, long long K,
   auto kern = infonce_tc_kernel<C, TN, DIAG, WANT_O, FUSED>;
   RMCL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(p.splits, p.row_blocks);
-  if (FUSED)
+  // RMCL_B200_INFONCE_COOP=0: plain launch of the same kernel (measurement aid: cost of the cooperative attribute).  The grid
+  // never exceeds the SM count and a CTA takes a whole SM's shared memory, so the CTAs are co-resident either way.
+  static const bool coop = [] { const char* e = getenv("RMCL_B200_INFONCE_COOP"); return !(e && e[0] == '0'); }();
+  if (FUSED && !coop) {
+    kern<<<grid, dim3(kTcThreads), smem, s>>>(tmap, q_hat, B, K, scale2, p.cols_per_split, want_argmax, out.m, out.l, out.av, out.ai,
+                                              reinterpret_cast<__nv_bfloat16*>(out.o), g_tc_timeline, out.n2, out.qn2, out.dist, fz);
+    RMCL_LAUNCH_OK("infonce_fused_kernel");
+  } else if (FUSED)
     RMCL_CUDA_OK(launch_cooperative(kern, grid, dim3(kTcThreads), smem, s, tmap, q_hat, B, K, scale2, p.cols_per_split, want_argmax,
                                     out.m, out.l, out.av, out.ai, reinterpret_cast<__nv_bfloat16*>(out.o), g_tc_timeline, out.n2,
                                     out.qn2, out.dist, fz));

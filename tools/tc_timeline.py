@@ -37,13 +37,17 @@ for rep in range(5):
     st = [tt[HEAD0 + 2 * c] for c in range(148)]
     en = [tt[HEAD0 + 2 * c + 1] for c in range(148)]
     print("profiled rep", rep, ops.profile_infonce_ms(), "kernel span by %globaltimer:", max(en) - min(st), "ns;",
-          " ".join(f"{n}={tt[i] - tt[0]}" for i, n in enumerate(["entry", "setup", "pdl", "q_in_tmem", "o_all_done", "stats", "stored"])))
+          " ".join(f"{n}={tt[i] - tt[0]}" for i, n in enumerate(["entry", "setup", "prep+barrier", "q_in_tmem", "o_all_done", "stats", "stored", "barrier2"])))
 ops.profile_enable(False)
 t = rows[-1]
 t0 = t[0]
-names = ["entry", "setup", "pdl", "q_in_tmem", "o_all_done", "stats", "stored"]
+names = ["entry", "setup", "prep+barrier", "q_in_tmem", "o_all_done", "stats", "stored", "barrier2"]
 for rep, tt in enumerate(rows):
     print("rep", rep, " ".join(f"{n}={tt[i] - tt[0]}" for i, n in enumerate(names)))
+for rep, tt in enumerate(rows):
+    if tt[312]:
+        print("rep", rep, "prep rows written at", tt[320] - tt[0], "| finalize row of team 0:",
+              " ".join(f"{n}={tt[312 + i] - tt[0]}" for i, n in enumerate(["start", "stats", "synced", "partials_summed", "synced2", "dq_written", "done"])))
 HEAD = 8 + 8 * 40
 n_cta = 148 if (B, C, K) == (256, 256, 65536) else 0
 for rep, tt in enumerate(rows):
