@@ -357,9 +357,13 @@ def run_cuda(args):
     # EMA duration is absorbed instead of being paid every step.  (The EMA has no data dependency on the InfoNCE
     # either in this kernels-only step — the link in the full step is the key-encoder forward — but running those two
     # concurrently measured no gain: both want every SM.)
+    # The side stream has HIGH priority and the EMA is released only once the side stream has passed its wait for the
+    # InfoNCE (ev_go): the EMA fills every SM with long-lived CTAs (2048 threads per SM, two waves of ~110 us), so an exchange
+    # kernel that loses the race for the SMs would not start before the EMA's first wave retires — or, behind the EMA's own
+    # second wave, not before its end, which serialises the exchange behind the EMA (measured: 0.333 ms/step at 8 GPUs).
     main_stream = torch.cuda.current_stream()
-    side_stream = torch.cuda.Stream() if world > 1 else None
-    ev_fwd, ev_side = torch.cuda.Event(), torch.cuda.Event()
+    side_stream = torch.cuda.Stream(priority=-1) if world > 1 else None
+    ev_fwd, ev_side, ev_go = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
 
     # N>1 exchange: the fused peer-memory kernel (rmcl_gather_enqueue_p2p: push over NVLink, signal, wait, enqueue — one
     # launch) or, if symmetric memory cannot be set up on this box / --exchange nccl, ncclAllGather + the enqueue kernel
@@ -393,10 +397,12 @@ def run_cuda(args):
         ev_fwd.record(main_stream)
         side_stream.wait_event(ev_fwd)
         with torch.cuda.stream(side_stream):
+            ev_go.record(side_stream)
             if after_fwd is not None:
                 after_fwd(res)          # e2e: the result read-back goes out as soon as the InfoNCE is done
             exchange_and_enqueue(res["k_hat"])
             ev_side.record(side_stream)
+        main_stream.wait_event(ev_go)
         ops.ema_multi_(plan, m)
         main_stream.wait_event(ev_side)  # stream order: ... EMA(n) | join | InfoNCE(n+1): the join sits in front of its consumer
         return res
@@ -753,7 +759,7 @@ def run_cuda(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, **CFG, "arithmetic": "InfoNCE: bf16 queue/q/k operands, fp32 accumulation and statistics; EMA: fp32 (bit-exact with ATen); enqueue: fp32 keys -> bf16 queue", "per_gpu_batch": B, "global_batch": world * B, "infonce_path": path,
                    "parallelism": f"dp{world}", "exchange": exchange_info,
-                   "streams": "single stream" if world == 1 else "key exchange + enqueue on a side stream under the EMA, joined in front of the next InfoNCE", "unit_of_value": "256-sample rank-steps per second, summed over ranks",
+                   "streams": "single stream" if world == 1 else "key exchange + enqueue on a high-priority side stream under the EMA, joined in front of the next InfoNCE", "unit_of_value": "256-sample rank-steps per second, summed over ranks",
                    "l2": "inputs larger than L2: each step streams 1.34 GB of parameters (EMA) between InfoNCE passes; L2 is 126 MB",
                    "timing": f"{n_blocks} blocks of exactly {args.steps} steps, each bracketed by barrier+synchronize, CUDA events, max over ranks; "
                              f"ms_per_step = median block / {args.steps}"},

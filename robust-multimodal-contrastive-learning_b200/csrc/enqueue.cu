@@ -163,10 +163,10 @@ extern "C" int rmcl_queue_split(const void* queue_f32, int C, int64_t K, int64_t
 //   4. enqueue the world*B staged keys into my replica of the queue (+ bf16 shadow) — the transposing scatter of
 //              enqueue_kernel — and advance my pointer.
 // Two slots suffice: a peer can push step n+2 into slot n&1 only after it has seen my signal of step n+1, which I
-// send after my step-n enqueue has finished reading that slot.  All CTAs are co-resident (grid = RMCL_P2P_MAX_CTAS = 16),
+// send after my step-n enqueue has finished reading that slot.  All CTAs are co-resident (grid = RMCL_P2P_MAX_CTAS = 32),
 // so the spin in step 3 cannot starve the pushes it waits for.
 #ifndef RMCL_P2P_MAX_CTAS
-#define RMCL_P2P_MAX_CTAS 16
+#define RMCL_P2P_MAX_CTAS 32
 #endif
 namespace rmcl {
 
@@ -186,11 +186,11 @@ __global__ void __launch_bounds__(256) gather_enqueue_p2p_kernel(float* const* _
                                                                  long long* ptr_dev, int rank, int world, int B, int C,
                                                                  long long K, long long ldq, __nv_bfloat16* __restrict__ shadow,
                                                                  long long lds, int planes) {
-  __shared__ float tile[32][33];
+  __shared__ float wtile[8][32][33];
   __shared__ long long s_ptr;
   __shared__ unsigned int s_epoch;
   unsigned int* ptr_words = reinterpret_cast<unsigned int*>(ptr_dev);
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tx = threadIdx.x & 31;
   const int Bt = world * B;
   unsigned int* my_flags = flag_ptrs[rank];      // [0] arrivals from all ranks, [1] local CTA counter, [2] completed calls
   if (threadIdx.x == 0) {
@@ -240,31 +240,36 @@ __global__ void __launch_bounds__(256) gather_enqueue_p2p_kernel(float* const* _
   }
   __syncthreads();
 
-  // 4. enqueue the staged keys (tiles of 32 keys x 32 channels, persistent loop)
+  // 4. enqueue the staged keys: tiles of 32 keys x 32 channels, one tile per WARP at a time (the grid is small on purpose,
+  //    so the parallelism has to come from inside the CTA: 8 warps x 32 loads in flight each; with one tile per CTA and two
+  //    block-wide barriers per tile the 512 tiles of an 8-rank exchange took 38 us on 16 CTAs)
   const float* staged = stage_ptrs[rank] + slot;
   const long long ptr = s_ptr;
   const int tiles_b = (Bt + 31) / 32, tiles_c = (C + 31) / 32;
-  for (int t = blockIdx.x; t < tiles_b * tiles_c; t += gridDim.x) {
+  const int warp = threadIdx.x >> 5, lane = tx;
+  float (*wt)[33] = wtile[warp];
+  for (int t = blockIdx.x * 8 + warp; t < tiles_b * tiles_c; t += gridDim.x * 8) {
     const int b0 = (t % tiles_b) * 32, c0 = (t / tiles_b) * 32;
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int b = b0 + ty + 8 * i, c = c0 + tx;
-      if (b < Bt && c < C) tile[ty + 8 * i][tx] = __ldcg(staged + (size_t)b * C + c);   // written by peers: bypass L1
+    __syncwarp();
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+      const int b = b0 + i, c = c0 + lane;
+      if (b < Bt && c < C) wt[i][lane] = __ldcg(staged + (size_t)b * C + c);   // written by peers: bypass L1
     }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c = c0 + ty + 8 * i, b = b0 + tx;
+    __syncwarp();
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+      const int c = c0 + i, b = b0 + lane;
       if (b < Bt && c < C) {
         long long col = ptr + b;
         if (col >= K) col -= K;
-        const float v = tile[tx][ty + 8 * i];
+        const float v = wt[lane][i];
         queue[(long long)c * ldq + col] = from_f32<TQ>(v);
         if (shadow) write_shadow(shadow, lds, C, planes, c, col, to_f32(from_f32<TQ>(v)));
       }
     }
   }
+  __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned int ticket = atomicAdd(ptr_words + 1, 1u);
     if (ticket == gridDim.x - 1u) {
@@ -295,7 +300,7 @@ extern "C" int rmcl_gather_enqueue_p2p(void* const* stage_ptrs_dev, void* const*
   // All CTAs must be resident at once (they spin on the flag), and while they wait for the slowest rank they hold their
   // SM's thread slots away from whatever runs beside them — in the training step that is the HBM-bound EMA the exchange is
   // meant to hide under.  The work is tiny (world x 256 KB of pushes, world*B*C*6 bytes of scatter), so a small fixed grid
-  // loses nothing: 16 CTAs move 8 x 256 KB in ~32 sweeps of 16-byte stores.  (Round 1 launched 2 CTAs per SM = 296 spinning
+  // loses nothing: 32 CTAs move 8 x 256 KB in ~16 sweeps of 16-byte stores and scatter 8 tiles each at a time.  (Round 1 launched 2 CTAs per SM = 296 spinning
   // CTAs; 1 -> 8 GPU weak scaling of the cfg2 step was 0.93.)
   long long grid = RMCL_P2P_MAX_CTAS;
   if (grid > 2ll * sms) grid = 2ll * sms;

@@ -69,7 +69,10 @@ __device__ __forceinline__ void prep_row(const PrepArgs& a, int row, float* red,
   }
   const TQ* qr = reinterpret_cast<const TQ*>(a.q) + (size_t)row * C;
   const TKK* kr = reinterpret_cast<const TKK*>(a.k) + (size_t)row * C;
+  // rolled loops on purpose (C/128 iterations): every CTA runs this once with a cold instruction cache, and the IEEE
+  // divisions below inline to ~40 instructions each — unrolled by 4 the kernel was 3400 instructions for a few hundred flops
   float sq = 0.f, sk = 0.f;
+#pragma unroll 1
   for (int c = tid; c < C; c += 128) {
     const float x = to_f32(qr[c]), y = to_f32(kr[c]);
     sq = fmaf(x, x, sq);
@@ -80,6 +83,7 @@ __device__ __forceinline__ void prep_row(const PrepArgs& a, int row, float* red,
   const float qn = fmaxf(sqrtf(sq), 1e-12f);
   const float kn = a.normalize_k ? fmaxf(sqrtf(sk), 1e-12f) : 1.f;
   float dot = 0.f, qq = 0.f;
+#pragma unroll 1
   for (int c = tid; c < C; c += 128) {
     const float qh = __fdiv_rn(to_f32(qr[c]), qn);
     qq = fmaf(qh, qh, qq);
@@ -282,41 +286,24 @@ __device__ __forceinline__ void finalize_row(const FinArgs& a, const int row, fl
 
   // row data needed after the merge: in flight now
   const bool own0 = a.want_grad && grp == 0 && ct < C;
-  float qh_pre[kColsPer], kh_pre[kColsPer], inv_pre = 0.f;
-#pragma unroll
-  for (int i = 0; i < kColsPer; ++i) {
-    const int c = ct + kColThreads * i;
-    const bool ok = a.want_grad && grp == 0 && c < C;
-    qh_pre[i] = ok ? __ldcg(a.q_hat + (size_t)row * C + c) : 0.f;
-    kh_pre[i] = ok ? __ldcg(a.k_hat + (size_t)row * C + c) : 0.f;
+  float qh_pre = 0.f, kh_pre = 0.f, inv_pre = 0.f;
+  if (own0) {
+    qh_pre = __ldcg(a.q_hat + (size_t)row * C + ct);
+    kh_pre = __ldcg(a.k_hat + (size_t)row * C + ct);
+    inv_pre = __ldcg(a.inv_norm + row);
   }
-  if (own0) inv_pre = __ldcg(a.inv_norm + row);
 
   if (tid < 32) {
-    // merge the split statistics (one warp; a row's statistics are contiguous => coalesced loads, all issued up front:
-    // up to 8 per lane covers 256 splits, the rare longer rows take the second loop)
+    // merge the split statistics (one warp; a row's statistics are contiguous => coalesced loads).  Rolled loops on purpose:
+    // every CTA runs this once, with a cold instruction cache, so code size is latency here
     const float* rm = a.pm + (size_t)row * splits;
     const float* rl = a.pl + (size_t)row * splits;
     const float* rav = a.pav + (size_t)row * splits;
     const int* rai = a.pai + (size_t)row * splits;
     const float p2 = __ldcg(a.pos2 + row);
     const unsigned poison_flag = __ldcg(a.counter + 1);
-    constexpr int kS = 8;
-    float vm[kS], vl[kS], vv[kS];
-    int vi[kS];
-#pragma unroll
-    for (int u = 0; u < kS; ++u) {
-      const int s = tid + 32 * u;
-      const bool ok = s < splits;
-      vm[u] = ok ? __ldcg(rm + s) : -INFINITY;
-      vl[u] = ok ? __ldcg(rl + s) : 0.f;
-      vv[u] = ok ? __ldcg(rav + s) : -INFINITY;
-      vi[u] = ok ? __ldcg(rai + s) : 0x7fffffff;
-    }
     float mmax = -INFINITY;
-#pragma unroll
-    for (int u = 0; u < kS; ++u) mmax = fmaxf(mmax, vm[u]);
-    for (int s = tid + 32 * kS; s < splits; s += 32) mmax = fmaxf(mmax, __ldcg(rm + s));
+    for (int s = tid; s < splits; s += 32) mmax = fmaxf(mmax, __ldcg(rm + s));
     mmax = warp_max(mmax);
     float lsum = 0.f;
     float bv = -INFINITY;
@@ -327,16 +314,14 @@ __device__ __forceinline__ void finalize_row(const FinArgs& a, const int row, fl
       dsum = warp_sum(dsum);
       if (tid == 0) fs->s_stats[2] = dsum;
     }
-    auto merge = [&](int s, float ms, float ls, float v, int i) {
+    for (int s = tid; s < splits; s += 32) {
+      const float ms = __ldcg(rm + s), ls = __ldcg(rl + s), v = __ldcg(rav + s);
+      const int i = __ldcg(rai + s);
       const float w = (ms == -INFINITY) ? 0.f : exp2f(ms - mmax);
       sw[s] = w;
       lsum = fmaf(ls, w, lsum);
       if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
-    };
-#pragma unroll
-    for (int u = 0; u < kS; ++u)
-      if (tid + 32 * u < splits) merge(tid + 32 * u, vm[u], vl[u], vv[u], vi[u]);
-    for (int s = tid + 32 * kS; s < splits; s += 32) merge(s, __ldcg(rm + s), __ldcg(rl + s), __ldcg(rav + s), __ldcg(rai + s));
+    }
     lsum = warp_sum(lsum);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -454,8 +439,8 @@ __device__ __forceinline__ void finalize_row(const FinArgs& a, const int row, fl
 #pragma unroll
             for (int g = 1; g < kGroups; ++g) s += part[(size_t)(g - 1) * C + c];
           }
-          const float kh = round_if(kh_pre[i], a.bf16_mode);
-          qh[i] = qh_pre[i];
+          const float kh = round_if(i == 0 ? kh_pre : __ldcg(a.k_hat + (size_t)row * C + c), a.bf16_mode);
+          qh[i] = (i == 0) ? qh_pre : __ldcg(a.q_hat + (size_t)row * C + c);
           dqh[i] = gs * fmaf(s, o_scale, pm1 * kh);
           dot = fmaf(qh[i], dqh[i], dot);
           if (a.dk) a.dk[(size_t)row * C + c] = gs * pm1 * round_if(qh[i], a.bf16_mode);
