@@ -216,9 +216,29 @@ __device__ __forceinline__ float ld_partial(const __nv_bfloat16* p) {
 
 // shared memory a finalize team needs: merge weights + per-group partial rows
 __host__ __device__ inline size_t finalize_smem_bytes(int C, int splits, bool bf16_partials, int team_threads) {
+  const int vc = bf16_partials ? 8 : 4;                       // columns per 16-byte load
   const int col_threads = team_threads < 256 ? team_threads : 256;
-  const size_t rows = bf16_partials ? (size_t)(team_threads / (C / 8)) : (size_t)(team_threads / col_threads - 1);
+  size_t rows;
+  if (C % vc == 0 && C / vc <= team_threads) rows = (size_t)(team_threads / (C / vc));   // 16-byte path: one row per split group
+  else rows = (size_t)(team_threads / col_threads - 1);                                  // scalar path
   return ((size_t)((splits + 3) & ~3) + rows * C) * sizeof(float);
+}
+
+// weighted accumulation of one 16-byte load of partials into kVC column sums
+__device__ __forceinline__ void fma_partial(const uint4& u, float w, float* acc, const __nv_bfloat16*) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(h[j]);
+    acc[2 * j] = fmaf(f.x, w, acc[2 * j]);
+    acc[2 * j + 1] = fmaf(f.y, w, acc[2 * j + 1]);
+  }
+}
+__device__ __forceinline__ void fma_partial(const uint4& u, float w, float* acc, const float*) {
+  acc[0] = fmaf(__uint_as_float(u.x), w, acc[0]);
+  acc[1] = fmaf(__uint_as_float(u.y), w, acc[1]);
+  acc[2] = fmaf(__uint_as_float(u.z), w, acc[2]);
+  acc[3] = fmaf(__uint_as_float(u.w), w, acc[3]);
 }
 
 // per-team scratch of finalize_row
@@ -256,17 +276,20 @@ __device__ __forceinline__ void finalize_row(const FinArgs& a, const int row, fl
   // batch of loads in flight before waiting for the statistics.
   constexpr int kPre = 8;
   float pre[kPre];
-  // bf16 partials (tcgen05 kernels; C % 8 == 0): 16-byte loads, 8 columns per thread, C/8 threads per pass over a row and
-  // NT / (C/8) split groups; a thread's loads are issued in batches of kPreV, the first batch before the statistics barrier
-  // (NT = 512 at cfg2: 5 loads per thread, one batch; a 128-thread team of the single-launch kernel: 19 loads, two batches).
-  constexpr bool kVec = (sizeof(TP) == 2);
+  // 16-byte loads of the partials whenever a row is a whole number of them (bf16: 8 columns, fp32: 4 columns per load):
+  // C/kVC threads per pass over a row and NT / (C/kVC) split groups; a thread's loads are issued in batches of kPreV, the
+  // first batch before the statistics barrier (NT = 512 at cfg2: 5 loads per thread, one batch).  The fp32 partials of
+  // the split-operand and CUDA-core kernels used to take the scalar path below: 73 dependent 4-byte loads per thread in
+  // batches of four at the cfg4 shape = 19.9 us under ncu, the largest piece of that call.
+  constexpr int kVC = 16 / (int)sizeof(TP);
+  const bool kVec = (C % kVC == 0) && (C / kVC <= NT);
   constexpr int kPreV = NT >= 512 ? 6 : 20;   // every load of a row in flight at once (registers are free in the row phases)
-  uint4 prev[kVec ? kPreV : 1];
-  const int vpr = C >> 3;                           // threads per row pass
+  uint4 prev[kPreV];
+  const int vpr = kVec ? C / kVC : NT;              // threads per row pass
   const int vgroups = kVec ? NT / vpr : 1;          // split groups
   const int vg = tid / vpr, vc = tid - vg * vpr;
   const bool vactive = kVec && a.want_grad && vg < vgroups;
-  const size_t sstride4 = (size_t)B * C / 8;
+  const size_t sstride4 = (size_t)B * C / kVC;
   const uint4* prow4 = reinterpret_cast<const uint4*>(po + (size_t)row * C) + vc;
   if (kVec) {
 #pragma unroll
@@ -360,18 +383,11 @@ __device__ __forceinline__ void finalize_row(const FinArgs& a, const int row, fl
     const size_t sstride = (size_t)B * C;
     const TP* prow = po + (size_t)row * C;
     if (kVec) {
-      // 8 columns per thread, weighted sum over this group's splits, then one row of partial sums per group in shared memory
-      float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (vactive) {
-        auto fma8 = [&](const uint4& u, float w) {
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+      // kVC columns per thread, weighted sum over this group's splits, then one row of partial sums per group in shared memory
+      float av[kVC];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = __bfloat1622float2(h[j]);
-            a8[2 * j] = fmaf(f.x, w, a8[2 * j]);
-            a8[2 * j + 1] = fmaf(f.y, w, a8[2 * j + 1]);
-          }
-        };
+      for (int j = 0; j < kVC; ++j) av[j] = 0.f;
+      if (vactive) {
         for (int base = 0; base < splits; base += kPreV * vgroups) {
           if (base > 0) {   // next batch: all of its loads in flight before the first use
 #pragma unroll
@@ -383,12 +399,12 @@ __device__ __forceinline__ void finalize_row(const FinArgs& a, const int row, fl
 #pragma unroll
           for (int u = 0; u < kPreV; ++u) {
             const int sp = base + vg + u * vgroups;
-            if (sp < splits) fma8(prev[u], sw[sp]);
+            if (sp < splits) fma_partial(prev[u], sw[sp], av, static_cast<const TP*>(nullptr));
           }
         }
-        float4* dst = reinterpret_cast<float4*>(part + (size_t)vg * C + vc * 8);
-        dst[0] = make_float4(a8[0], a8[1], a8[2], a8[3]);
-        dst[1] = make_float4(a8[4], a8[5], a8[6], a8[7]);
+        float* dst = part + (size_t)vg * C + vc * kVC;
+#pragma unroll
+        for (int j = 0; j < kVC; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(av[j], av[j + 1], av[j + 2], av[j + 3]);
       }
     } else {
 #pragma unroll

@@ -38,6 +38,10 @@ namespace rmcl {
 #ifndef RMCL_PGD_MIN_CTAS
 #define RMCL_PGD_MIN_CTAS 5
 #endif
+// independent 16-byte steps per thread in the update phase (2: 4 loads in flight per thread)
+#ifndef RMCL_PGD_UPDATE_UNROLL
+#define RMCL_PGD_UPDATE_UNROLL 2
+#endif
 constexpr int kPgdThreads = 256;
 constexpr int kPgdChunkBytes = RMCL_PGD_CHUNK_KB * 1024;                 // per operand per work item
 #ifndef RMCL_PGD_BATCH_MB
@@ -411,14 +415,14 @@ __global__ void __launch_bounds__(kPgdThreads, (sizeof(TD) + sizeof(TG) == 8) ? 
         proj = s_norm[1];
       }
       if (vec) {
-        // one thread step = VE elements = 16 B of the narrower-typed operand
+        // one thread step = VE elements = 16 B of the narrower-typed operand; kH independent steps in flight per thread
+        constexpr int kH = RMCL_PGD_UPDATE_UNROLL;
         const long long nv = n / VE;
-        for (long long i = threadIdx.x; i < nv; i += 2 * kPgdThreads) {
-          const bool second = (i + kPgdThreads) < nv;
-          float gx[2][VE], dx[2][VE];
+        for (long long i = threadIdx.x; i < nv; i += kH * kPgdThreads) {
+          float gx[kH][VE], dx[kH][VE];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (h == 1 && !second) break;
+          for (int h = 0; h < kH; ++h) {
+            if (i + h * kPgdThreads >= nv) break;
             const long long base = (i + h * kPgdThreads) * VE;
 #pragma unroll
             for (int q = 0; q < VE / VG; ++q) {
@@ -436,8 +440,8 @@ __global__ void __launch_bounds__(kPgdThreads, (sizeof(TD) + sizeof(TG) == 8) ? 
             }
           }
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (h == 1 && !second) break;
+          for (int h = 0; h < kH; ++h) {
+            if (i + h * kPgdThreads >= nv) break;
             const long long base = (i + h * kPgdThreads) * VE;
 #pragma unroll
             for (int q = 0; q < VE / VD; ++q) {

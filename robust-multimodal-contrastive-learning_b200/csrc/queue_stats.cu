@@ -86,11 +86,13 @@ __global__ void __launch_bounds__(256) queue_colnorm_kernel(const TQ* __restrict
   }
 }
 
+constexpr int kRowsumThreads = 1024;   // one CTA per row and at most one row per SM: the bytes in flight have to come from the CTA
+
 template <typename TQ>
-__global__ void __launch_bounds__(256) queue_rowsum_kernel(const TQ* __restrict__ queue, long long K, long long ldq,
+__global__ void __launch_bounds__(kRowsumThreads) queue_rowsum_kernel(const TQ* __restrict__ queue, long long K, long long ldq,
                                                            const float* __restrict__ colnorm2, float eps,
                                                            float* __restrict__ sum_vec, float* __restrict__ sum_unit) {
-  __shared__ float red[2][8];
+  __shared__ float red[2][kRowsumThreads / 32];
   const int c = blockIdx.x;
   const TQ* row = queue + (size_t)c * ldq;
   float s0 = 0.f, s1 = 0.f;
@@ -105,18 +107,19 @@ __global__ void __launch_bounds__(256) queue_rowsum_kernel(const TQ* __restrict_
     s1 = fmaf(v.w, __fdiv_rn(1.f, fmaxf(sqrtf(n.w), eps)), s1);
   };
   long long j = (long long)threadIdx.x * 4;
-  for (; j + 3 * 1024 < K4; j += 4 * 1024) {     // four independent 16-byte loads of the row (+ four of the norms) in flight
+  constexpr long long kStep = 4ll * kRowsumThreads;
+  for (; j + 3 * kStep < K4; j += 4 * kStep) {     // four independent 16-byte loads of the row (+ four of the norms) in flight
     float4 v[4], n[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      v[u] = ld4<TQ>(row + j + u * 1024);
-      n[u] = __ldg(reinterpret_cast<const float4*>(colnorm2 + j + u * 1024));
+      v[u] = ld4<TQ>(row + j + u * kStep);
+      n[u] = __ldg(reinterpret_cast<const float4*>(colnorm2 + j + u * kStep));
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) acc4(v[u], n[u]);
   }
-  for (; j < K4; j += 1024) acc4(ld4<TQ>(row + j), __ldg(reinterpret_cast<const float4*>(colnorm2 + j)));
-  for (long long t = K4 + threadIdx.x; t < K; t += 256) {
+  for (; j < K4; j += kStep) acc4(ld4<TQ>(row + j), __ldg(reinterpret_cast<const float4*>(colnorm2 + j)));
+  for (long long t = K4 + threadIdx.x; t < K; t += kRowsumThreads) {
     const float v = to_f32(row[t]);
     s0 += v;
     s1 = fmaf(v, __fdiv_rn(1.f, fmaxf(sqrtf(colnorm2[t]), eps)), s1);
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(256) queue_rowsum_kernel(const TQ* __restrict_
   __syncthreads();
   if (threadIdx.x == 0) {
     float t0 = 0.f, t1 = 0.f;
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < kRowsumThreads / 32; ++w) {
       t0 += red[0][w];
       t1 += red[1][w];
     }
@@ -153,12 +156,12 @@ extern "C" int rmcl_queue_stats(const void* queue, rmcl_dtype queue_dtype, int C
   if (queue_dtype == RMCL_F32) {
     rmcl::queue_colnorm_kernel<float><<<grid, 256, 0, s>>>((const float*)queue, C, K, ldq, colnorm2);
     RMCL_LAUNCH_OK("queue_colnorm_kernel");
-    rmcl::queue_rowsum_kernel<float><<<C, 256, 0, s>>>((const float*)queue, K, ldq, colnorm2, cos_eps, sum_vec, sum_unit);
+    rmcl::queue_rowsum_kernel<float><<<C, rmcl::kRowsumThreads, 0, s>>>((const float*)queue, K, ldq, colnorm2, cos_eps, sum_vec, sum_unit);
   } else {
     using bf16 = __nv_bfloat16;
     rmcl::queue_colnorm_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)queue, C, K, ldq, colnorm2);
     RMCL_LAUNCH_OK("queue_colnorm_kernel");
-    rmcl::queue_rowsum_kernel<bf16><<<C, 256, 0, s>>>((const bf16*)queue, K, ldq, colnorm2, cos_eps, sum_vec, sum_unit);
+    rmcl::queue_rowsum_kernel<bf16><<<C, rmcl::kRowsumThreads, 0, s>>>((const bf16*)queue, K, ldq, colnorm2, cos_eps, sum_vec, sum_unit);
   }
   RMCL_LAUNCH_OK("queue_rowsum_kernel");
   return RMCL_OK;

@@ -131,13 +131,15 @@ def _close(a, b, rtol, what):
     assert err <= rtol * max(ref, 1e-12), f"{what}: max err {err:.3e} vs scale {ref:.3e}"
 
 
-@pytest.mark.parametrize("name", ["ref_facade_c128", "ref_facade_c16"])
-def test_compute_moco_contrastive_matches_reference(golden, name):
+@pytest.mark.parametrize("name,path", [("ref_facade_c128", "simt"), ("ref_facade_c16", "simt"), ("ref_facade_c128", "auto")])
+def test_compute_moco_contrastive_matches_reference(golden, name, path):
+    """path="simt": exact fp32 products on the CUDA cores; path="auto" on the fp32 queue with C = 128: the fp32-accurate
+    split-operand tcgen05 kernels for the main-step AND the PGD-inner InfoNCE (the default of the drop-in) — same bars."""
     import rmcl_b200
     g = golden(name)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
-    mod = TinyModule(g, "simt").to(DEV).train()
+    mod = TinyModule(g, path).to(DEV).train()
     for s in range(g.i("meta/steps")):
         mod.zero_grad()
         mod.logged.clear()
@@ -158,8 +160,8 @@ def test_compute_moco_contrastive_matches_reference(golden, name):
                 want = g.t(f"step{s}/k_after/{k}")
                 if s == 0:
                     assert torch.equal(v.detach().cpu(), want), k
-                else:
-                    _close(v, want, 1e-5, k)
+                else:   # step 1 runs on parameters nudged by step 0's gradients (fp32-level differences between the paths)
+                    _close(v, want, 1e-5 if path == "simt" else 1e-4, k)
             elif f"step{s}/grad/{k}" in g:
                 _close(v.grad, g.np(f"step{s}/grad/{k}"), 5e-3, f"step {s} grad {k}")
         rate = mod.logged["moco_attack/PGD_success_rate"]
@@ -315,7 +317,8 @@ def test_other_pgd_attackers_match_reference(golden):
         assert got.abs().max().item() <= float(np.float32(eps))
 
     one = dict(base, image=[g.t("batch/image").to(DEV)])
-    close(P.PGDAttack_bartlowtwins(cfg).pgd_attack(mod, deepcopy(one), k_modality=g.t("k_barlowtwins").to(DEV)), "barlowtwins")
+    close(P.PGDAttack_bartlowtwins(cfg, fused_loss=False).pgd_attack(mod, deepcopy(one), k_modality=g.t("k_barlowtwins").to(DEV)),
+          "barlowtwins")                       # the reference's fp32 inner loss in torch
     close(P.PGDAttack_vqa(cfg).pgd_attack(mod, deepcopy(one)), "vqa")
     two = dict(base, image=[g.t("batch/image").to(DEV)], image_0=[g.t("batch/image_0").to(DEV)],
                image_1=[g.t("batch/image_1").to(DEV)], answers=[0, 1, 1, 0])
@@ -326,7 +329,7 @@ def test_other_pgd_attackers_match_reference(golden):
     assert d0.abs().max().item() == 0.0
     close(d1, "nlvr2_only1_1")
     # fused inner loss (bf16 tensor-core Gram path): same perturbation within the bf16 bar, signs agree
-    df = P.PGDAttack_bartlowtwins(cfg, fused_loss=True).pgd_attack(mod, deepcopy(one), k_modality=g.t("k_barlowtwins").to(DEV))
+    df = P.PGDAttack_bartlowtwins(cfg).pgd_attack(mod, deepcopy(one), k_modality=g.t("k_barlowtwins").to(DEV))   # the default
     want = g.t("delta/barlowtwins")
     assert (df.cpu() - want).abs().max().item() <= 2e-2 * eps
     nz = want.abs() > 1e-3 * eps
@@ -361,7 +364,7 @@ class BarlowModule(nn.Module):
         self.max_image_len = 200
         cfg = dict(adv_steps_img=g.i("meta/n_pgd"), adv_lr_img=g.f("meta/lr"), adv_max_norm_img=g.f("meta/eps"),
                    max_image_len=200)
-        self.pgd_attacker = rmcl_b200.PGDAttack_bartlowtwins(cfg)
+        self.pgd_attacker = rmcl_b200.PGDAttack_bartlowtwins(cfg, fused_loss=False)   # fp32 inner loss: the golden run is held to 1e-3 on the diagnostics
         for phase in ("train", "val"):
             for name in ("barlowtwins_loss", "barlowtwins_loss_invariance_img", "barlowtwins_loss_redundancy_img"):
                 setattr(self, f"{phase}_{name}", lambda x: x)

@@ -6,13 +6,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "robust-multimodal-contrastive-learning_b200")
 VARIANTS = {
     "base": [],
-    "ilv": ["-DRMCL_PGD_INTERLEAVE=1"],
-    "pf": ["-DRMCL_PGD_L2_PREFETCH=1"],
-    "pf_ilv": ["-DRMCL_PGD_L2_PREFETCH=1", "-DRMCL_PGD_INTERLEAVE=1"],
-    "pf_ilv_cta6": ["-DRMCL_PGD_L2_PREFETCH=1", "-DRMCL_PGD_INTERLEAVE=1", "-DRMCL_PGD_MIN_CTAS=6"],
-    "pf_ilv_cta4": ["-DRMCL_PGD_L2_PREFETCH=1", "-DRMCL_PGD_INTERLEAVE=1", "-DRMCL_PGD_MIN_CTAS=4"],
-    "pf_ilv_b16": ["-DRMCL_PGD_L2_PREFETCH=1", "-DRMCL_PGD_INTERLEAVE=1", "-DRMCL_PGD_BATCH_MB=16", "-DRMCL_PGD_BATCH_MB_L2=32"],
-    "pf_ilv_b32": ["-DRMCL_PGD_L2_PREFETCH=1", "-DRMCL_PGD_INTERLEAVE=1", "-DRMCL_PGD_BATCH_MB=32", "-DRMCL_PGD_BATCH_MB_L2=48"],
+    "u4": ["-DRMCL_PGD_UPDATE_UNROLL=4"],
+    "u4_cta4": ["-DRMCL_PGD_UPDATE_UNROLL=4", "-DRMCL_PGD_MIN_CTAS=4"],
+    "u4_cta3": ["-DRMCL_PGD_UPDATE_UNROLL=4", "-DRMCL_PGD_MIN_CTAS=3"],
+    "u3_cta4": ["-DRMCL_PGD_UPDATE_UNROLL=3", "-DRMCL_PGD_MIN_CTAS=4"],
+    "u1_cta6": ["-DRMCL_PGD_UPDATE_UNROLL=1", "-DRMCL_PGD_MIN_CTAS=6"],
 }
 if "--build" in sys.argv:
     sys.path.insert(0, os.path.join(PKG, "csrc"))
