@@ -223,6 +223,31 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // of the ~10 KB unrolled softmax body costs ~5 k cycles in instruction-cache misses (measured with the
     // timeline: 5.0 k for tile 0 against 1.7 k for every later tile), so it is paid during that wait
     // instead of on the critical path of the first tile.
+    // ---- Q^ rows: the global loads are ISSUED here and consumed at it == 0, so that the optional dry pass of the tile body
+    //      (it == -1) runs while they are in flight instead of in front of them
+    if (FUSED) grid_barrier(fz.bar_words, (unsigned)n_ctas, 15, kSoftmaxWarps * 32);   // every CTA's prep rows are written
+    else pdl_wait();   // launched early (PDL): q_hat is written by the prep kernel that may still be running
+    if (tid == 0) tl_stamp(tl, 2);
+    constexpr int kChunks = C / 64;                     // 64-column chunks of a row
+    constexpr int kMine = (kChunks + 1) / 2;            // chunks handled by this warp: ch = 2*t + par
+    uint4 v[kMine][8];
+    {
+      const __nv_bfloat16* qw = q_hat + (size_t)(split % kQhatReplicas) * ((size_t)gridDim.y * kTcRows * C) +
+                                (size_t)(row0 + quad * 32) * C;
+#pragma unroll
+      for (int t = 0; t < kMine; ++t) {
+        const int ch = 2 * t + par;
+        if (ch < kChunks) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            v[t][j] = FUSED ? __ldcg(reinterpret_cast<const uint4*>(qw + (size_t)(4 * j + (lane >> 3)) * C + ch * 64) + (lane & 7))
+                            : __ldg(reinterpret_cast<const uint4*>(qw + (size_t)(4 * j + (lane >> 3)) * C + ch * 64) + (lane & 7));
+        }
+      }
+    }
+    // Measured again in round 2 with the loads issued in front of the dry pass (profiles/r2_ab_dry.txt): whole call 32.8 us
+    // without, 33.6 us with the dry softmax pass, 33.7 us with both dry passes — over consecutive calls the instruction cache
+    // is warm anyway, so the dry passes stay compiled out.
 #ifndef RMCL_TC_DRY_SOFTMAX
 #define RMCL_TC_DRY_SOFTMAX 0
 #endif
@@ -236,26 +261,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         // Coalesced global loads (8 lanes cover one 128-byte row segment), all issued before the first
         // use, transposed through this warp's 4 KB of the (still unused) P buffers with the same
         // 16-byte XOR swizzle that keeps the segment writes and the row-per-lane reads conflict free.
-        if (FUSED) grid_barrier(fz.bar_words, (unsigned)n_ctas, 15, kSoftmaxWarps * 32);   // every CTA's prep rows are written
-        else pdl_wait();   // launched early (PDL): q_hat is written by the prep kernel that may still be running
-        if (tid == 0) tl_stamp(tl, 2);
         {
-          constexpr int kChunks = C / 64;                     // 64-column chunks of a row
-          constexpr int kMine = (kChunks + 1) / 2;            // chunks handled by this warp: ch = 2*t + par
           uint8_t* scratch = pbuf + warp * 4096;
-          const __nv_bfloat16* qw = q_hat + (size_t)(split % kQhatReplicas) * ((size_t)gridDim.y * kTcRows * C) +
-                                    (size_t)(row0 + quad * 32) * C;
-          uint4 v[kMine][8];
-    #pragma unroll
-          for (int t = 0; t < kMine; ++t) {
-            const int ch = 2 * t + par;
-            if (ch < kChunks) {
-    #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                v[t][j] = FUSED ? __ldcg(reinterpret_cast<const uint4*>(qw + (size_t)(4 * j + (lane >> 3)) * C + ch * 64) + (lane & 7))
-                                : __ldg(reinterpret_cast<const uint4*>(qw + (size_t)(4 * j + (lane >> 3)) * C + ch * 64) + (lane & 7));
-            }
-          }
     #pragma unroll
           for (int t = 0; t < kMine; ++t) {
             const int ch = 2 * t + par;
