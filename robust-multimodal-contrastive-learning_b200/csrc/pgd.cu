@@ -23,6 +23,15 @@
 // the items it waits for have smaller tickets, i.e. are already running, so the wait cannot deadlock
 // regardless of how many CTAs are resident.  Per-chunk partials are combined by a fixed-shape tree, so
 // the result is deterministic (and the inf-norm, hence REF_LINF, is exact).
+//
+// Round 2, two alternatives to the L2-resident scheme were built and measured on B200 (profiles/r2_pgd_staged_experiment.txt)
+// and dropped: (a) a persistent one-CTA-per-SM pipeline that keeps the chunks in SHARED memory between norm and update
+// (bulk-async loads, tagged per-chunk partials polled by a control warp): 152-240 us against 147 us for the pixel ref_linf
+// case — the 30 MB of shared memory on the chip hold only ~7 us of input, about the residency a chunk needs (load latency +
+// skew between the ~75 CTAs that share a sample + a 2.6 k-cycle L2 poll under DRAM load + update), so every CTA runs in
+// lock-step with its neighbours; (b) this kernel with its operands staged through a double-buffered shared-memory stage by
+// cp.async.bulk one item ahead: 240 us — one item in flight per CTA is fewer bytes in flight than the register path has, and
+// the per-item latency chains (ticket, partial publish, totals) no longer overlap across 5 CTAs x 8 warps.
 #include "common.cuh"
 
 namespace rmcl {
@@ -39,6 +48,9 @@ namespace rmcl {
 #define RMCL_PGD_MIN_CTAS 5
 #endif
 // independent 16-byte steps per thread in the update phase (2: 4 loads in flight per thread)
+#ifndef RMCL_PGD_PRELOAD
+#define RMCL_PGD_PRELOAD 1
+#endif
 #ifndef RMCL_PGD_UPDATE_UNROLL
 #define RMCL_PGD_UPDATE_UNROLL 2
 #endif
@@ -57,14 +69,27 @@ constexpr int kPgdChunkBytes = RMCL_PGD_CHUNK_KB * 1024;                 // per 
 constexpr long long kPgdBatchBytes = (long long)RMCL_PGD_BATCH_MB * 1024 * 1024;
 constexpr long long kPgdBatchBytesL2 = (long long)RMCL_PGD_BATCH_MB_L2 * 1024 * 1024;
 
+// max|g| with torch.norm(p=inf)'s NaN behaviour: |x| and the running maximum are non-negative floats or NaNs with a clear
+// sign bit, and on those bit patterns the unsigned integer order is the float order with every NaN above +inf — so an integer
+// maximum propagates a NaN gradient into the sample's norm (fmaxf would drop it), as ATen does.
+__device__ __forceinline__ float absmax_nan(float acc, float x) {
+  const unsigned a = __float_as_uint(acc), b = __float_as_uint(x) & 0x7fffffffu;
+  return __uint_as_float(a > b ? a : b);
+}
+__device__ __forceinline__ float warp_absmax_nan(float v) {
+  return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(v)));
+}
+// torch.clamp(x, min=lo) keeps a NaN
+__device__ __forceinline__ float clamp_min_nan(float x, float lo) { return (x != x) ? x : fmaxf(x, lo); }
+
 __device__ __forceinline__ float block_reduce(float v, bool is_max, float* red /*[32]*/) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  v = is_max ? warp_max(v) : warp_sum(v);
+  v = is_max ? warp_absmax_nan(v) : warp_sum(v);
   __syncthreads();
   if (lane == 0) red[w] = v;
   __syncthreads();
   float r = (lane < nw) ? red[lane] : 0.f;
-  r = is_max ? warp_max(r) : warp_sum(r);
+  r = is_max ? warp_absmax_nan(r) : warp_sum(r);
   return r;  // valid in every thread
 }
 
@@ -75,7 +100,7 @@ template <>
 __device__ __forceinline__ float pgd_apply<float>(float delta, float g, float lr, float denom, int mode) {
   float step;
   if (mode == RMCL_PGD_SIGN_LINF) {
-    const float sg = (g > 0.f) ? 1.f : ((g < 0.f) ? -1.f : (g == g ? 0.f : g));
+    const float sg = (g > 0.f) ? 1.f : ((g < 0.f) ? -1.f : 0.f);   // torch.sign: 0 for +-0 and for NaN
     step = __fmul_rn(lr, sg);
   } else {
     step = __fdiv_rn(__fmul_rn(lr, g), denom);
@@ -90,11 +115,11 @@ __device__ __forceinline__ float pgd_apply<__nv_bfloat16>(float delta, float g, 
 }
 template <typename TD> __device__ __forceinline__ float clamp_eps(float v, float eps);
 template <> __device__ __forceinline__ float clamp_eps<float>(float v, float eps) {
-  return fminf(fmaxf(v, -eps), eps);
+  return (v != v) ? v : fminf(fmaxf(v, -eps), eps);   // ATen's clamp keeps a NaN
 }
 template <> __device__ __forceinline__ float clamp_eps<__nv_bfloat16>(float v, float eps) {
   const float e = __bfloat162float(__float2bfloat16_rn(eps));  // ATen casts the bound to the tensor dtype
-  return fminf(fmaxf(v, -e), e);
+  return (v != v) ? v : fminf(fmaxf(v, -e), e);
 }
 
 struct PgdPlan {
@@ -112,9 +137,11 @@ struct PgdPlan {
   // workspace
   unsigned int* ticket;  // [1]
   unsigned int* exits;   // [1] CTAs that have left the work loop
-  unsigned int* done;    // [B] chunks of the sample whose norm phase has finished (+1 once the totals are published)
+  unsigned int* done;    // [B] chunks of the sample whose norm phase has finished
   float* part;           // [3][B][chunks] per-chunk partials
-  float* norm;           // [3][B] totals, combined by the last arriving chunk of the sample
+  unsigned long long* words;  // [B][2] {1 : 32 | fp32 bits : 32}: denominator, projection scale of the sample — flag and value in
+                              // one 64-bit word, so a waiter needs ONE L2 round trip (2-2.6 k cycles under DRAM load) instead of
+                              // flag-then-totals, and the double-precision combination is done once per sample, not per chunk
 };
 
 struct PgdItem {
@@ -198,6 +225,16 @@ __device__ __forceinline__ void spin_until(const unsigned int* counter, unsigned
   } while (v < target);
 }
 
+__device__ __forceinline__ unsigned long long ld_word(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_word(unsigned long long* p, float val) {
+  const unsigned long long v = (1ull << 32) | (unsigned long long)__float_as_uint(val);
+  asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 // Stores this item's partials; the item that arrives last for its sample combines all the sample's
 // partials (thread c takes chunks c, c+256, ... then a fixed-shape block tree: deterministic no matter
 // which CTA happens to be last) and publishes the sample totals, followed by one more arrival, so that
@@ -219,19 +256,29 @@ __device__ __forceinline__ void pgd_publish_partials(const PgdPlan& p, const Pgd
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  float tot[3] = {0.f, 0.f, 0.f};
   for (int k = 0; k < p.n_sums; ++k) {
     const float* pp = p.part + k * plane + (long long)it.sample * p.chunks;
     float acc = 0.f;
     for (int c = threadIdx.x; c < p.chunks; c += kPgdThreads) {
       const float v = __ldcg(pp + c);
-      acc = is_max ? fmaxf(acc, v) : acc + v;
+      acc = is_max ? absmax_nan(acc, v) : acc + v;
     }
-    acc = block_reduce(acc, is_max, red);
-    if (threadIdx.x == 0) p.norm[k * p.B + it.sample] = acc;
+    tot[k] = block_reduce(acc, is_max, red);
   }
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(p.done + it.sample, 1u);
+    const float dn = clamp_min_nan(is_max ? tot[0] : sqrtf(tot[0]), 1e-8f);
+    float pj = 1.f;
+    if (p.n_sums == 3) {
+      // |delta + a g|^2 = |delta|^2 + 2a <delta,g> + a^2 |g|^2 with a = lr/denom, combined in double (three fp32 totals; the
+      // cross term may cancel)
+      const double a = (double)p.lr / (double)dn;
+      double n2 = (double)tot[2] + 2.0 * a * (double)tot[1] + a * a * (double)tot[0];
+      if (n2 < 0.0) n2 = 0.0;
+      pj = fminf(__fdiv_rn(p.eps, fmaxf((float)sqrt(n2), 1e-12f)), 1.f);
+    }
+    st_word(p.words + 2 * (long long)it.sample, dn);
+    st_word(p.words + 2 * (long long)it.sample + 1, pj);
   }
 }
 
@@ -273,7 +320,11 @@ __global__ void __launch_bounds__(kPgdThreads, (sizeof(TD) + sizeof(TG) == 8) ? 
       // The last CTA to leave returns the control words to zero, so the next call needs no memset launch
       // (every item has completed by then: a CTA only gets here after finishing all its items).
       if (threadIdx.x == 0 && atomicAdd(p.exits, 1u) == gridDim.x - 1u) {
-        for (int i = 0; i < p.B; ++i) p.done[i] = 0u;
+        for (int i = 0; i < p.B; ++i) {
+          p.done[i] = 0u;
+          p.words[2 * i] = 0ull;
+          p.words[2 * i + 1] = 0ull;
+        }
         *p.exits = 0u;
         __threadfence();
         *p.ticket = 0u;
@@ -324,7 +375,7 @@ __global__ void __launch_bounds__(kPgdThreads, (sizeof(TD) + sizeof(TG) == 8) ? 
 #pragma unroll
             for (int j = 0; j < VG; ++j) {
               const float x = to_f32(e[j]);
-              acc = is_max ? fmaxf(acc, fabsf(x)) : fmaf(x, x, acc);
+              acc = is_max ? absmax_nan(acc, x) : fmaf(x, x, acc);
             }
           }
         }
@@ -334,7 +385,7 @@ __global__ void __launch_bounds__(kPgdThreads, (sizeof(TD) + sizeof(TG) == 8) ? 
 #pragma unroll
           for (int j = 0; j < VG; ++j) {
             const float x = to_f32(e[j]);
-            acc = is_max ? fmaxf(acc, fabsf(x)) : fmaf(x, x, acc);
+            acc = is_max ? absmax_nan(acc, x) : fmaf(x, x, acc);
           }
         }
       } else if (vec) {
@@ -376,7 +427,7 @@ __global__ void __launch_bounds__(kPgdThreads, (sizeof(TD) + sizeof(TG) == 8) ? 
       } else {
         for (long long i = threadIdx.x; i < n; i += kPgdThreads) {
           const float x = to_f32(g[i]);
-          acc = is_max ? fmaxf(acc, fabsf(x)) : fmaf(x, x, acc);
+          acc = is_max ? absmax_nan(acc, x) : fmaf(x, x, acc);
           if (l2proj) {
             const float y = to_f32(d[i]);
             adg = fmaf(y, x, adg);
@@ -393,22 +444,32 @@ __global__ void __launch_bounds__(kPgdThreads, (sizeof(TD) + sizeof(TG) == 8) ? 
     } else {
       // ------------------------------------------------------------ P2: the update
       float denom = 1.f, proj = 1.f;
+      // The first kH steps of the update are requested BEFORE the totals are waited for: they do not depend on them, and the
+      // L2 round trip of the wait (2-2.6 k cycles under DRAM load) then overlaps the first DRAM access instead of preceding it.
+      constexpr int kH = RMCL_PGD_UPDATE_UNROLL;
+      const long long nv = n / VE;
+      uint4 pg[kH][VE / VG], pd[kH][VE / VD];
+      if (vec && RMCL_PGD_PRELOAD) {
+#pragma unroll
+        for (int h = 0; h < kH; ++h) {
+          if ((long long)threadIdx.x + h * kPgdThreads >= nv) break;
+          const long long base = ((long long)threadIdx.x + h * kPgdThreads) * VE;
+#pragma unroll
+          for (int q = 0; q < VE / VG; ++q) pg[h][q] = ld_u4_hint(reinterpret_cast<const uint4*>(g + base) + q, stream);
+#pragma unroll
+          for (int q = 0; q < VE / VD; ++q) pd[h][q] = ld_u4_hint(reinterpret_cast<const uint4*>(d + base) + q, stream);
+        }
+      }
       if (p.mode != RMCL_PGD_SIGN_LINF) {
         if (threadIdx.x == 0) {
-          spin_until(p.done + it.sample, (unsigned)p.chunks + 1u);   // +1: the sample totals have been published
-          const float tot = __ldcg(p.norm + it.sample);
-          const float dn = fmaxf(is_max ? tot : sqrtf(tot), 1e-8f);
-          float pj = 1.f;
-          if (l2proj) {
-            // |delta + a g|^2 with a = lr/denom, combined in double (three fp32 totals; the cross term may cancel)
-            const double a = (double)p.lr / (double)dn;
-            double n2 = (double)__ldcg(p.norm + 2 * p.B + it.sample) + 2.0 * a * (double)__ldcg(p.norm + p.B + it.sample) +
-                        a * a * (double)tot;
-            if (n2 < 0.0) n2 = 0.0;
-            pj = fminf(__fdiv_rn(p.eps, fmaxf((float)sqrt(n2), 1e-12f)), 1.f);
-          }
-          s_norm[0] = dn;
-          s_norm[1] = pj;
+          const unsigned long long* w = p.words + 2 * (long long)it.sample;
+          unsigned long long w0, w1;
+          do {   // both words in flight together: one round trip once the sample's last chunk has published
+            w0 = ld_word(w);
+            w1 = ld_word(w + 1);
+          } while ((w0 >> 32) == 0ull || (w1 >> 32) == 0ull);
+          s_norm[0] = __uint_as_float((unsigned)w0);
+          s_norm[1] = __uint_as_float((unsigned)w1);
         }
         __syncthreads();
         denom = s_norm[0];
@@ -416,40 +477,44 @@ __global__ void __launch_bounds__(kPgdThreads, (sizeof(TD) + sizeof(TG) == 8) ? 
       }
       if (vec) {
         // one thread step = VE elements = 16 B of the narrower-typed operand; kH independent steps in flight per thread
-        constexpr int kH = RMCL_PGD_UPDATE_UNROLL;
-        const long long nv = n / VE;
+        bool first = RMCL_PGD_PRELOAD != 0;
         for (long long i = threadIdx.x; i < nv; i += kH * kPgdThreads) {
-          float gx[kH][VE], dx[kH][VE];
+          if (!first) {
+#pragma unroll
+            for (int h = 0; h < kH; ++h) {
+              if (i + h * kPgdThreads >= nv) break;
+              const long long base = (i + h * kPgdThreads) * VE;
+#pragma unroll
+              for (int q = 0; q < VE / VG; ++q) pg[h][q] = ld_u4_hint(reinterpret_cast<const uint4*>(g + base) + q, stream);  // last use of g
+#pragma unroll
+              for (int q = 0; q < VE / VD; ++q) pd[h][q] = ld_u4_hint(reinterpret_cast<const uint4*>(d + base) + q, stream);
+            }
+          }
+          first = false;
 #pragma unroll
           for (int h = 0; h < kH; ++h) {
             if (i + h * kPgdThreads >= nv) break;
             const long long base = (i + h * kPgdThreads) * VE;
+            float gx[VE], dx[VE];
 #pragma unroll
             for (int q = 0; q < VE / VG; ++q) {
-              const uint4 u = ld_u4_hint(reinterpret_cast<const uint4*>(g + base) + q, stream);  // last use of g
-              const TG* e = reinterpret_cast<const TG*>(&u);
+              const TG* e = reinterpret_cast<const TG*>(&pg[h][q]);
 #pragma unroll
-              for (int j = 0; j < VG; ++j) gx[h][q * VG + j] = to_f32(e[j]);
+              for (int j = 0; j < VG; ++j) gx[q * VG + j] = to_f32(e[j]);
             }
 #pragma unroll
             for (int q = 0; q < VE / VD; ++q) {
-              const uint4 u = ld_u4_hint(reinterpret_cast<const uint4*>(d + base) + q, stream);
-              const TD* e = reinterpret_cast<const TD*>(&u);
+              const TD* e = reinterpret_cast<const TD*>(&pd[h][q]);
 #pragma unroll
-              for (int j = 0; j < VD; ++j) dx[h][q * VD + j] = to_f32(e[j]);
+              for (int j = 0; j < VD; ++j) dx[q * VD + j] = to_f32(e[j]);
             }
-          }
-#pragma unroll
-          for (int h = 0; h < kH; ++h) {
-            if (i + h * kPgdThreads >= nv) break;
-            const long long base = (i + h * kPgdThreads) * VE;
 #pragma unroll
             for (int q = 0; q < VE / VD; ++q) {
               uint4 u;
               TD* e = reinterpret_cast<TD*>(&u);
 #pragma unroll
               for (int j = 0; j < VD; ++j) {
-                float v = pgd_apply<TD>(dx[h][q * VD + j], gx[h][q * VD + j], p.lr, denom, p.mode);
+                float v = pgd_apply<TD>(dx[q * VD + j], gx[q * VD + j], p.lr, denom, p.mode);
                 if (do_clamp) v = clamp_eps<TD>(v, p.eps);
                 if (l2proj && proj < 1.f) v = __fmul_rn(v, proj);
                 e[j] = from_f32<TD>(v);
@@ -470,12 +535,15 @@ __global__ void __launch_bounds__(kPgdThreads, (sizeof(TD) + sizeof(TG) == 8) ? 
   }
 }
 
+
 static int pgd_make_plan(int B, long long N, float lr, float eps, int mode, size_t gsize, size_t dsize, PgdPlan* p) {
   p->N = N;
   p->B = B;
   p->mode = mode;
   p->lr = lr;
   p->eps = eps;
+  p->phases = (mode == RMCL_PGD_SIGN_LINF) ? 1 : 2;
+  p->n_sums = (mode == RMCL_PGD_L2 && eps > 0.f) ? 3 : 1;
   p->chunk_elems = kPgdChunkBytes / (int)gsize;
   const long long chunks = (N + p->chunk_elems - 1) / p->chunk_elems;
   if (chunks > (1ll << 30)) {
@@ -483,8 +551,6 @@ static int pgd_make_plan(int B, long long N, float lr, float eps, int mode, size
     return RMCL_E_UNSUPPORTED_DIM;
   }
   p->chunks = (int)chunks;
-  p->phases = (mode == RMCL_PGD_SIGN_LINF) ? 1 : 2;
-  p->n_sums = (mode == RMCL_PGD_L2 && eps > 0.f) ? 3 : 1;
   // bytes per sample that must survive in L2 between the two phases
   const long long resident = N * (long long)(gsize + (p->n_sums == 3 ? dsize : 0));
   long long batch = (p->n_sums == 3 ? kPgdBatchBytesL2 : kPgdBatchBytes) / resident;
@@ -497,8 +563,10 @@ static int pgd_make_plan(int B, long long N, float lr, float eps, int mode, size
 }
 
 static size_t pgd_ctrl_bytes(const PgdPlan& p) { return ((size_t)(2 + p.B) * sizeof(unsigned int) + 255) / 256 * 256; }
+// [ticket, exits, done[B] | words[B][2] | part[3][B][chunks]]
+static size_t pgd_words_bytes(const PgdPlan& p) { return ((size_t)p.B * 16 + 255) / 256 * 256; }
 static size_t pgd_ws_bytes(const PgdPlan& p) {
-  return pgd_ctrl_bytes(p) + 3 * ((size_t)p.B * p.chunks + p.B) * sizeof(float);
+  return pgd_ctrl_bytes(p) + pgd_words_bytes(p) + 3 * (size_t)p.B * p.chunks * sizeof(float);
 }
 
 template <typename TD, typename TG>
@@ -514,8 +582,8 @@ static int launch_pgd(void* delta, const void* grad, PgdPlan p, void* ws, size_t
   p.ticket = c;
   p.exits = c + 1;
   p.done = c + 2;
-  p.part = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + pgd_ctrl_bytes(p));
-  p.norm = p.part + 3 * (size_t)p.B * p.chunks;
+  p.words = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ws) + pgd_ctrl_bytes(p));
+  p.part = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + pgd_ctrl_bytes(p) + pgd_words_bytes(p));
   long long grid = (long long)sms * 8;
   if (grid > p.total_items) grid = p.total_items;
   pgd_ticket_kernel<TD, TG><<<(unsigned)grid, kPgdThreads, 0, s>>>((TD*)delta, (const TG*)grad, p);

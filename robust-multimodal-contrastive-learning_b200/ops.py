@@ -536,13 +536,14 @@ def enqueue_(queue, keys, ptr, shadow=None):
 # ------------------------------------------------------------------------------------ PGD
 def pgd_step_(delta, grad, lr, eps, mode="ref_linf", _scratch={}):
     """In-place perturbation update (attack/pgd_attack_vilt.py:162-173 for ``ref_linf``)."""
+    mode_arg = _lib.PGD_MODES[mode]
     _need_cuda(delta, grad)
     if delta.shape != grad.shape:
         raise ValueError("delta/grad shape mismatch")
     if not (delta.is_contiguous() and grad.is_contiguous()):
         raise ValueError("delta and grad must be contiguous")
     if _lib.ffi() == "torch":
-        _lib.torch_ops().pgd_step_(delta, grad, float(lr), float(eps), _lib.PGD_MODES[mode])
+        _lib.torch_ops().pgd_step_(delta, grad, float(lr), float(eps), mode_arg)
         return delta
     B = delta.shape[0]
     N = delta.numel() // B
@@ -556,7 +557,7 @@ def pgd_step_(delta, grad, lr, eps, mode="ref_linf", _scratch={}):
         ws = _scratch[key] = torch.zeros(nbytes + 256, dtype=torch.uint8, device=delta.device)   # zero-filled once
     off = (-ws.data_ptr()) % 256
     rc = _lib.lib().rmcl_pgd_step(_p(delta), _dt(delta), _p(grad), _dt(grad), B, N, float(lr), float(eps),
-                                  _lib.PGD_MODES[mode], C.c_void_p(ws.data_ptr() + off), ws.numel() - off, _stream())
+                                  mode_arg, C.c_void_p(ws.data_ptr() + off), ws.numel() - off, _stream())
     check(rc, "rmcl_pgd_step")
     return delta
 

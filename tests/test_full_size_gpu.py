@@ -109,6 +109,81 @@ def test_pgd_back_to_back_calls_share_the_workspace(ops):
     assert torch.equal(dd.cpu(), ref)
 
 
+# ------------------------------------------------------------------------------------------- PGD, dtype pairs x shapes
+MIXED_SHAPES = [(1, 4), (2, 64), (5, 6144), (300, 20000), (3, 900_000), (148, 12288), (149, 12352), (37, 3, 64, 64)]
+
+
+@pytest.mark.parametrize("shape", MIXED_SHAPES, ids=[str(s) for s in MIXED_SHAPES])
+@pytest.mark.parametrize("ddt", [torch.float32, torch.bfloat16], ids=["d32", "d16"])
+@pytest.mark.parametrize("gdt", [torch.float32, torch.bfloat16], ids=["g32", "g16"])
+def test_pgd_dtype_pairs_vs_oracle(ops, shape, ddt, gdt):
+    """All four (delta, grad) dtype pairs of csrc/pgd.cu at shapes with one chunk per sample, many chunks per sample,
+    ragged last chunks, fewer / one more work item than resident CTAs, N not a multiple of the 8-element bf16 vector
+    (scalar path): ref_linf bit-exact against oracle.pgd_update over three steps with adversarial samples, l2 (with and
+    without the projection) within 1e-4 (fp32 delta) / 2e-2 (bf16 delta) of the float64 oracle."""
+    B = shape[0]
+    g = torch.Generator(device=DEV).manual_seed(B)
+    dd = (torch.randn(shape, generator=g, device=DEV) * 0.01).to(ddt)
+    ref = dd.cpu()
+    for step in range(3):
+        grad = (_adversarial_grad(shape, step, seed=B)).to(gdt)
+        ops.pgd_step_(dd, grad, 0.05, 8.0 / 255.0, "ref_linf")
+        ref = O.pgd_update(ref, grad.cpu(), 0.05, 8.0 / 255.0)
+        assert torch.equal(dd.cpu(), ref), step
+    for eps in (0.1, 0.0):            # with and without the projection (three sums / one sum)
+        a = (torch.randn(shape, generator=g, device=DEV) * 0.01).to(ddt)
+        a.view(B, -1)[-1] *= 30.0     # starts outside the ball
+        ref = a.double().cpu()
+        for step in range(2):
+            grad = (_adversarial_grad(shape, step + 2, seed=B + 1)).to(gdt)
+            ops.pgd_step_(a, grad, 0.5, eps, "l2")
+            ref = O.pgd_update(ref, grad.cpu().double(), 0.5, eps, mode="l2")
+            assert rel_err(a, ref) < (1e-4 if ddt == torch.float32 else 2e-2), (eps, step)
+            if ddt != torch.float32:
+                ref = a.double().cpu()
+
+
+@pytest.mark.parametrize("mode", ["ref_linf", "sign_linf", "l2"])
+def test_pgd_nan_gradient_poisons_its_sample_only(ops, mode):
+    """torch.norm(p=inf) / clamp propagate a NaN (attack/pgd_attack_vilt.py:164-165, 170): one NaN gradient element
+    turns that sample's whole perturbation into NaN (ref_linf, l2) and leaves the other samples exactly as without it;
+    sign_linf follows torch.sign, which maps NaN to 0."""
+    shape = (6, 3, 64, 64)
+    g = torch.Generator().manual_seed(5)
+    grad = torch.randn(shape, generator=g)
+    grad[4, 1, 7, 9] = float("nan")
+    d0 = torch.randn(shape, generator=g) * 0.01
+    lr, eps = (0.5, 0.1) if mode == "l2" else (0.05, 8.0 / 255.0)
+    want = O.pgd_update(d0.double() if mode == "l2" else d0, grad.double() if mode == "l2" else grad, lr, eps, mode=mode)
+    got = ops.pgd_step_(d0.to(DEV), grad.to(DEV), lr, eps, mode).cpu()
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    assert torch.isnan(got).sum().item() == (0 if mode == "sign_linf" else 3 * 64 * 64)   # torch.sign(nan) == 0
+    ok = ~torch.isnan(want)
+    if mode == "l2":
+        assert rel_err(got[ok], want[ok]) < 1e-4
+    else:
+        assert torch.equal(got[ok], want[ok])
+
+
+def test_pgd_modes_alternate_on_one_workspace(ops):
+    """16 launches alternating between the three modes on one workspace, no sync in between: the self-resetting control
+    words serve the one-phase and the two-phase plans alike."""
+    shape = (40, 185, 768)
+    grads = [_adversarial_grad(shape, s, seed=21) for s in range(4)]
+    dd = torch.zeros(shape, device=DEV)
+    plan = ["ref_linf", "ref_linf", "sign_linf", "l2", "ref_linf", "sign_linf", "l2", "ref_linf"] * 2
+    for i, mode in enumerate(plan):
+        ops.pgd_step_(dd, grads[i % 4], 0.02, 8.0 / 255.0 if mode != "l2" else 1.0, mode)
+    ref = torch.zeros(shape, dtype=torch.float64)
+    gc = [x.cpu().double() for x in grads]
+    for i, mode in enumerate(plan):
+        if mode == "l2":
+            ref = O.pgd_update(ref, gc[i % 4], 0.02, 1.0, mode="l2")
+        else:   # fp32 arithmetic of the reference rule, carried in the float64 trajectory
+            ref = O.pgd_update(ref.float(), gc[i % 4].float(), 0.02, 8.0 / 255.0, mode=mode).double()
+    assert rel_err(dd, ref) < 1e-4
+
+
 # ------------------------------------------------------------------------------------------- InfoNCE, cfg5 full size
 def _rows_oracle_bf16(q_rows, k_rows, queue_bf16, T, B_full, chunk=32768):
     """float64 InfoNCE of a few rows against the whole queue, streamed over column chunks (the 768 x 262144 queue is

@@ -6,11 +6,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "robust-multimodal-contrastive-learning_b200")
 VARIANTS = {
     "base": [],
-    "u4": ["-DRMCL_PGD_UPDATE_UNROLL=4"],
-    "u4_cta4": ["-DRMCL_PGD_UPDATE_UNROLL=4", "-DRMCL_PGD_MIN_CTAS=4"],
-    "u4_cta3": ["-DRMCL_PGD_UPDATE_UNROLL=4", "-DRMCL_PGD_MIN_CTAS=3"],
+    "nopre": ["-DRMCL_PGD_PRELOAD=0"],
+    "cta4": ["-DRMCL_PGD_MIN_CTAS=4"],
+    "cta6": ["-DRMCL_PGD_MIN_CTAS=6"],
     "u3_cta4": ["-DRMCL_PGD_UPDATE_UNROLL=3", "-DRMCL_PGD_MIN_CTAS=4"],
     "u1_cta6": ["-DRMCL_PGD_UPDATE_UNROLL=1", "-DRMCL_PGD_MIN_CTAS=6"],
+    "b16": ["-DRMCL_PGD_BATCH_MB=16", "-DRMCL_PGD_BATCH_MB_L2=32"],
+    "b32": ["-DRMCL_PGD_BATCH_MB=32", "-DRMCL_PGD_BATCH_MB_L2=56"],
 }
 if "--build" in sys.argv:
     sys.path.insert(0, os.path.join(PKG, "csrc"))

@@ -11,6 +11,7 @@ for tag, shape, mode, lr, eps in (("pixel ref_linf", (128, 3, 384, 384), "ref_li
                                   ("pixel l2", (128, 3, 384, 384), "l2", 0.5, 1.0),
                                   ("embed ref_linf", (128, 185, 768), "ref_linf", 0.05, 8 / 255),
                                   ("embed l2", (128, 185, 768), "l2", 0.5, 1.0),
+                                  ("pixel sign", (128, 3, 384, 384), "sign_linf", 2 / 255, 8 / 255),
                                   ("embed sign", (128, 185, 768), "sign_linf", 2 / 255, 8 / 255)):
     grad = torch.randn(shape, device=dev, generator=g)
     delta = torch.zeros(shape, device=dev)
