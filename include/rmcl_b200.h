@@ -267,6 +267,8 @@ int rmcl_enqueue_shadow(void* queue, rmcl_dtype queue_dtype, void* shadow_bf16, 
  * REF_LINF in f32 is bit-identical to the reference: fadd(delta, fdiv(fmul(lr,g), d)).
  * L2 with eps > 0 takes the projection scale from |delta|^2 + 2a<delta,g> + a^2|g|^2 (a = lr/|g|),
  * so delta is written once, already projected.
+ * NaN: a NaN gradient element makes its sample's norm NaN and hence the whole sample's delta NaN (REF_LINF, L2), as
+ * torch.norm / torch.clamp do; SIGN_LINF maps it to a zero step like torch.sign.  Other samples are unaffected.
  * One persistent launch; the gradient is re-read from L2, so DRAM sees 12 B/element.
  *   workspace  rmcl_pgd_workspace_bytes(B, N, grad_dtype) bytes, 256-byte aligned, caller-owned
  *              (arrival counters + per-chunk partial norms).  It must be ZERO-FILLED once before

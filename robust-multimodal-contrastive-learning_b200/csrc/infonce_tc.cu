@@ -108,6 +108,11 @@ __device__ __forceinline__ long long global_ns() {
 #ifndef RMCL_TC_TIMELINE
 #define RMCL_TC_TIMELINE 0
 #endif
+// Timing experiments (results are garbage): bit 0 no tcgen05.ld of S, 1 no exponentials, 2 no P stores, 3 no decision
+// handshake — which part of the softmax side slows the tile loop (profiles/r2_tc_experiments.txt)
+#ifndef RMCL_TC_EXPERIMENT
+#define RMCL_TC_EXPERIMENT 0
+#endif
 __device__ __forceinline__ void tl_stamp(long long* tl, int idx) {
 #if RMCL_TC_TIMELINE
   if (tl != nullptr && idx < kTimelineHead) tl[idx] = clock64();
@@ -303,9 +308,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         if (quad == 0) tl_stamp(tl, 8 + 8 * i + 1);
       }
       uint32_t sv[TN];
+#if RMCL_TC_EXPERIMENT & 1   // timing experiment: no tcgen05.ld of S
+#pragma unroll
+      for (int j = 0; j < TN; ++j) sv[j] = __float_as_uint(0.001f * (float)(j + lane));
+#else
 #pragma unroll
       for (int ch = 0; ch < TN / 32; ++ch) tc_ld32(ts + ch * 32, sv + ch * 32);
       tc_wait_ld();
+#endif
       tc_fence_before();
       if (live) {
         mbar_arrive(&sh.s_free[b]);                       // S[b] is in registers
@@ -348,7 +358,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const float m_tile = mx * scale2;
 
       // ---- decision point of tile i: everything up to tile i-1 has been decided by the other warp
+#if !(RMCL_TC_EXPERIMENT & 8)   // timing experiment: no decision handshake between the two warps of a quadrant
       if (live && i > 0) named_bar_sync(dec_other, 64);
+#endif
       float m_now = (i > 0) ? sh.m_ref[r] : m_tile + kInitMargin;
       if (m_now != m_mine) {            // the other warp moved the reference (or this is my first tile)
         l_run *= exp2f(m_mine - m_now); // first tile: l_run == 0
@@ -377,10 +389,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         tc_wait_st();
       }
       if (live && (i == 0 || grow)) sh.m_ref[r] = m_mine;
+#if !(RMCL_TC_EXPERIMENT & 8)
       if (live && i + 1 < n_tiles) {    // publish the decision to the warp that owns tile i+1
         __threadfence_block();
         named_bar_arrive(dec_mine, 64);
       }
+#endif
 
       if (live && quad == 0) tl_stamp(tl, 8 + 8 * i + 7);
       // ---- P = 2^(S*scale - m) as bf16 pairs, row sum in fp32
@@ -389,8 +403,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       uint32_t pw[TN / 2];
 #pragma unroll
       for (int j = 0; j < TN / 2; ++j) {
+#if RMCL_TC_EXPERIMENT & 2   // timing experiment: no exponentials
+        const float p0 = fmaf(__uint_as_float(sv[2 * j]), scale2, neg_m);
+        const float p1 = fmaf(__uint_as_float(sv[2 * j + 1]), scale2, neg_m);
+#else
         const float p0 = ex2_ftz(fmaf(__uint_as_float(sv[2 * j]), scale2, neg_m));
         const float p1 = ex2_ftz(fmaf(__uint_as_float(sv[2 * j + 1]), scale2, neg_m));
+#endif
         ls[j & 3] += p0 + p1;
         const __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
         pw[j] = *reinterpret_cast<const uint32_t*>(&pk);
@@ -407,11 +426,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       //  l_run keeps the exponentials alive for the compiler)
       if (live && want_o) {
         uint8_t* prow = pbuf + b * kPBytes + r * 128;
+#if RMCL_TC_EXPERIMENT & 4   // timing experiment: P is not stored (one word keeps pw alive)
+        if (l_run == 123.456f) *reinterpret_cast<uint32_t*>(prow) = pw[0] ^ pw[TN / 2 - 1];
+#else
 #pragma unroll
         for (int c = 0; c < TN / 8; ++c) {
           uint8_t* dst = prow + (c >> 3) * 16384 + (((c & 7) ^ (r & 7)) << 4);
           *reinterpret_cast<uint4*>(dst) = make_uint4(pw[4 * c], pw[4 * c + 1], pw[4 * c + 2], pw[4 * c + 3]);
         }
+#endif
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor core reads
         mbar_arrive(&sh.p_full[b]);
         if (quad == 0) tl_stamp(tl, 8 + 8 * i + 2);
@@ -513,65 +536,88 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #endif
     int j_first = RMCL_TC_DRY_MMA ? -1 : 0;
     asm volatile("" : "+r"(j_first));
+    // RMCL_TC_MERGED_ISSUE: the S GEMM of tile j and the O GEMM of tile j-2 are issued as ONE straight-line burst of 20 MMAs
+    // behind a single wait phase.  tools/mma_bench.cu (profiles/r2_mma_bench.txt): the identical MMA stream runs at 1042
+    // cycles per tile (98 % of the tensor roof) when issued as one burst per tile, beside the kernel's tcgen05.ld / P-store /
+    // bulk-load traffic at 1193 (86 %) — the tile loop here took ~1700: the tensor pipe accepts only a few MMAs ahead of
+    // execution, so each of the two wait-then-issue phases per tile (barrier probes, fence, elect) drains it.
+    //   1: always merged (the burst waits for P(j-2) before S(j) is issued)
+    //   2: merged when P(j-2) is already there (non-blocking probe), else S(j) first as before
+#ifndef RMCL_TC_MERGED_ISSUE
+#define RMCL_TC_MERGED_ISSUE 2
+#endif
     for (int j = j_first; j < n_tiles + 2; ++j) {
       const bool live = j >= 0;
       if (j == 0) {
         mbar_wait(&sh.q_full, 0);
         tc_fence_after();
       }
-      if (!live || j < n_tiles) {
-        // ------------------------------------------------------------------ S GEMM of tile i = j
-        const int i = live ? j : 0;
-        const int st = i % kStages;
-        if (live) {
-          if (i >= 2) {
-            mbar_wait(&sh.s_free[i & 1], ((i - 2) >> 1) & 1);
-            tl_stamp(tl, 8 + 8 * i + 5);
-          }
-          mbar_wait(&sh.k_full[st], (i / kStages) & 1);
-          tc_fence_after();
-          tl_stamp(tl, 8 + 8 * i + 0);
-        }
-        uint64_t* bar_s = live ? &sh.s_full[i & 1] : &sh.dry;
-        if (elect_one()) {
-          const uint32_t sbase = smem_u32(ring + (size_t)st * kStageBytes);
-          const uint32_t dd = tmem + kTmS + (i & 1) * TN;
+      const bool do_s = !live || j < n_tiles;
+      const bool do_o = want_o && (!live || j >= 2);
+      const int is = live ? j : 0, io = live ? j - 2 : 0;
+      const int st_s = is % kStages, st_o = io % kStages;
+      uint64_t* bar_s = live ? &sh.s_full[is & 1] : &sh.dry;
+      uint64_t* bar_k = live ? &sh.k_empty[st_o] : &sh.dry;
+      uint64_t* bar_o = live ? &sh.o_done[io & 1] : &sh.dry;
+      // -------- S GEMM of tile is: B = tile as [N=TN columns][K=16 rows of C], MN-major: 8-row groups 1024 B apart,
+      //          64-column boxes kBoxBytes apart
+      auto issue_s = [&]() {
+        const uint32_t sbase = smem_u32(ring + (size_t)st_s * kStageBytes);
+        const uint32_t dd = tmem + kTmS + (is & 1) * TN;
 #pragma unroll
-          for (int s = 0; s < C / 16; ++s) {
-            // B = tile as [N=TN columns][K=16 rows of C], MN-major: 8-row groups 1024 B apart,
-            // 64-column boxes kBoxBytes apart
-            const uint64_t bd = make_sw128_desc(sbase + s * 2048, kBoxBytes, 1024);
-            tc_mma_ts(dd, tmem + kTmQ + s * 8, bd, kIdescS, s > 0);
-          }
-          tc_commit(bar_s);
-          if (!want_o && live) tc_commit(&sh.k_empty[st]);   // no O GEMM will read this stage
+        for (int s = 0; s < C / 16; ++s) {
+          const uint64_t bd = make_sw128_desc(sbase + s * 2048, kBoxBytes, 1024);
+          tc_mma_ts(dd, tmem + kTmQ + s * 8, bd, kIdescS, s > 0);
         }
-        __syncwarp();
+        tc_commit(bar_s);
+        if (!want_o && live) tc_commit(&sh.k_empty[st_s]);   // no O GEMM will read this stage
+      };
+      // -------- O GEMM of tile io: A = P as [M=128 rows][K=16 columns], B = tile as [N=C rows][K=16 columns]; both K-major:
+      //          rows 128 B apart, 8-row groups 1024 B apart, 16 columns = 32 B inside the swizzled row
+      auto issue_o = [&]() {
+        const uint32_t sbase = smem_u32(ring + (size_t)st_o * kStageBytes);
+        const uint32_t pa = smem_u32(pbuf + (io & 1) * kPBytes);
+#pragma unroll
+        for (int s = 0; s < TN / 16; ++s) {
+          const uint64_t ad = make_sw128_desc(pa + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024);
+          const uint64_t bd = make_sw128_desc(sbase + (s >> 2) * kBoxBytes + (s & 3) * 32, 16, 1024);
+          tc_mma_ss(tmem + kTmO, ad, bd, kIdescO, (io > 0 || s > 0) ? 1u : 0u);
+        }
+        tc_commit(bar_k);
+        tc_commit(bar_o);
+      };
+      if (do_s && live) {
+        if (is >= 2) {
+          mbar_wait(&sh.s_free[is & 1], ((is - 2) >> 1) & 1);
+          tl_stamp(tl, 8 + 8 * is + 5);
+        }
+        mbar_wait(&sh.k_full[st_s], (is / kStages) & 1);
       }
-      if (want_o && (!live || j >= 2)) {
-        // ------------------------------------------------------------------ O GEMM of tile i = j - 2
-        const int i = live ? j - 2 : 0;
-        const int st = i % kStages;
-        if (live) {
-          mbar_wait(&sh.p_full[i & 1], (i >> 1) & 1);
-          tc_fence_after();
-          tl_stamp(tl, 8 + 8 * i + 3);
+      bool merged = false;
+      if (do_s && do_o) {
+        if (RMCL_TC_MERGED_ISSUE == 1 || !live) {
+          if (live) mbar_wait(&sh.p_full[io & 1], (io >> 1) & 1);
+          merged = true;
+        } else if (RMCL_TC_MERGED_ISSUE == 2) {
+          merged = mbar_try_wait(&sh.p_full[io & 1], (io >> 1) & 1);
         }
-        uint64_t* bar_k = live ? &sh.k_empty[st] : &sh.dry;
-        uint64_t* bar_o = live ? &sh.o_done[i & 1] : &sh.dry;
+      }
+      // one code instance of each GEMM's issue sequence (instruction cache): pass 0 issues S (and O when merged), pass 1 the
+      // O GEMM that still had to wait for its P tile
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        const bool s_now = do_s && pass == 0;
+        const bool o_now = do_o && (pass == (merged ? 0 : 1));
+        if (!s_now && !o_now) continue;
+        if (live) {
+          if (o_now && !merged) mbar_wait(&sh.p_full[io & 1], (io >> 1) & 1);
+          tc_fence_after();
+          if (s_now) tl_stamp(tl, 8 + 8 * is + 0);
+          if (o_now) tl_stamp(tl, 8 + 8 * io + 3);
+        }
         if (elect_one()) {
-          const uint32_t sbase = smem_u32(ring + (size_t)st * kStageBytes);
-          const uint32_t pa = smem_u32(pbuf + (i & 1) * kPBytes);
-#pragma unroll
-          for (int s = 0; s < TN / 16; ++s) {
-            // A = P as [M=128 rows][K=16 columns], B = tile as [N=C rows][K=16 columns]; both K-major:
-            // rows 128 B apart, 8-row groups 1024 B apart, 16 columns = 32 B inside the swizzled row
-            const uint64_t ad = make_sw128_desc(pa + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024);
-            const uint64_t bd = make_sw128_desc(sbase + (s >> 2) * kBoxBytes + (s & 3) * 32, 16, 1024);
-            tc_mma_ss(tmem + kTmO, ad, bd, kIdescO, (i > 0 || s > 0) ? 1u : 0u);
-          }
-          tc_commit(bar_k);
-          tc_commit(bar_o);
+          if (s_now) issue_s();
+          if (o_now) issue_o();
         }
         __syncwarp();
       }
