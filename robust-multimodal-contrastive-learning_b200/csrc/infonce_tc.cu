@@ -109,7 +109,8 @@ __device__ __forceinline__ long long global_ns() {
 #define RMCL_TC_TIMELINE 0
 #endif
 // Timing experiments (results are garbage): bit 0 no tcgen05.ld of S, 1 no exponentials, 2 no P stores, 3 no decision
-// handshake — which part of the softmax side slows the tile loop (profiles/r2_tc_experiments.txt)
+// handshake, 4 queue tiles fetched only for the first ring round, 5 no O write-out, 6 no Q^ fetch — which part of the kernel
+// the time goes to (profiles/r2_tc_experiments.txt)
 #ifndef RMCL_TC_EXPERIMENT
 #define RMCL_TC_EXPERIMENT 0
 #endif
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                       long long K, float scale2, long long cols_per_split, int want_argmax, float* __restrict__ pm,
                       float* __restrict__ pl, float* __restrict__ pav, int* __restrict__ pai, __nv_bfloat16* __restrict__ po,
                       long long* __restrict__ timeline, const float* __restrict__ n2, const float* __restrict__ qn2,
-                      float* __restrict__ pdist, const FusedArgs fz) {
+                      float* __restrict__ pdist, const FusedArgs fz, const __nv_bfloat16* __restrict__ queue_raw, long long ldq) {
   constexpr bool want_o = WANT_O;   // compile-time: the with-gradient instantiation is the tuned kernel, untouched
   // want_o == false (no gradient requested: the clean-query argmax call, the greedy attack's candidate losses): the statistics
   // pass only — no P tile, no O GEMM, no partial write-out; ring stages are released by the S GEMM's own commit.
@@ -245,7 +246,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         if (ch < kChunks) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            v[t][j] = FUSED ? __ldcg(reinterpret_cast<const uint4*>(qw + (size_t)(4 * j + (lane >> 3)) * C + ch * 64) + (lane & 7))
+            v[t][j] = (RMCL_TC_EXPERIMENT & 64) ? make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u) :   // experiment bit 6: no Q^ fetch
+                      FUSED ? __ldcg(reinterpret_cast<const uint4*>(qw + (size_t)(4 * j + (lane >> 3)) * C + ch * 64) + (lane & 7))
                             : __ldg(reinterpret_cast<const uint4*>(qw + (size_t)(4 * j + (lane >> 3)) * C + ch * 64) + (lane & 7));
         }
       }
@@ -481,7 +483,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // was bf16 already, so this adds one more 2^-9 relative rounding per split to dq.
     uint8_t* stage = ring + (size_t)r * (2 * C + 16) + par * HC * 2;   // every TMA write has been consumed
 #pragma unroll 1
-    for (int ch = 0; want_o && ch < HC / 32; ++ch) {
+    for (int ch = 0; want_o && !(RMCL_TC_EXPERIMENT & 32) && ch < HC / 32; ++ch) {   // experiment bit 5: no O write-out
       uint32_t o[32];
       tc_ld32(tlane + kTmO + par * HC + ch * 32, o);
       tc_wait_ld();
@@ -495,7 +497,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       for (int j = 0; j < 4; ++j)
         *reinterpret_cast<uint4*>(stage + ch * 64 + 16 * j) = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
     }
-    if (row_ok && want_o) {
+    if (row_ok && want_o && !(RMCL_TC_EXPERIMENT & 32)) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       bulk_store_row(po + ((size_t)split * B + row0 + r) * C + par * HC, stage, HC * 2);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -507,16 +509,38 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     tc_fence_before();
   } else if (warp == kTmaWarp) {
     // ========================================================================= TMA producer
+    // RMCL_TC_L2_PREFETCH: a tile is C rows x 128 bytes, each row in a different DRAM page (row stride = 2K bytes), i.e. the
+    // TMA boxes reach DRAM as 128-byte accesses scattered over C pages.  This CTA's whole share of a queue row is one
+    // contiguous segment of cols_per_split x 2 bytes (1.75 KB at cfg2): ask the L2 for it with one bulk prefetch per row before
+    // the tile loop, so DRAM sees C long bursts instead of C x n_tiles short ones and the boxes then hit in L2.
+    // Measured (profiles/r2_tc_experiments.txt): the flash pass gets SLOWER, 22.0 -> 25.1 us at cfg2 — fetching the tiles is not
+    // what limits the kernel (skipping the fetches altogether gains 0.4 us), and 148 x 256 prefetches land in front of the Q^
+    // fetch and the first tiles.  Off.
+#ifndef RMCL_TC_L2_PREFETCH
+#define RMCL_TC_L2_PREFETCH 0
+#endif
+    if (RMCL_TC_L2_PREFETCH && n_tiles > 1 && queue_raw != nullptr) {
+      const uint32_t bytes = (uint32_t)((k_end - k_begin) * 2);   // K % 8 == 0 and k_begin % TN == 0: multiples of 16
+      for (int row = lane; row < C; row += 32)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(queue_raw + (size_t)row * ldq + k_begin), "r"(bytes) : "memory");
+    }
     for (int i = 0; i < n_tiles; ++i) {
       const int st = i % kStages;
       mbar_wait(&sh.k_empty[st], ((i / kStages) & 1) ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(&sh.k_full[st], kStageBytes);
-        const long long col0 = k_begin + (long long)i * TN;
+#if RMCL_TC_EXPERIMENT & 16   // timing experiment: only the first kStages tiles are fetched, later ones reuse the stale stage
+        if (i >= kStages) {
+          mbar_arrive(&sh.k_full[st]);
+        } else
+#endif
+        {
+          mbar_expect_tx(&sh.k_full[st], kStageBytes);
+          const long long col0 = k_begin + (long long)i * TN;
 #pragma unroll
-        for (int bx = 0; bx < kBoxes; ++bx)
-          tma_load_2d(ring + (size_t)st * kStageBytes + (size_t)bx * kBoxBytes, &tmap_queue, &sh.k_full[st],
-                      (int)(col0 + bx * 64), 0);
+          for (int bx = 0; bx < kBoxes; ++bx)
+            tma_load_2d(ring + (size_t)st * kStageBytes + (size_t)bx * kBoxBytes, &tmap_queue, &sh.k_full[st],
+                        (int)(col0 + bx * 64), 0);
+        }
       }
       __syncwarp();
     }
@@ -586,20 +610,35 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         tc_commit(bar_k);
         tc_commit(bar_o);
       };
-      if (do_s && live) {
-        if (is >= 2) {
-          mbar_wait(&sh.s_free[is & 1], ((is - 2) >> 1) & 1);
-          tl_stamp(tl, 8 + 8 * is + 5);
-        }
-        mbar_wait(&sh.k_full[st_s], (is / kStages) & 1);
-      }
       bool merged = false;
-      if (do_s && do_o) {
-        if (RMCL_TC_MERGED_ISSUE == 1 || !live) {
-          if (live) mbar_wait(&sh.p_full[io & 1], (io >> 1) & 1);
-          merged = true;
-        } else if (RMCL_TC_MERGED_ISSUE == 2) {
-          merged = mbar_try_wait(&sh.p_full[io & 1], (io >> 1) & 1);
+      if (live && do_s && do_o && RMCL_TC_MERGED_ISSUE == 2) {
+        // steady state: the three barriers of a tile are probed TOGETHER (three try_waits in flight, ~one probe latency
+        // instead of three in a row): tcgen05.mma issue blocks while the pipe executes and the pipe runs dry within a few
+        // MMAs once this thread stops feeding it, so whatever the issuer does between two bursts is tensor-pipe idle time
+        const long long t0 = clock64();
+        for (;;) {
+          const uint32_t got = mbar_try_wait3(&sh.s_free[is & 1], ((is - 2) >> 1) & 1, &sh.k_full[st_s], (is / kStages) & 1,
+                                              &sh.p_full[io & 1], (io >> 1) & 1);
+          if ((got & 3u) == 3u) {
+            merged = (got & 4u) != 0u;
+            break;
+          }
+          if (clock64() - t0 > 4000000000ll) __trap();
+        }
+        tl_stamp(tl, 8 + 8 * is + 5);
+      } else {
+        if (do_s && live) {
+          if (is >= 2) {
+            mbar_wait(&sh.s_free[is & 1], ((is - 2) >> 1) & 1);
+            tl_stamp(tl, 8 + 8 * is + 5);
+          }
+          mbar_wait(&sh.k_full[st_s], (is / kStages) & 1);
+        }
+        if (do_s && do_o) {
+          if (RMCL_TC_MERGED_ISSUE == 1 || !live) {
+            if (live) mbar_wait(&sh.p_full[io & 1], (io >> 1) & 1);
+            merged = true;
+          }
         }
       }
       // one code instance of each GEMM's issue sequence (instruction cache): pass 0 issues S (and O when merged), pass 1 the
@@ -692,16 +731,17 @@ int launch_tc(const __nv_bfloat16* q_hat, const void* queue, int B, long long K,
   static const bool coop = [] { const char* e = getenv("RMCL_B200_INFONCE_COOP"); return !(e && e[0] == '0'); }();
   if (FUSED && !coop) {
     kern<<<grid, dim3(kTcThreads), smem, s>>>(tmap, q_hat, B, K, scale2, p.cols_per_split, want_argmax, out.m, out.l, out.av, out.ai,
-                                              reinterpret_cast<__nv_bfloat16*>(out.o), g_tc_timeline, out.n2, out.qn2, out.dist, fz);
+                                              reinterpret_cast<__nv_bfloat16*>(out.o), g_tc_timeline, out.n2, out.qn2, out.dist, fz,
+                                              reinterpret_cast<const __nv_bfloat16*>(queue), ldq);
     RMCL_LAUNCH_OK("infonce_fused_kernel");
   } else if (FUSED)
     RMCL_CUDA_OK(launch_cooperative(kern, grid, dim3(kTcThreads), smem, s, tmap, q_hat, B, K, scale2, p.cols_per_split, want_argmax,
                                     out.m, out.l, out.av, out.ai, reinterpret_cast<__nv_bfloat16*>(out.o), g_tc_timeline, out.n2,
-                                    out.qn2, out.dist, fz));
+                                    out.qn2, out.dist, fz, reinterpret_cast<const __nv_bfloat16*>(queue), ldq));
   else
     RMCL_CUDA_OK(launch_pdl(kern, grid, dim3(kTcThreads), smem, s, tmap, q_hat, B, K, scale2, p.cols_per_split, want_argmax,
                             out.m, out.l, out.av, out.ai, reinterpret_cast<__nv_bfloat16*>(out.o), g_tc_timeline, out.n2,
-                            out.qn2, out.dist, fz));
+                            out.qn2, out.dist, fz, reinterpret_cast<const __nv_bfloat16*>(queue), ldq));
   return RMCL_OK;
 }
 

@@ -218,13 +218,6 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes, 
   asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(p), "r"(bytes), "l"(policy) : "memory");
 }
 
-__device__ __forceinline__ void spin_until(const unsigned int* counter, unsigned int target) {
-  unsigned int v;
-  do {
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-  } while (v < target);
-}
-
 __device__ __forceinline__ unsigned long long ld_word(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -464,10 +457,13 @@ __global__ void __launch_bounds__(kPgdThreads, (sizeof(TD) + sizeof(TG) == 8) ? 
         if (threadIdx.x == 0) {
           const unsigned long long* w = p.words + 2 * (long long)it.sample;
           unsigned long long w0, w1;
-          do {   // both words in flight together: one round trip once the sample's last chunk has published
+          const long long t0 = clock64();
+          for (;;) {   // both words in flight together: one round trip once the sample's last chunk has published
             w0 = ld_word(w);
             w1 = ld_word(w + 1);
-          } while ((w0 >> 32) == 0ull || (w1 >> 32) == 0ull);
+            if ((w0 >> 32) != 0ull && (w1 >> 32) != 0ull) break;
+            if (clock64() - t0 > 4000000000ll) __trap();   // a protocol bug becomes a CUDA error, not a hung GPU
+          }
           s_norm[0] = __uint_as_float((unsigned)w0);
           s_norm[1] = __uint_as_float((unsigned)w1);
         }

@@ -31,6 +31,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Three barriers probed with their try_waits in flight together; bit i of the result = barrier i's phase has completed.
+__device__ __forceinline__ uint32_t mbar_try_wait3(uint64_t* b0, uint32_t p0, uint64_t* b1, uint32_t p1, uint64_t* b2, uint32_t p2) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred pa, pb, pc;\n\t.reg .u32 ra, rb, rc;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 pa, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 pb, [%3], %4;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 pc, [%5], %6;\n\t"
+      "selp.u32 ra, 1, 0, pa;\n\t"
+      "selp.u32 rb, 2, 0, pb;\n\t"
+      "selp.u32 rc, 4, 0, pc;\n\t"
+      "or.b32 ra, ra, rb;\n\t"
+      "or.b32 %0, ra, rc;\n\t}"
+      : "=r"(r)
+      : "r"(smem_u32(b0)), "r"(p0), "r"(smem_u32(b1)), "r"(p1), "r"(smem_u32(b2)), "r"(p2)
+      : "memory");
+  return r;
+}
 // Bounded wait: a protocol bug becomes a trap (CUDA error) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;

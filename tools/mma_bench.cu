@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(128, 1) mma_bench_kernel(Case c, long long* ou
 //   bit 5  ... and the issuer waits for the commit of the S GEMM two tiles back before each S GEMM          (s_full-like dependency)
 __global__ void __launch_bounds__(448, 1) mma_stress_kernel(int mode, int period, int tiles, const uint8_t* gsrc, long long* out) {
   extern __shared__ uint8_t raw[];
-  __shared__ uint64_t bar, lbar, dummy[4], sbar[2];
+  __shared__ uint64_t bar, lbar, dummy[4], sbar[2], done3[3];
+  __shared__ volatile int goflag;
   __shared__ uint32_t tmem_base;
   __shared__ volatile int stop;
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
@@ -134,6 +135,11 @@ __global__ void __launch_bounds__(448, 1) mma_stress_kernel(int mode, int period
     for (int i = 0; i < 4; ++i) mbar_init(&dummy[i], 1);
     mbar_init(&sbar[0], 1);
     mbar_init(&sbar[1], 1);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&done3[i], 1);
+      mbar_arrive(&done3[i]);     // phase 0 complete: a parity-0 wait succeeds at once
+    }
+    goflag = 1;
     stop = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -172,6 +178,36 @@ __global__ void __launch_bounds__(448, 1) mma_stress_kernel(int mode, int period
       for (int g = 0; g < tiles; ++g) {
         const int gg = rep * tiles + g;
         if ((mode & 32) && gg >= 2) mbar_wait(&sbar[gg & 1], ((gg - 2) >> 1) & 1);
+        if (mode & 128) {          // the kernel's issuer between two bursts: probe three (complete) barriers, fence
+          while ((mbar_try_wait3(&done3[0], 0, &done3[1], 0, &done3[2], 0) & 7u) != 7u) {}
+          tc_fence_after();
+        }
+        if (mode & 256) {          // a flag posted by a helper warp instead of the probe
+          int f;
+          do { asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(f) : "r"(smem_u32((const void*)&goflag)) : "memory"); } while (f == 0);
+          tc_fence_after();
+        }
+        if (mode & 512) tc_fence_after();
+        if (mode & 1024) {         // single elect block per tile (merged burst), as the kernel issues it now
+          if (elect_one()) {
+#pragma unroll
+            for (int s = 0; s < 16; ++s) {
+              const uint64_t bd = make_sw128_desc(sbase + 65536 + s * 2048, 32768, 1024);
+              tc_mma_ts(tmem + 384 + (g & 1) * 64, tmem + s * 8, bd, idS, s > 0);
+            }
+            tc_commit(&dummy[0]);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+              const uint64_t ad = make_sw128_desc(sbase + (g & 1) * 16384 + s * 32, 16, 1024);
+              const uint64_t bd = make_sw128_desc(sbase + 65536 + 32768 + s * 32, 16, 1024);
+              tc_mma_ss(tmem + 128, ad, bd, idO, 1);
+            }
+            tc_commit(&dummy[1]);
+            tc_commit(&dummy[2]);
+          }
+          __syncwarp();
+          continue;
+        }
         if (elect_one()) {
 #pragma unroll
           for (int s = 0; s < 16; ++s) {
@@ -308,15 +344,15 @@ int main() {
   cudaFuncSetAttribute(mma_stress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int tiles = 256;
   printf("tile loop (%d tiles, ideal %d cycles) beside the kernel's other traffic, grid 148\n", tiles, tiles * 1024);
-  for (int grid : {1, 148}) for (int period : {1024}) {
-    for (int mode : {0, 64, 32 + 15, 64 + 32 + 15}) {
+  for (int grid : {148}) for (int period : {1024}) {
+    for (int mode : {1024, 1024 + 512, 1024 + 128, 1024 + 256, 1024 + 128 + 15, 1024 + 256 + 15}) {
       long long h[2] = {0, 0};
       mma_stress_kernel<<<grid, 448, smem>>>(mode, period, tiles, gsrc, d);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("stress mode %d: %s\n", mode, cudaGetErrorString(e)); return 1; }
       cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
       printf("  grid %3d burst period %4d  [%s%s%s%s]%*s %7lld cyc = %6.1f per tile -> %.0f %% of the tensor roof\n", grid, period, (mode & 1) || (mode & 8) ? " tcgen05.ld" : "",
-             (mode & 8) ? "+ex2" : "", (mode & 2) ? " P-stores" : "", (mode & 4) ? " bulk-loads" : "", 2, (mode & 64) ? ((mode & 32) ? " commits+dependent wait, RANDOM operands" : " RANDOM operands") : ((mode & 32) ? " commits+dependent wait" : ((mode & 16) ? " commits" : "")), h[0], (double)h[0] / tiles,
+             (mode & 8) ? "+ex2" : "", (mode & 2) ? " P-stores" : "", (mode & 4) ? " bulk-loads" : "", 2, (mode & 1024) ? ((mode & 128) ? " one burst/tile + 3 commits, 3-barrier probe + fence between bursts" : (mode & 256) ? " one burst/tile + 3 commits, flag poll + fence between bursts" : (mode & 512) ? " one burst/tile + 3 commits, fence between bursts" : " one burst/tile + 3 commits") : "", h[0], (double)h[0] / tiles,
              100.0 * tiles * 1024 / h[0]);
     }
   }
