@@ -524,8 +524,16 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       for (int row = lane; row < C; row += 32)
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(queue_raw + (size_t)row * ldq + k_begin), "r"(bytes) : "memory");
     }
+    // RMCL_TC_TILES_BEFORE_Q: the first S GEMM needs Q^ AND tile 0; the ring prefetch (kStages x 32 KB per SM, 24 MB over the
+    // chip) is issued at kernel entry and the Q^ fetch (64 KB per SM, out of L2) then queues behind it on the way into the
+    // SM — measured as 2.6 us of fill that neither more nor fewer Q^ replicas change (profiles/r2_tc_experiments.txt).  Only
+    // this many tiles are requested ahead of Q^; the rest of the ring follows once Q^ is in tensor memory.
+#ifndef RMCL_TC_TILES_BEFORE_Q
+#define RMCL_TC_TILES_BEFORE_Q 2
+#endif
     for (int i = 0; i < n_tiles; ++i) {
       const int st = i % kStages;
+      if (i == RMCL_TC_TILES_BEFORE_Q && i < kStages) mbar_wait(&sh.q_full, 0);
       mbar_wait(&sh.k_empty[st], ((i / kStages) & 1) ^ 1);
       if (elect_one()) {
 #if RMCL_TC_EXPERIMENT & 16   // timing experiment: only the first kStages tiles are fetched, later ones reuse the stale stage

@@ -48,6 +48,10 @@ constexpr int kChunkBytes = kChunkRows * kTN * 2;   // 32 KB
 constexpr float kMargin = 24.f;        // initial reference = first tile's row maximum + 2^24 (see infonce_tc.cu)
 constexpr float kOverflow = 100.f;     // P~ would exceed 2^100 (bf16 tops out at 2^127): flag it
 
+#ifndef RMCL_TC2_Q_FIRST
+#define RMCL_TC2_Q_FIRST 1
+#endif
+
 struct SShared {
   uint64_t k_full[8];
   uint64_t k_empty[8];
@@ -282,6 +286,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     // ===================================================================== TMA producer
     for (int i = 0; i < n_tiles; ++i) {
       const long long col0 = k_begin + (long long)i * kTN;
+      // only tile 0 is requested ahead of Q^: the rest of the ring would otherwise sit in front of the Q^ fetch on the way into
+      // the SM (infonce_tc.cu, RMCL_TC_TILES_BEFORE_Q; the split path's Q^ rows are twice as wide)
+      if (RMCL_TC2_Q_FIRST && i == 1) mbar_wait(&sh.q_full, 0);
       for (int c = 0; c < kChunks; ++c) {
         const int it = i * kChunks + c, st = it % kStages;
         mbar_wait(&sh.k_empty[st], ((it / kStages) & 1) ^ 1);

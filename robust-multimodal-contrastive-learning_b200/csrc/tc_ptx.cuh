@@ -31,14 +31,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Three barriers probed with their try_waits in flight together; bit i of the result = barrier i's phase has completed.
+// Three barriers probed with their waits in flight together; bit i of the result = barrier i's phase has completed.  The
+// first two are try_waits (the caller needs them anyway: a potentially blocking probe is what it wants), the third is a
+// non-blocking test_wait — an optional dependency must not hold the thread (try_wait suspends it until the phase completes
+// or a time limit of thousands of cycles expires: seen in the timeline as the S GEMM of tile 2 waiting for the P tile of a
+// cold tile 0).
 __device__ __forceinline__ uint32_t mbar_try_wait3(uint64_t* b0, uint32_t p0, uint64_t* b1, uint32_t p1, uint64_t* b2, uint32_t p2) {
   uint32_t r;
   asm volatile(
       "{\n\t.reg .pred pa, pb, pc;\n\t.reg .u32 ra, rb, rc;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 pa, [%1], %2;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 pb, [%3], %4;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 pc, [%5], %6;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 pc, [%5], %6;\n\t"
       "selp.u32 ra, 1, 0, pa;\n\t"
       "selp.u32 rb, 2, 0, pb;\n\t"
       "selp.u32 rc, 4, 0, pc;\n\t"
