@@ -91,16 +91,30 @@ int infonce_make_plan(int B, int C, long long K, int queue_dtype, int path, bool
 }
 
 // ------------------------------------------------------------------------------------ prep
+// RMCL_PREP_WARP_ROWS: one WARP per row (shuffles only, a lane keeps its C/32 elements of q and k in flight together) instead
+// of a 128-thread team per row (8 named barriers on the row's critical path).  The whole call waits for this kernel — the
+// flash pass sits in griddepcontrol.wait until it has finished —, so its latency, not its throughput, is what counts.
+// Measured (profiles/r2_tc_experiments.txt): SLOWER — whole call 36.5 us against 33.2 us at cfg2: a lane then runs 8 elements'
+// worth of IEEE divisions and stores in a row where a team thread runs 2.  Off.
+#ifndef RMCL_PREP_WARP_ROWS
+#define RMCL_PREP_WARP_ROWS 0
+#endif
+constexpr int kPrepWarps = 2;   // rows per CTA in the warp-per-row variant (B = 256: 128 CTAs, under one per SM)
+
 template <typename TQ, typename TKK>
-__global__ void __launch_bounds__(128) infonce_prep_kernel(const PrepArgs a, unsigned int* __restrict__ counter) {
+__global__ void __launch_bounds__(128) infonce_prep_kernel(const PrepArgs a, unsigned int* __restrict__ counter, int rows) {
   __shared__ float red[4];
-  const int row = blockIdx.x;
   if (threadIdx.x == 0) pdl_trigger();   // the partial kernel may set itself up while this one runs
-  if (row == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     counter[0] = 0u;
     counter[1] = 0u;   // overflow flag of the two-pass tcgen05 variant
   }
-  prep_row<TQ, TKK>(a, row, red, threadIdx.x, kBarPrep);
+#if RMCL_PREP_WARP_ROWS
+  const int row = blockIdx.x * kPrepWarps + (threadIdx.x >> 5);
+  if (row < rows) prep_row_warp<TQ, TKK>(a, row, threadIdx.x & 31);
+#else
+  prep_row<TQ, TKK>(a, blockIdx.x, red, threadIdx.x, kBarPrep);
+#endif
 }
 
 // -------------------------------------------------------------------------------- finalize
@@ -140,7 +154,11 @@ static PrepArgs make_prep_args(const void* q, const void* k, int B, int C, float
 template <typename TQ, typename TKK>
 static int launch_prep(const PrepArgs& a, char* ws, const InfoNcePlan& p, cudaStream_t s) {
   const int rows = a.q_hat_bf16 ? p.b_pad : a.B;
-  infonce_prep_kernel<TQ, TKK><<<rows, 128, 0, s>>>(a, (unsigned int*)(ws + p.off_counter));
+#if RMCL_PREP_WARP_ROWS
+  infonce_prep_kernel<TQ, TKK><<<(rows + kPrepWarps - 1) / kPrepWarps, 32 * kPrepWarps, 0, s>>>(a, (unsigned int*)(ws + p.off_counter), rows);
+#else
+  infonce_prep_kernel<TQ, TKK><<<rows, 128, 0, s>>>(a, (unsigned int*)(ws + p.off_counter), rows);
+#endif
   RMCL_LAUNCH_OK("infonce_prep_kernel");
   return RMCL_OK;
 }

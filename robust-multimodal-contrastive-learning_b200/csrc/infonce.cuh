@@ -17,12 +17,13 @@
 namespace rmcl {
 
 // The bf16 copy of Q^ is the one operand every CTA of the tcgen05 kernel reads in full at the same
-// moment (148 CTAs x 64 KB out of a 128 KB footprint at cfg2): that is ~6 cache lines per L2 slice,
-// each requested 74 times, and the slice imbalance (not the volume) set the fill time.  prep writes
-// kQhatReplicas copies and CTA `split` reads copy split % kQhatReplicas, which spreads the same traffic
-// over 8x more lines.
+// moment (148 CTAs x 64 KB out of a 128 KB footprint at cfg2).  Round 1 wrote kQhatReplicas = 8 copies (CTA `split` reads
+// copy split % kQhatReplicas) to spread that over more L2 lines.  Measured again in round 2 with 1 / 2 / 8 / 32 / 74 copies
+// (profiles/r2_tc_experiments.txt): the flash pass does not change (20.5-20.6 us at cfg2 for every count — what delayed the
+// fetch was the ring prefetch in front of it, RMCL_TC_TILES_BEFORE_Q), and every extra copy is written by the prep kernel on
+// the critical path of the call (whole call 33.1 us with 1 copy, 33.4 with 8, 39.3 with 74).  One copy.
 #ifndef RMCL_QHAT_REPLICAS
-#define RMCL_QHAT_REPLICAS 8
+#define RMCL_QHAT_REPLICAS 1
 #endif
 constexpr int kQhatReplicas = RMCL_QHAT_REPLICAS;
 
