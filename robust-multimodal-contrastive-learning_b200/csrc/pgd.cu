@@ -48,6 +48,14 @@ namespace rmcl {
 #define RMCL_PGD_MIN_CTAS 5
 #endif
 // independent 16-byte steps per thread in the update phase (2: 4 loads in flight per thread)
+// Timing experiments (results are garbage): bit 0 update items do not wait for the sample totals, 1 norm items publish
+// nothing, 2 the update is not stored, 3 norm items do nothing, 4 update items do nothing (profiles/r2_pgd_experiments.txt)
+#ifndef RMCL_PGD_EXPERIMENT
+#define RMCL_PGD_EXPERIMENT 0
+#endif
+#ifndef RMCL_PGD_P1_UNROLL
+#define RMCL_PGD_P1_UNROLL 4
+#endif
 #ifndef RMCL_PGD_PRELOAD
 #define RMCL_PGD_PRELOAD 1
 #endif
@@ -328,7 +336,8 @@ __global__ void __launch_bounds__(kPgdThreads, (sizeof(TD) + sizeof(TG) == 8) ? 
     if (threadIdx.x == 0) {
       t_next = (long long)atomicAdd(p.ticket, 1u);
 #if RMCL_PGD_L2_PREFETCH
-      if (vec && p.phases == 1 && t_next < p.total_items) {     // single-phase (sign) mode only, see above
+      // 1: the single-phase (sign) mode only, see above; 2: also the NORM items of the two-phase modes (not their update items)
+      if (vec && t_next < p.total_items && (p.phases == 1 || RMCL_PGD_L2_PREFETCH >= 2)) {
         const PgdItem nx = pgd_decode(p, t_next);
         const long long ne0 = (long long)nx.chunk * p.chunk_elems;
         long long nn = p.N - ne0;
@@ -338,7 +347,7 @@ __global__ void __launch_bounds__(kPgdThreads, (sizeof(TD) + sizeof(TG) == 8) ? 
         if (nx.phase == 0) {            // norm item: g comes from DRAM (and delta too under the L2 projection); both are re-read later
           l2_prefetch_bulk(ng, (unsigned)(nn * sizeof(TG)), keep);
           if (l2proj) l2_prefetch_bulk(nd, (unsigned)(nn * sizeof(TD)), keep);
-        } else if (!l2proj) {           // update item: g is L2-resident already, delta comes from DRAM, used once
+        } else if (!l2proj && p.phases == 1) {   // update item: g is L2-resident already, delta comes from DRAM, used once
           l2_prefetch_bulk(nd, (unsigned)(nn * sizeof(TD)), stream);
         }
       }
@@ -351,6 +360,12 @@ __global__ void __launch_bounds__(kPgdThreads, (sizeof(TD) + sizeof(TG) == 8) ? 
     const TG* g = grad + (long long)it.sample * p.N + e0;
     TD* d = delta + (long long)it.sample * p.N + e0;
 
+#if RMCL_PGD_EXPERIMENT & 8    // timing experiment: norm items do nothing (update items then read everything from DRAM)
+    if (it.phase == 0) continue;
+#endif
+#if RMCL_PGD_EXPERIMENT & 16   // timing experiment: update items do nothing
+    if (it.phase != 0) continue;
+#endif
     if (it.phase == 0) {
       // ------------------------------------------------------------ P1: partial norm(s) of the chunk
       float acc = 0.f, adg = 0.f, add = 0.f;
@@ -358,12 +373,13 @@ __global__ void __launch_bounds__(kPgdThreads, (sizeof(TD) + sizeof(TG) == 8) ? 
         const uint4* gv = reinterpret_cast<const uint4*>(g);
         const long long nv = n / VG;
         long long i = threadIdx.x;
-        for (; i + 3 * kPgdThreads < nv; i += 4 * kPgdThreads) {
-          uint4 u[4];
+        constexpr int kU = RMCL_PGD_P1_UNROLL;   // independent 16-byte loads in flight per thread in the norm phase
+        for (; i + (kU - 1) * kPgdThreads < nv; i += kU * kPgdThreads) {
+          uint4 u[kU];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) u[k] = ld_u4_hint(gv + i + k * kPgdThreads, keep);
+          for (int k = 0; k < kU; ++k) u[k] = ld_u4_hint(gv + i + k * kPgdThreads, keep);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < kU; ++k) {
             const TG* e = reinterpret_cast<const TG*>(&u[k]);
 #pragma unroll
             for (int j = 0; j < VG; ++j) {
@@ -433,7 +449,11 @@ __global__ void __launch_bounds__(kPgdThreads, (sizeof(TD) + sizeof(TG) == 8) ? 
         adg = block_reduce(adg, false, red);
         add = block_reduce(add, false, red);
       }
+#if RMCL_PGD_EXPERIMENT & 2     // timing experiment: partials are not published (no global writes, no atomic)
+      if (acc == 123.456f && adg == 1.f && add == 2.f) pgd_publish_partials(p, it, acc, adg, add, is_max, red);
+#else
       pgd_publish_partials(p, it, acc, adg, add, is_max, red);
+#endif
     } else {
       // ------------------------------------------------------------ P2: the update
       float denom = 1.f, proj = 1.f;
@@ -453,7 +473,7 @@ __global__ void __launch_bounds__(kPgdThreads, (sizeof(TD) + sizeof(TG) == 8) ? 
           for (int q = 0; q < VE / VD; ++q) pd[h][q] = ld_u4_hint(reinterpret_cast<const uint4*>(d + base) + q, stream);
         }
       }
-      if (p.mode != RMCL_PGD_SIGN_LINF) {
+      if (p.mode != RMCL_PGD_SIGN_LINF && !(RMCL_PGD_EXPERIMENT & 1)) {   // experiment bit 0: no wait for the totals
         if (threadIdx.x == 0) {
           const unsigned long long* w = p.words + 2 * (long long)it.sample;
           unsigned long long w0, w1;
@@ -515,7 +535,11 @@ __global__ void __launch_bounds__(kPgdThreads, (sizeof(TD) + sizeof(TG) == 8) ? 
                 if (l2proj && proj < 1.f) v = __fmul_rn(v, proj);
                 e[j] = from_f32<TD>(v);
               }
+#if RMCL_PGD_EXPERIMENT & 4     // timing experiment: the update is not stored
+              if (u.x == 0x12345678u && u.y == 0x9abcdef0u) st_u4_hint(reinterpret_cast<uint4*>(d + base) + q, u, stream);
+#else
               st_u4_hint(reinterpret_cast<uint4*>(d + base) + q, u, stream);
+#endif
             }
           }
         }

@@ -6,13 +6,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "robust-multimodal-contrastive-learning_b200")
 VARIANTS = {
     "base": [],
-    "nopre": ["-DRMCL_PGD_PRELOAD=0"],
-    "cta4": ["-DRMCL_PGD_MIN_CTAS=4"],
-    "cta6": ["-DRMCL_PGD_MIN_CTAS=6"],
-    "u3_cta4": ["-DRMCL_PGD_UPDATE_UNROLL=3", "-DRMCL_PGD_MIN_CTAS=4"],
-    "u1_cta6": ["-DRMCL_PGD_UPDATE_UNROLL=1", "-DRMCL_PGD_MIN_CTAS=6"],
-    "b16": ["-DRMCL_PGD_BATCH_MB=16", "-DRMCL_PGD_BATCH_MB_L2=32"],
-    "b32": ["-DRMCL_PGD_BATCH_MB=32", "-DRMCL_PGD_BATCH_MB_L2=56"],
+    "pf2": ["-DRMCL_PGD_L2_PREFETCH=2"],
+    "u8": ["-DRMCL_PGD_P1_UNROLL=8"],
+    "u8_cta4": ["-DRMCL_PGD_P1_UNROLL=8", "-DRMCL_PGD_MIN_CTAS=4"],
+    "pf2_u8": ["-DRMCL_PGD_L2_PREFETCH=2", "-DRMCL_PGD_P1_UNROLL=8"],
+    "pf2_norm_only": ["-DRMCL_PGD_L2_PREFETCH=2", "-DRMCL_PGD_EXPERIMENT=18"],
+    "u8_norm_only": ["-DRMCL_PGD_P1_UNROLL=8", "-DRMCL_PGD_EXPERIMENT=18"],
 }
 if "--build" in sys.argv:
     sys.path.insert(0, os.path.join(PKG, "csrc"))
