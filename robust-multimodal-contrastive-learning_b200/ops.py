@@ -145,6 +145,7 @@ def _split_ok(queue):
 DIAG_NAMES = ("pos_dist", "pos_cosine", "pos_dot", "neg_dist", "neg_cosine", "neg_dot")
 _OUT_ORDER = ("loss", "loss_per_row", "lse", "pos", "argmax", "dq", "dk", "k_hat")          # csrc/torch_ext.cpp
 _WANT_BITS = {name: 1 << i for i, name in enumerate(_OUT_ORDER)}
+_WANT_PLANS = {}   # want tuple -> (output mask, ((index, name), ...))
 
 
 class QueueStats:
@@ -198,12 +199,20 @@ def infonce_fwd_bwd(q, k, queue, temperature, *, loss_scale=1.0, normalize_k=Fal
         raise _lib.RmclError("tcgen05 InfoNCE on an fp32 queue needs C in {64,128,256}, K % 8 == 0 and a 16-byte aligned, "
                              f"contiguous-row queue (got C={queue.shape[0]} K={queue.shape[1]})")
     if _lib.ffi() == "torch":
-        mask = sum(bit for name, bit in _WANT_BITS.items() if name in want)
+        # host time matters here (the whole op is ~22 us of GPU time at the cfg4 shape): the output mask and the index list of
+        # a ``want`` tuple are computed once
+        plan = _WANT_PLANS.get(want) if isinstance(want, tuple) else None
+        if plan is None:
+            plan = (sum(bit for name, bit in _WANT_BITS.items() if name in want),
+                    tuple((i, name) for i, name in enumerate(_OUT_ORDER) if name in want))
+            if isinstance(want, tuple):
+                _WANT_PLANS[want] = plan
+        mask, picks = plan
         r = _lib.torch_ops().infonce_fwd_bwd(        # detached: this op is not differentiable (the loss op is infonce_loss)
             q.detach(), k.detach(), queue, float(temperature), float(loss_scale), bool(normalize_k), bool(need_grad), _lib.INFONCE_PATHS[path],
             None if diag is None else diag.colnorm2, None if diag is None else diag.sum_vec,
             None if diag is None else diag.sum_unit, 1e-6 if diag is None else diag.cos_eps, mask, bool(_partial_only))
-        out = {name: r[i] for i, name in enumerate(_OUT_ORDER) if name in want and r[i].numel() > 0}
+        out = {name: r[i] for i, name in picks if r[i].numel() > 0}
         if "loss" in out:
             out["loss"] = out["loss"].reshape(())
         if diag is not None:
