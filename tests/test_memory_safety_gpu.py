@@ -223,3 +223,39 @@ def test_ema_stays_inside_its_buffers(L, dtype):
         assert torch.equal(q, before), "a query parameter was modified"
     for k, before in zip(ks, k0):
         assert bool(torch.isfinite(k.float()).all()) and not torch.equal(k, before)
+
+
+# ------------------------------------------------------------------------------------------------ Barlow-Twins
+@pytest.mark.parametrize("Bg,D,path,b0,Bl", [(96, 1024, 2, 0, 96), (128, 8192, 2, 32, 64), (200, 512, 1, 0, 200), (128, 1024, 1, 64, 64)],
+                         ids=["gram96", "gram128x8192-rows32..96", "direct200", "direct128-rows64..128"])
+def test_barlow_stays_inside_its_buffers_and_is_deterministic(L, Bg, D, path, b0, Bl):
+    def run():
+        gen = torch.Generator(device=DEV).manual_seed(Bg + D)
+        a = Arena(96 << 20)
+        k = a.take((Bg, D), torch.float32, torch.randn(Bg, D, generator=gen, device=DEV))
+        q = a.take((Bg, D), torch.float32, 0.7 * k + 0.7 * torch.randn(Bg, D, generator=gen, device=DEV))
+        on, off, loss = (a.take((1,), torch.float32) for _ in range(3))
+        dq = a.take((Bl, D), torch.float32)
+        cdiag = a.take((D,), torch.float32)
+        nws = L.rmcl_barlow_workspace_bytes(Bg, D)
+        assert nws > 0, L.rmcl_last_error()
+        ws = a.take_bytes(nws, zero=False)      # this workspace needs no initialisation: poison is as good as anything
+        snap = (q.clone(), k.clone())
+        rc = L.rmcl_barlow_fwd_bwd(P(q), F32, P(k), F32, Bg, D, b0, Bl, 1.0 / Bg, 0.0051, 1.0, 0.0051, 1.0, path, P(on), P(off),
+                                   P(loss), P(dq), P(cdiag), P(ws), nws, _stream())
+        assert rc == 0, L.rmcl_last_error()
+        a.check()
+        assert torch.equal(snap[0], q) and torch.equal(snap[1], k), "an input was modified"
+        out = torch.cat([on, off, loss, dq.flatten(), cdiag]).clone()
+        assert bool(torch.isfinite(out).all())
+        return out
+
+    ref = run()
+    side = torch.cuda.Stream()
+    for rep in range(5):
+        if rep % 2:
+            with torch.cuda.stream(side):
+                out = run()
+        else:
+            out = run()
+        assert torch.equal(ref, out), f"run {rep} differs between identical runs"
