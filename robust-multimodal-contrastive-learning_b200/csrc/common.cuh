@@ -80,6 +80,17 @@ __device__ __forceinline__ void st_stream_u4(void* p, const uint4& v) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Every kernel of the step is launched with the programmatic-dependent-launch attribute and starts with pdl_wait(): its
+// launch is processed while the kernel in front of it still runs, and it touches nothing before that kernel has completed
+// (cfg2 step 256.7 -> 250.5 us).  RMCL_PDL_EARLY_TRIGGER bits say which kernels ALSO let their successor's CTAs become
+// resident before they end: 1 the EMA, from each CTA's last chunk on — the InfoNCE prep and flash kernels then set up (TMEM,
+// barriers, the first queue tiles) in the slots the EMA's tail frees: 250.5 -> 239.5 us per step, 3480 -> 3590 steps/s end
+// to end; 2 the enqueue and 4 the finalize kernel at entry — neutral alone, harmful together (263 us: the next step's EMA
+// grid then becomes resident and idles beside the finalize kernel).  profiles/r2_pdl_experiments.txt.
+#ifndef RMCL_PDL_EARLY_TRIGGER
+#define RMCL_PDL_EARLY_TRIGGER 1
+#endif
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                               Args... args) {

@@ -66,7 +66,14 @@ template <typename T>
 __global__ void __launch_bounds__(kEmaThreads) ema_multi_kernel(const rmcl_ema_chunk* __restrict__ chunks,
                                                                 long long n_chunks, float mf, float omf) {
   using V = EmaVec<T>;
+  // launched with the programmatic-dependent-launch attribute: the launch itself is processed while the previous kernel
+  // of the stream still runs, and nothing is touched before that kernel has completed
+  pdl_wait();
   for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+#if RMCL_PDL_EARLY_TRIGGER & 1
+    // last chunk of this CTA: the next kernel's CTAs may take the slots the tail of this grid frees (they wait for its end)
+    if (c + gridDim.x >= n_chunks && threadIdx.x == 0) pdl_trigger();
+#endif
     const rmcl_ema_chunk ch = chunks[c];
     T* __restrict__ kp = reinterpret_cast<T*>(ch.k);
     const T* __restrict__ qp = reinterpret_cast<const T*>(ch.q);
@@ -139,9 +146,10 @@ extern "C" int rmcl_ema_multi(const rmcl_ema_chunk* chunks_dev, int64_t n_chunks
   if (grid > n_chunks) grid = n_chunks;
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == RMCL_F32)
-    rmcl::ema_multi_kernel<float><<<(unsigned)grid, rmcl::kEmaThreads, 0, s>>>(chunks_dev, n_chunks, mf, omf);
+    RMCL_CUDA_OK(rmcl::launch_pdl(rmcl::ema_multi_kernel<float>, dim3((unsigned)grid), dim3(rmcl::kEmaThreads), 0, s, chunks_dev,
+                                  (long long)n_chunks, mf, omf));
   else
-    rmcl::ema_multi_kernel<__nv_bfloat16><<<(unsigned)grid, rmcl::kEmaThreads, 0, s>>>(chunks_dev, n_chunks, mf, omf);
-  RMCL_LAUNCH_OK("ema_multi_kernel");
+    RMCL_CUDA_OK(rmcl::launch_pdl(rmcl::ema_multi_kernel<__nv_bfloat16>, dim3((unsigned)grid), dim3(rmcl::kEmaThreads), 0, s,
+                                  chunks_dev, (long long)n_chunks, mf, omf));
   return RMCL_OK;
 }

@@ -60,6 +60,10 @@ __global__ void __launch_bounds__(256) enqueue_kernel(TQ* __restrict__ queue, co
   __shared__ long long s_ptr;
   unsigned int* ptr_words = reinterpret_cast<unsigned int*>(ptr_dev);
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#if RMCL_PDL_EARLY_TRIGGER & 2
+  if (threadIdx.x == 0) pdl_trigger();   // a tiny grid: whatever follows may queue up behind it right away
+#endif
+  pdl_wait();   // programmatic dependent launch: the keys come from the kernel in front of this one
   if (threadIdx.x == 0) s_ptr = (long long)(*reinterpret_cast<volatile unsigned int*>(ptr_words));
   const int b0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
 #pragma unroll
@@ -110,14 +114,17 @@ static int enqueue_impl(void* queue, rmcl_dtype queue_dtype, const void* keys, r
   using bf16 = __nv_bfloat16;
   bf16* sh = reinterpret_cast<bf16*>(shadow);
   if (keys_dtype == RMCL_F32 && queue_dtype == RMCL_F32)
-    rmcl::enqueue_kernel<float, float><<<grid, 256, 0, s>>>((float*)queue, (const float*)keys, p, B, C, K, ldq, sh, lds, planes);
+    RMCL_CUDA_OK(rmcl::launch_pdl(rmcl::enqueue_kernel<float, float>, grid, dim3(256), 0, s, (float*)queue, (const float*)keys, p, B, C, (long long)K, (long long)ldq, sh,
+                                  (long long)lds, planes));
   else if (keys_dtype == RMCL_F32 && queue_dtype == RMCL_BF16)
-    rmcl::enqueue_kernel<float, bf16><<<grid, 256, 0, s>>>((bf16*)queue, (const float*)keys, p, B, C, K, ldq, sh, lds, planes);
+    RMCL_CUDA_OK(rmcl::launch_pdl(rmcl::enqueue_kernel<float, bf16>, grid, dim3(256), 0, s, (bf16*)queue, (const float*)keys, p, B, C, (long long)K, (long long)ldq, sh,
+                                  (long long)lds, planes));
   else if (keys_dtype == RMCL_BF16 && queue_dtype == RMCL_F32)
-    rmcl::enqueue_kernel<bf16, float><<<grid, 256, 0, s>>>((float*)queue, (const bf16*)keys, p, B, C, K, ldq, sh, lds, planes);
+    RMCL_CUDA_OK(rmcl::launch_pdl(rmcl::enqueue_kernel<bf16, float>, grid, dim3(256), 0, s, (float*)queue, (const bf16*)keys, p, B, C, (long long)K, (long long)ldq, sh,
+                                  (long long)lds, planes));
   else
-    rmcl::enqueue_kernel<bf16, bf16><<<grid, 256, 0, s>>>((bf16*)queue, (const bf16*)keys, p, B, C, K, ldq, sh, lds, planes);
-  RMCL_LAUNCH_OK("enqueue_kernel");
+    RMCL_CUDA_OK(rmcl::launch_pdl(rmcl::enqueue_kernel<bf16, bf16>, grid, dim3(256), 0, s, (bf16*)queue, (const bf16*)keys, p, B, C, (long long)K, (long long)ldq, sh,
+                                  (long long)lds, planes));
   return RMCL_OK;
 }
 

@@ -105,6 +105,7 @@ template <typename TQ, typename TKK>
 __global__ void __launch_bounds__(128) infonce_prep_kernel(const PrepArgs a, unsigned int* __restrict__ counter, int rows) {
   __shared__ float red[4];
   if (threadIdx.x == 0) pdl_trigger();   // the partial kernel may set itself up while this one runs
+  pdl_wait();                            // itself launched ahead of the end of the kernel in front of it (q, k come from there)
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     counter[0] = 0u;
     counter[1] = 0u;   // overflow flag of the two-pass tcgen05 variant
@@ -125,6 +126,9 @@ template <typename TP>
 __global__ void __launch_bounds__(kFinThreads, 2) infonce_finalize_kernel(const FinArgs a) {
   extern __shared__ float fin_smem[];
   __shared__ FinShared fs;
+#if RMCL_PDL_EARLY_TRIGGER & 4
+  if (threadIdx.x == 0) pdl_trigger();        // the enqueue behind this kernel may queue up
+#endif
   pdl_wait();                                 // launched early (PDL): the partials must be complete
   finalize_row<TP, kFinThreads>(a, blockIdx.x, fin_smem, &fs, threadIdx.x, kBarFin);
 }
@@ -157,9 +161,8 @@ static int launch_prep(const PrepArgs& a, char* ws, const InfoNcePlan& p, cudaSt
 #if RMCL_PREP_WARP_ROWS
   infonce_prep_kernel<TQ, TKK><<<(rows + kPrepWarps - 1) / kPrepWarps, 32 * kPrepWarps, 0, s>>>(a, (unsigned int*)(ws + p.off_counter), rows);
 #else
-  infonce_prep_kernel<TQ, TKK><<<rows, 128, 0, s>>>(a, (unsigned int*)(ws + p.off_counter), rows);
+  RMCL_CUDA_OK(launch_pdl(infonce_prep_kernel<TQ, TKK>, dim3(rows), dim3(128), 0, s, a, (unsigned int*)(ws + p.off_counter), rows));
 #endif
-  RMCL_LAUNCH_OK("infonce_prep_kernel");
   return RMCL_OK;
 }
 
